@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200:  exact top-100 cosine queries/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg1|cfg3shard|cfg0]
+
+A "step" is one pass of the hot path (rvo_search_topk: normalise queries -> threshold seeding -> fused tcgen05
+scan/select -> exact top-k -> fp32 re-score) over one synthetic query batch.
+
+  N = 1   workload cfg1 = BASELINE.json configs[1]: 1M x 1024 bf16 DB, 256-query batch, top-100 (the metric's own
+          100M x 1280 DB does not fit one GPU, so the largest single-GPU search configuration is used).
+  N > 1   the SAME total DB row-sharded over the N ranks (strong scaling): every rank scans its shard, ONE NCCL
+          all-gather of the packed per-shard lists, K3 merge on every rank.  Launch with torchrun (one rank per GPU).
+
+Printed JSON (rank 0, one line): value = queries/s with inputs resident in HBM; e2e = the same through the public
+`B200VectorDB.search_batch` with HOST buffers (H2D of the queries and D2H of ids/scores/counts inside the timed
+region); roofline = the dominant kernel (full-DB scan) against MEASURED_PEAKS.json; cpu_baseline = the CPU oracle
+(numpy port of the reference's qdrant-local search) timed on this box's host cores on a bounded query sample.
+
+`--impl reference` times that CPU implementation alone (numpy-only process; the reference's own dependency
+qdrant-client is not installable here, so kind="port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (rows, dim, queries, k, description)
+    "cfg0": (10_000, 1024, 1, 10, "configs[0]: 10k x 1024, single query, top-10"),
+    "cfg1": (1_000_000, 1024, 256, 100, "configs[1]: 1M x 1024 bf16 DB, 256-query batch, top-100, fp32 rescore"),
+    "cfg3shard": (12_500_000, 1280, 4096, 100, "configs[3] per-GPU shard: 12.5M x 1280 bf16, 4096-query batch, top-100"),
+    "cfg3small": (12_500_000, 1280, 16, 100, "configs[3] per-GPU shard, bandwidth regime: 12.5M x 1280, 16 queries"),
+}
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return d, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the CPU implementation of the path (numpy-only process)
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from oracle import reverso_oracle as O
+    n, d, nq, k, desc = WORKLOADS[args.workload]
+    t0 = time.perf_counter()
+    rng = np.random.default_rng(1000)
+    db = np.empty((n, d), dtype=np.float32)
+    step = 1 << 16
+    for lo in range(0, n, step):
+        blk = rng.standard_normal((min(step, n - lo), d), dtype=np.float32)
+        blk /= np.linalg.norm(blk, axis=1, keepdims=True)
+        db[lo: lo + len(blk)] = O.round_to_bf16_inplace(blk)          # the same bf16-valued DB the GPU searches
+    gen_s = time.perf_counter() - t0
+    # bounded sample: calibrate on one query, then size the per-step query sample so that the whole
+    # --steps/--warmup run stays near `--cpu-budget` seconds of CPU work
+    q1 = rng.standard_normal((1, d), dtype=np.float32)
+    O.search_batch(db, q1, k, None, db_is_normalized=True)
+    t = time.perf_counter()
+    O.search_batch(db, q1, k, None, db_is_normalized=True)
+    t_q = time.perf_counter() - t
+    sample_q = int(args.cpu_budget / max(t_q * (args.steps + args.warmup), 1e-9))
+    sample_q = max(1, min(nq, args.sample_queries, sample_q))
+    q = rng.standard_normal((sample_q, d), dtype=np.float32)
+
+    def one_step():
+        # exactly how the reference issues queries: one search() per query (core_system.py:657-664)
+        return O.search_batch(db, q, k, None, db_is_normalized=True)
+
+    for _ in range(args.warmup):
+        one_step()
+    times = []
+    for _ in range(args.steps):
+        t = time.perf_counter()
+        one_step()
+        times.append(time.perf_counter() - t)
+    total = sum(times)
+    qps = sample_q * args.steps / total
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "exact top-%d cosine queries/s" % k, "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "rows": n, "dim": d, "queries": nq, "k": k},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_q} of {nq} queries per step against the full {n}x{d} fp32 DB, one numpy "
+                                   f"gemv + full argsort per query (qdrant-local semantics), median step "
+                                   f"{1e3 * statistics.median(times):.1f} ms, DB generation {gen_s:.1f} s untimed"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML), runs during the timed regions
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                util = self.nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((mhz, util))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=1)
+        if not self.samples:
+            return None
+        loaded = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from revers_o_b200 import _lib, ops, synth
+    from revers_o_b200.sharded import ShardedIndex, shard_bounds
+    from revers_o_b200.vector_db import B200VectorDB, models
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torchrun", file=sys.stderr)
+
+    n, d, nq, k, desc = WORKLOADS[args.workload]
+    lo, hi = shard_bounds(n, world, rank)
+    n_local = hi - lo
+    q_dev = synth.make_queries(nq, d, seed=7, device=dev)
+    db = synth.make_db(n_local, d, q_dev, n_plant=max(1, 128 // world), seed=1000 + rank, device=dev)
+    index = ShardedIndex(db, n_local, d, lo)
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return index.search(q_dev, k)
+
+    # ---- value: inputs resident in HBM --------------------------------------------------------------
+    sampler = ClockSampler(local)
+    for _ in range(max(3, args.warmup)):
+        out = step_resident()
+    barrier()
+    sampler.start()
+    l0 = _lib.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_resident()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.kernel_launch_count() - l0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = nq / (ms_step / 1e3)
+    counts_ok = bool((out[2] == k).all().item())
+
+    # ---- roofline: the dominant kernel (full-shard scan), CUDA events around that one launch ---------
+    _lib.set_option("time_scan", 1)
+    scan_ms = []
+    for _ in range(max(5, min(args.steps, 30))):
+        index.search_local(q_dev, k)
+        scan_ms.append(float(lib.rvo_last_scan_ms()))
+    _lib.set_option("time_scan", 0)
+    torch.cuda.synchronize()
+    scan_avg = statistics.mean(scan_ms)
+    peaks, peaks_kind = load_peaks()
+    alg_bytes = n_local * d * 2
+    alg_flops = 2.0 * nq * n_local * d
+    hbm_ach = alg_bytes / (scan_avg * 1e-3) / 1e9
+    tf_ach = alg_flops / (scan_avg * 1e-3) / 1e12
+    small = nq <= _lib.RVO_SMALL_Q
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": hbm_ach / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peaks_kind,
+                "kernel": "scan_small_kernel" if small else "scan_tc_kernel<FILTER> (full-DB level)",
+                "kernel_ms": scan_avg, "algorithmic_bytes": alg_bytes,
+                "share_of_step": scan_avg / ms_step}
+    roofline_tensor = None if small else {
+        "bound": "tensor", "achieved": tf_ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": tf_ach / peaks["bf16_tflops"], "peak_kind": peaks_kind + " burst (kernel timed alone)",
+        "algorithmic_flops": alg_flops}
+
+    # ---- e2e: public API with HOST buffers (N=1: B200VectorDB.search_batch; N>1: H2D + sharded search + D2H) --
+    q_host = q_dev.cpu().numpy()
+    h2d = q_host.nbytes
+    d2h = nq * k * 12 + nq * 4
+    if world == 1:
+        vdb = B200VectorDB(device=dev)
+        vdb.recreate_collection("bench", vectors_config=models.VectorParams(size=d, distance=models.Distance.COSINE))
+        c = vdb._coll("bench")
+        c.vectors, c.n = db, n_local            # adopt the resident shard (ids/payload tables are not on the hot path)
+
+        def step_e2e():
+            return vdb.search_batch("bench", q_host, k)
+    else:
+        pin_q = torch.from_numpy(q_host).pin_memory()
+        qd = torch.empty_like(q_dev)
+        pi = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+        ps = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+        pc = torch.empty((nq,), dtype=torch.int32).pin_memory()
+
+        def step_e2e():
+            qd.copy_(pin_q, non_blocking=True)
+            a, b, c_ = index.search(qd, k)
+            pi.copy_(a, non_blocking=True); ps.copy_(b, non_blocking=True); pc.copy_(c_, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return pi, ps, pc
+    for _ in range(max(3, args.warmup)):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        r = step_e2e()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.steps
+    clocks = sampler.stop()
+
+    # ---- cpu baseline (rank 0, N=1): the oracle port in a numpy-only subprocess, bounded sample ----------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+                   "--steps", "3", "--warmup", "1", "--sample-queries", str(args.sample_queries)]
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            cpu = json.loads(p.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:  # the GPU numbers stand on their own
+            cpu = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": "exact top-%d cosine queries/s" % k, "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "rows": n, "dim": d, "queries": nq, "k": k, "rows_per_gpu": n_local,
+                       "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+                       "l2": f"inputs larger than L2: each step streams the {alg_bytes / 1e9:.2f} GB shard",
+                       "path": "small-q fp32 scan" if small else "tcgen05 scan + fused threshold select + fp32 rescore"},
+            "e2e": {"value": nq / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "api": "B200VectorDB.search_batch(host numpy)" if world == 1 else "pinned H2D + ShardedIndex.search + D2H"},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_tensor": roofline_tensor, "cpu_baseline": cpu, "clocks": clocks,
+            "results_ok": counts_ok,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
+    ap.add_argument("--sample-queries", type=int, default=8, help="queries per CPU step (bounded sample)")
+    ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,160 @@
+/*
+ * revers_o_b200.h — C ABI of the B200-native region-similarity hot path of kolenyo2099/revers-o.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own
+ * (it is pure Python); every entry point below names the reference call site whose arithmetic it
+ * replaces.  A reference-side maintainer binds these with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every pointer marked [dev] is a device pointer of ONE GPU; the library derives the device
+ *     from the first device pointer of the call, makes it current, and borrows the pointers only
+ *     for the duration of the call (it never frees or retains them);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it and the call returns without synchronising unless stated;
+ *   - return value: 0 = ok, negative = error (see RVO_E_*); `rvo_last_error()` gives the text of the
+ *     last error on the calling thread.  Python maps errors to the reference's status-string
+ *     convention (core_system.py:93-119,652-666); nothing raises into Gradio.
+ *   - there is NO CPU fallback: without a Blackwell (sm_100) device every compute entry fails.
+ */
+#ifndef REVERS_O_B200_H
+#define REVERS_O_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVO_OK               0
+#define RVO_E_INVALID      (-1)  /* bad argument (null pointer, unsupported size, misalignment)      */
+#define RVO_E_CUDA         (-2)  /* a CUDA runtime/driver call failed                                */
+#define RVO_E_NO_DEVICE    (-3)  /* no sm_100 device / driver entry point missing                    */
+#define RVO_E_WORKSPACE    (-4)  /* workspace too small (call rvo_*_workspace_bytes)                 */
+
+/* Limits of the fused search path. */
+#define RVO_MAX_K          512   /* largest `limit` served by rvo_search_topk                        */
+#define RVO_SMALL_Q        4     /* batches of <= RVO_SMALL_Q queries take the exact fp32 scan       */
+
+/* Library / ABI version (major*10000 + minor*100 + patch). */
+int rvo_version(void);
+
+/* Text of the last error raised on this thread ("" if none). */
+const char* rvo_last_error(void);
+
+/* Number of SMs of the device that owns `dev_ptr` (148 on B200); <0 on error. */
+int rvo_device_sm_count(const void* dev_ptr);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ingest: L2-normalise float32 rows and store them as bf16 DB rows.
+ * Replaces: qdrant-local upsert into a COSINE collection (vector normalised, appended to the
+ *           collection matrix) behind core_system.py:608-621, and the `e / e.norm()` of
+ *           core_system.py:407,447 when called with out_f32.
+ *   src      [dev] float32 [n, d], row pitch src_ld elements
+ *   dst_bf16 [dev] bf16    [n, d_pad] row pitch dst_ld elements (dst_ld % 8 == 0, >= d); columns
+ *            d..dst_ld-1 are written as zero.  May be NULL.
+ *   dst_f32  [dev] float32 [n, d] row pitch d: the normalised rows in float32.  May be NULL.
+ * A zero row stays zero (qdrant divides by eps; the reference never stores one, see
+ * core_system.py:402-404).
+ * ---------------------------------------------------------------------------------------------- */
+int rvo_normalize_rows(const float* src, int64_t n, int32_t d, int64_t src_ld,
+                       uint16_t* dst_bf16, int64_t dst_ld, float* dst_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 — segmented mask pooling + L2 normalise.
+ * Replaces: the per-region python loop of core_system.py:363-408 (binarise :398-400, skip empty
+ *           :402-404, region embedding + normalise :406-408) with the mask-pooled definition the
+ *           reference states (main.py:8-9): e_m = mean of patch features under mask m, then L2.
+ *   feats   [dev] bf16  [B, P, D]   patch-feature map, D contiguous (D % 8 == 0)
+ *   masks   [dev] uint8 [B, M, P]   nonzero = patch p belongs to region m
+ *   max_regions          only the first min(M, max_regions) regions of an image are visited
+ *                        (core_system.py:363 uses 50); <=0 means M
+ *   out     [dev] float32 [B*M, D]  compacted: rows of non-empty regions in (image, region) order
+ *   out_counts [dev] int32 [B]      regions kept per image (M' of core_system.py:402-404)
+ *   out_src [dev] int32 [B*M]       for each output row, b*M + m of its source region (may be NULL)
+ *   out_total [dev] int32 [1]       number of output rows (sum of out_counts)
+ *   workspace [dev]                 rvo_mask_pool_workspace_bytes(B, M, P, D) bytes, 256-B aligned
+ * ---------------------------------------------------------------------------------------------- */
+size_t rvo_mask_pool_workspace_bytes(int32_t B, int32_t M, int32_t P, int32_t D);
+int rvo_mask_pool(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
+                  int32_t max_regions, float* out, int32_t* out_counts, int32_t* out_src, int32_t* out_total,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2 — exact cosine top-k over one DB shard.
+ * Replaces: `QdrantClient.search(collection_name, query_vector, limit, score_threshold)` in local
+ *           mode behind core_system.py:659-664 (normalise query, scores = vectors @ q over the
+ *           whole collection, descending argsort, stop at first score < score_threshold, first
+ *           `limit` hits), batched over nq queries row by row.
+ *   db      [dev] bf16 [n_rows, db_ld] L2-normalised rows (db_ld % 64 == 0, columns >= d zero)
+ *   queries [dev] float32 [nq, d] row pitch d; NOT required to be normalised
+ *   k       1..RVO_MAX_K  (`limit`)
+ *   score_threshold   hits with score < threshold are dropped; pass -INFINITY for "None"
+ *   id_offset         added to local row numbers (row-sharded DB: first global row of the shard)
+ *   out_ids    [dev] int64   [nq, k]  global row ids, score-descending, ties by lower id; -1 pad
+ *   out_scores [dev] float32 [nq, k]  fp32 cosine (fp32 query x bf16 row, fp32 accumulate); -inf pad
+ *   out_counts [dev] int32   [nq]     hits per query (0..k), or -1 if the query OVERFLOWED the
+ *                                     candidate buffers of the fused path (pathological tie mass);
+ *                                     the caller must re-run such queries in batches of
+ *                                     <= RVO_SMALL_Q, which never overflow.
+ *   workspace  [dev] rvo_search_workspace_bytes(...) bytes, 1024-B aligned.  Contents are scratch.
+ * nq <= RVO_SMALL_Q: exact fp32 CUDA-core scan (HBM-bound).  nq > RVO_SMALL_Q: bf16 tcgen05 scan
+ * with the threshold-select fused in its epilogue, candidates re-scored in fp32.
+ * ---------------------------------------------------------------------------------------------- */
+size_t rvo_search_workspace_bytes(int64_t n_rows, int32_t d, int32_t nq, int32_t k);
+int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld,
+                    const float* queries, int32_t nq, int32_t k, float score_threshold, int64_t id_offset,
+                    int64_t* out_ids, float* out_scores, int32_t* out_counts,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Rows the tcgen05 path pads a batch of nq queries to (query blocks of <=256, multiples of 16). */
+int rvo_padded_queries(int32_t nq, int32_t d);
+
+/* Dense score block (diagnostics / tests): scores[q, r] = <bf16(q_hat), db[r]> computed by the
+ * tcgen05 scan in DENSE mode over rows r = i*row_stride, i < n_sample.
+ *   out [dev] float32 [rvo_padded_queries(nq, d), out_ld], out_ld >= n_sample */
+int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld,
+                     const float* queries, int32_t nq, int64_t row_stride, int64_t n_sample,
+                     float* out, int64_t out_ld, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3 — merge per-shard top-k lists (after one all-gather of [nq,k] ids/scores/counts per rank).
+ * No reference counterpart (the reference is single-process); semantics = K2 over the union.
+ *   ids [dev] int64 [G, nq, k], scores [dev] float32 [G, nq, k], counts [dev] int32 [G, nq]
+ *   (a count of -1 marks an overflowed shard list and propagates to out_counts)
+ *   out_* as in rvo_search_topk.   G*k <= 4096.
+ * ---------------------------------------------------------------------------------------------- */
+int rvo_merge_topk(const int64_t* ids, const float* scores, const int32_t* counts,
+                   int32_t G, int32_t nq, int32_t k,
+                   int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream);
+
+/* Same merge over the buffer ONE all-gather produces: G blobs, `rank_stride_bytes` apart, each laid out
+ * as [ids int64 nq*k | scores float32 nq*k | counts int32 nq] (rvo_packed_result_bytes(nq,k) bytes,
+ * a multiple of 8). */
+size_t rvo_packed_result_bytes(int32_t nq, int32_t k);
+int rvo_merge_topk_packed(const void* gathered, int64_t rank_stride_bytes, int32_t G, int32_t nq, int32_t k,
+                          int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Counters for bench.py's `gpu_launches` claim: number of kernels THIS library has launched on the
+ * calling process since load (monotonic).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t rvo_kernel_launch_count(void);
+
+/* Device time of the dominant scan kernel of the LAST rvo_search_topk call on this process (the full-DB
+ * FILTER launch of the tcgen05 path, or the fp32 small-q scan), measured with CUDA events recorded on the
+ * call's stream around that one launch.  Only recorded while option "time_scan" is 1.  Synchronises on the
+ * stop event.  <0 if nothing was recorded. */
+float rvo_last_scan_ms(void);
+
+/* Tuning knobs (benchmarks/tests only; defaults reproduce the documented behaviour).
+ *   name: "force_path" (0 auto, 1 small-q scan, 2 tcgen05 scan), "m_sub" (0 auto,1,2),
+ *         "cand_cap" (candidates per query, default 16384), "final_ratio" (default 48),
+ *         "time_scan" (0/1, see rvo_last_scan_ms)                                                */
+int rvo_set_option(const char* name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REVERS_O_B200_H */

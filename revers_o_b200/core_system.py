@@ -1,0 +1,491 @@
+"""Drop-in for the reference's `core_system.SimpleReverso` on the region-similarity hot path.
+
+Same class name, method names, argument meaning, return shapes and status-string error convention as
+/root/reference core_system.py:44-757, so that the unmodified `ui.py` keeps working
+(`from core_system import SimpleReverso`, ui.py:19-20).  What changes is what runs underneath:
+
+  extract_embeddings / process_image_direct_pe  (core_system.py:320-455)
+        -> K1 mask-pool + L2-normalise CUDA kernel (`ops.mask_pool`) / `ops.normalize_rows`
+  create_database ingest tail                   (core_system.py:593-625)
+        -> `B200VectorDB.recreate_collection` + `upsert` (bf16 rows on the GPU)
+  search_similar query head                     (core_system.py:650-666)
+        -> `B200VectorDB.search` (K2 scan + exact select + fp32 re-score)
+
+Out of scope and therefore injected, not re-implemented: the PE encoder
+(`encoder(image_tensor) -> [1,N,D] | [1,D]`, `preprocess(pil) -> tensor`) and the GroundedSAM detector
+(`detector(pil, prompt) -> object with .mask [n,H,W], .confidence, .class_id, .xyxy`).  With no
+argument the constructor tries the reference's own imports lazily and reports a ❌ status if they are
+absent; nothing on the similarity path depends on them.
+
+`parity_mode`:
+  "reference"  every non-empty region gets the normalised GLOBAL embedding, exactly what
+               core_system.py:406-407 computes today — bit-for-bit UI parity;
+  "pooled"     the reference's stated design (main.py:8-9): patch features averaged under each mask.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import uuid
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import RvoError
+from .vector_db import B200VectorDB, models
+
+DB_ROOT = "./simple_reverso_db"          # core_system.py:76,95,471
+COLLECTION_PREFIX = "simple_reverso_"    # core_system.py:101,597
+MAX_REGIONS = 50                         # core_system.py:363
+UPSERT_BATCH = 100                       # core_system.py:612
+
+
+def binarize_mask(mask: np.ndarray) -> np.ndarray:
+    """core_system.py:398-400."""
+    m = np.asarray(mask)
+    if m.dtype == bool:
+        return m.astype(np.uint8)
+    if np.issubdtype(m.dtype, np.floating):
+        return (m > 0.5).astype(np.uint8)
+    return m.astype(np.uint8)
+
+
+def mask_to_patch_grid(mask: np.ndarray, grid: int = 24) -> np.ndarray:
+    """Image-resolution mask -> binary patch-grid mask [grid*grid] (rule fixed in DESIGN.md §3: a patch
+    is in the region when more than half of its pixels are; a non-empty mask never becomes empty)."""
+    m = binarize_mask(mask)
+    H, W = m.shape
+    rb = (np.arange(grid + 1) * H) // grid
+    cb = (np.arange(grid + 1) * W) // grid
+    r0, c0 = rb[:-1], cb[:-1]
+    r1 = np.minimum(np.maximum(rb[1:], r0 + 1), H)
+    c1 = np.minimum(np.maximum(cb[1:], c0 + 1), W)
+    ii = np.zeros((H + 1, W + 1), dtype=np.int64)
+    ii[1:, 1:] = m.astype(np.int64).cumsum(0).cumsum(1)
+    s = ii[r1][:, c1] - ii[r0][:, c1] - ii[r1][:, c0] + ii[r0][:, c0]
+    area = np.maximum((r1 - r0)[:, None] * (c1 - c0)[None, :], 1)
+    frac = s / area
+    out = (frac > 0.5).astype(np.uint8)
+    if out.sum() == 0 and m.sum() > 0:
+        out.flat[int(np.argmax(frac))] = 1
+    return out.reshape(-1)
+
+
+class SimpleReverso:
+    """Simplified visual investigation system (B200-native hot path)."""
+
+    def __init__(self, encoder=None, preprocess=None, detector=None, parity_mode: str = "reference",
+                 db_root: str = DB_ROOT, device=None):
+        print("🚀 Initializing Simple Revers-o (B200-native similarity path)...")
+        if parity_mode not in ("reference", "pooled"):
+            raise ValueError("parity_mode must be 'reference' or 'pooled'")
+        self.parity_mode = parity_mode
+        self.db_root = db_root
+        self.device = torch.device(device) if device is not None else (
+            torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu"))
+        self.pe_model, self.preprocess = encoder, preprocess
+        self._detector = detector
+        self.grounded_sam = None
+        self.vector_db = None
+        self.current_database = None
+        self.detected_regions = []
+        self.region_embeddings = None
+        self.query_embedding_for_search = None
+        self._stop_requested = False
+        self._last_processed_file = None
+        self._partial_embeddings = []
+        self._partial_metadata = []
+        print("✅ Simple Revers-o ready!")
+
+    # ---- database housekeeping (core_system.py:74-154) ------------------------------------------
+    def list_databases(self):
+        if not os.path.exists(self.db_root):
+            return []
+        return [n for n in os.listdir(self.db_root) if os.path.isdir(os.path.join(self.db_root, n))]
+
+    def load_database(self, database_name):
+        if not database_name:
+            return "❌ Please provide a database name"
+        db_path = f"{self.db_root}/{database_name}"
+        if not os.path.exists(db_path):
+            return f"❌ Database not found: {database_name}"
+        try:
+            client = B200VectorDB(path=db_path, device=self.device)
+            collection_name = f"{COLLECTION_PREFIX}{database_name}"
+            names = [c.name for c in client.get_collections().collections]
+            if collection_name not in names:
+                if database_name in names:  # legacy naming, core_system.py:107-109
+                    collection_name = database_name
+                else:
+                    return f"❌ Collection not found in database: {database_name}"
+            self.vector_db = client
+            self.current_database = collection_name
+            return f"✅ Loaded database: {database_name}"
+        except Exception as e:  # status strings, never raise into Gradio
+            return f"❌ Error loading database: {str(e)}"
+
+    def delete_database(self, database_name):
+        if not database_name:
+            return "❌ Please provide a database name"
+        db_path = f"{self.db_root}/{database_name}"
+        if not os.path.exists(db_path):
+            return f"❌ Database not found: {database_name}"
+        try:
+            if self.current_database in (f"{COLLECTION_PREFIX}{database_name}", database_name):
+                self.vector_db = None
+                self.current_database = None
+            shutil.rmtree(db_path)
+            return f"✅ Deleted database: {database_name}"
+        except Exception as e:
+            return f"❌ Error deleting database: {str(e)}"
+
+    def unlock_database(self, database_name):
+        if not database_name:
+            return "❌ Please provide a database name"
+        lock = f"{self.db_root}/{database_name}/.lock"
+        if os.path.exists(lock):
+            os.remove(lock)
+            return f"✅ Unlocked database: {database_name}"
+        return f"ℹ️ Database was not locked: {database_name}"
+
+    # ---- detection (third-party; injected) -------------------------------------------------------
+    def detect_regions(self, image, text_prompt):
+        """core_system.py:226-318.  Returns the number of regions; the detector only PRODUCES masks."""
+        try:
+            if self._detector is None:
+                return 0 if self._fail("GroundedSAM detector not available in this environment") else 0
+            pil = self._to_pil(image)
+            self.detected_regions = self._detector(pil, text_prompt)
+            n = len(self.detected_regions) if self.detected_regions is not None else 0
+            print(f"✅ Detected {n} regions")
+            return n
+        except Exception as e:
+            print(f"❌ Detection error: {e}")
+            self.detected_regions = []
+            return 0
+
+    # ---- embedding half --------------------------------------------------------------------------
+    def _encode(self, image):
+        if self.pe_model is None or self.preprocess is None:
+            raise RvoError("PE encoder not available: pass encoder= and preprocess= (perception_models is not vendored)")
+        pil = self._to_pil(image)
+        x = self.preprocess(pil.convert("RGB")).unsqueeze(0).to(self.device)
+        with torch.no_grad():
+            fn = getattr(self.pe_model, "encode_image", self.pe_model)
+            return fn(x), pil
+
+    def _global_embedding(self, features: torch.Tensor) -> torch.Tensor:
+        """core_system.py:345-353 + :407: tokens [1,N,D] -> mean over N -> L2; pooled [1,D] -> L2.
+        Both run in the CUDA library: the token mean is K1 with an all-ones mask."""
+        if features.dim() == 3:
+            _, N, D = features.shape
+            feats = features[:1].to(torch.bfloat16).contiguous()  # encoder-side cast; K1 consumes bf16 features
+            ones = torch.ones((1, 1, N), dtype=torch.uint8, device=feats.device)
+            out, _, _, _ = ops.mask_pool(feats, ones)
+            return out[0]
+        if features.dim() == 2:
+            _, f32 = ops.normalize_rows(features[:1].float().contiguous(), want_f32=True)
+            return f32[0]
+        raise ValueError(f"Unexpected feature shape: {tuple(features.shape)}")
+
+    def extract_embeddings(self, image):
+        """core_system.py:320-429.  Returns (list[Tensor[D]] on CPU, list[dict])."""
+        if self.detected_regions is None or len(self.detected_regions) == 0:
+            print("❌ No regions detected")
+            return [], []
+        try:
+            features, pil = self._encode(image)
+        except Exception as e:
+            print(f"❌ {e}")
+            return [], []
+        if features.dim() not in (2, 3):
+            print(f"[ERROR] Unexpected feature shape: {features.shape}")
+            return [], []
+        det = self.detected_regions
+        masks = getattr(det, "mask", None)
+        n_reg = min(len(det), MAX_REGIONS)
+        conf = getattr(det, "confidence", None)
+        cls = getattr(det, "class_id", None)
+        names = self._class_names()
+
+        keep, metas = [], []
+        for i in range(n_reg):
+            raw_conf = float(conf[i]) if conf is not None and i < len(conf) else 0.0
+            cid = int(cls[i]) if cls is not None and i < len(cls) else -1
+            if masks is None or i >= len(masks):
+                dc = names[cid] if 0 <= cid < len(names) else "unknown"
+                keep.append((i, None))
+                metas.append({"region_id": str(uuid.uuid4()), "bbox": [0, 0, pil.width, pil.height], "area_ratio": 1.0,
+                              "detection_index": i, "confidence": raw_conf, "detected_class": dc,
+                              "mask_status": "missing_or_unavailable"})
+                continue
+            m = binarize_mask(masks[i])
+            if m.sum() == 0:  # core_system.py:402-404: dropped, later regions shift up
+                print(f"⚠️ Empty mask for region {i}, skipping")
+                continue
+            ys, xs = np.where(m)
+            dc = names[cid] if 0 <= cid < len(names) else "object"
+            keep.append((i, m))
+            metas.append({"region_id": str(uuid.uuid4()),
+                          "bbox": [int(xs.min()), int(ys.min()), int(xs.max()), int(ys.max())],
+                          "area_ratio": float(m.sum() / m.size), "detection_index": i, "confidence": raw_conf,
+                          "detected_class": dc, "mask_status": "processed"})
+
+        embeddings = []
+        if keep:
+            pooled_ok = self.parity_mode == "pooled" and features.dim() == 3
+            if pooled_ok:
+                embeddings = self._pooled_embeddings(features, [m for _, m in keep])
+            else:
+                g = self._global_embedding(features).cpu()
+                embeddings = [g.clone() for _ in keep]
+        self.region_embeddings = embeddings
+        print(f"🎯 Extracted {len(embeddings)} region embeddings")
+        return embeddings, metas
+
+    def _pooled_embeddings(self, features: torch.Tensor, masks_hw: list):
+        """north_star path: patch tokens averaged under each mask (K1).  A leading class token is
+        dropped when N is not a perfect square but N-1 is."""
+        _, N, D = features.shape
+        g = int(round(np.sqrt(N)))
+        tokens = features[0]
+        if g * g != N:
+            g = int(round(np.sqrt(N - 1)))
+            if g * g != N - 1:
+                raise RvoError(f"cannot map {N} tokens to a square patch grid")
+            tokens = tokens[1:]
+        P = g * g
+        M = len(masks_hw)
+        pm = np.ones((1, M, P), dtype=np.uint8)
+        for j, m in enumerate(masks_hw):
+            if m is not None:
+                pm[0, j] = mask_to_patch_grid(m, g)
+        feats = tokens.to(torch.bfloat16).contiguous().unsqueeze(0)
+        out, counts, src, total = ops.mask_pool(feats, torch.from_numpy(pm).to(feats.device))
+        out = out[:M].cpu()  # every mask is non-empty here, so total == M
+        return [out[j].clone() for j in range(M)]
+
+    def process_image_direct_pe(self, image):
+        """core_system.py:431-455."""
+        print("🧠 Processing image directly with PE...")
+        features, pil = self._encode(image)
+        emb = self._global_embedding(features).cpu()
+        self.region_embeddings = [emb]
+        meta = {"region_id": str(uuid.uuid4()), "bbox": [0, 0, pil.width, pil.height], "area_ratio": 1.0,
+                "detection_index": 0, "confidence": 1.0, "detected_class": "full_image"}
+        print("✅ Extracted global image embedding")
+        return [emb], [meta]
+
+    def request_stop(self):
+        """core_system.py:457-459."""
+        self._stop_requested = True
+
+    # ---- ingest ------------------------------------------------------------------------------------
+    def create_database(self, folder_path, database_name, text_prompt="person . car . building .", use_direct_pe=False,
+                        resume_from_checkpoint=True, include_subfolders=False, progress_callback=None):
+        """core_system.py:461-648.  Orchestration is unchanged in meaning; the checkpoint feature is dead code in
+        the reference and is not reproduced."""
+        status_messages = []
+
+        def log_status(msg, progress=None):
+            print(msg)
+            status_messages.append(msg)
+            if progress_callback:
+                try:
+                    progress_callback(msg, progress)
+                except Exception:
+                    pass
+            return msg
+
+        try:
+            if not os.path.exists(folder_path):
+                return log_status(f"❌ Folder not found: {folder_path}")
+            if not database_name:
+                return log_status("❌ Please provide a database name")
+            exts = (".jpg", ".jpeg", ".png", ".bmp", ".tiff", ".webp")
+            files = []
+            if include_subfolders:
+                for root, _, fs in os.walk(folder_path):
+                    files += [os.path.join(root, f) for f in fs if f.lower().endswith(exts)]
+            else:
+                files = [os.path.join(folder_path, f) for f in os.listdir(folder_path) if f.lower().endswith(exts)]
+            files.sort()
+            if not files:
+                return log_status(f"❌ No images found in {folder_path}")
+            log_status(f"📁 Found {len(files)} images", 0.0)
+
+            db_path = f"{self.db_root}/{database_name}"
+            os.makedirs(db_path, exist_ok=True)
+            client = B200VectorDB(path=None, device=self.device)
+            processed = failed = 0
+            for n, path in enumerate(files):
+                if self._stop_requested:
+                    log_status("🛑 Stop requested. Progress saved.")
+                    return "\n".join(status_messages) + "\n\n⏸️ Processing stopped. You can resume later."
+                try:
+                    from PIL import Image
+                    image = Image.open(path).convert("RGB")
+                    if use_direct_pe:
+                        embs, metas = self.process_image_direct_pe(image)
+                    else:
+                        if self.detect_regions(image, text_prompt) == 0:
+                            failed += 1
+                            continue
+                        embs, metas = self.extract_embeddings(image)
+                    for m in metas:
+                        m["image_source"] = path
+                        m["filename"] = os.path.basename(path)
+                        m.setdefault("original_region_id", m["region_id"])
+                    self._partial_embeddings += embs
+                    self._partial_metadata += metas
+                    processed += 1
+                    self._last_processed_file = path
+                    log_status(f"✅ {os.path.basename(path)}: {len(embs)} regions", 0.8 * (n + 1) / len(files))
+                except Exception as e:
+                    failed += 1
+                    log_status(f"❌ Error processing {os.path.basename(path)}: {e}")
+            if not self._partial_embeddings:
+                return log_status("❌ No embeddings extracted from any images")
+
+            vector_dim = self._partial_embeddings[0].shape[0]
+            collection_name = f"{COLLECTION_PREFIX}{database_name}"
+            client.recreate_collection(collection_name=collection_name,
+                                       vectors_config=models.VectorParams(size=vector_dim, distance=models.Distance.COSINE))
+            log_status(f"📦 Recreated collection: {collection_name}", 0.8)
+            points = [models.PointStruct(id=meta["region_id"], vector=emb.cpu().numpy(), payload=meta)
+                      for emb, meta in zip(self._partial_embeddings, self._partial_metadata)]
+            for j in range(0, len(points), UPSERT_BATCH):
+                if self._stop_requested:
+                    log_status("🛑 Stop requested during database storage. Progress saved.")
+                    return "\n".join(status_messages) + "\n\n⏸️ Processing stopped. You can resume later."
+                batch = points[j:j + UPSERT_BATCH]
+                client.upsert(collection_name=collection_name, points=batch)
+                log_status(f"💾 Stored batch {j // UPSERT_BATCH + 1}/{(len(points) + UPSERT_BATCH - 1) // UPSERT_BATCH} "
+                           f"({len(batch)} points)", 0.8 + 0.1 * j / len(points))
+            client.save(db_path)
+            client.path = db_path
+            self.vector_db = client
+            self.current_database = collection_name
+            log_status("\n📊 Final Summary:", 0.9)
+            log_status(f"✅ Successfully processed: {processed} images")
+            if failed > 0:
+                log_status(f"⚠️ Failed to process: {failed} images")
+            log_status(f"🔍 Total embeddings stored: {len(self._partial_embeddings)}")
+            log_status(f"🎯 Database '{database_name}' ready for searching!", 1.0)
+        except Exception as e:
+            log_status(f"❌ Error creating database: {e}")
+        finally:
+            self._stop_requested = False
+            self._partial_embeddings = []
+            self._partial_metadata = []
+        return "\n".join(status_messages)
+
+    # ---- search ------------------------------------------------------------------------------------
+    def search_similar(self, similarity_threshold=0.7, max_results=5):
+        """core_system.py:650-717.  Returns (status text, list of dict{image, score, filename, bbox})."""
+        if not self.region_embeddings:
+            return "❌ No query embeddings available. Please detect/process an image first.", []
+        if not self.vector_db or not self.current_database:
+            return "❌ No database loaded. Please create or load a database first.", []
+        print(f"🔍 Searching for similar regions (threshold={similarity_threshold}, max_results={max_results})")
+        query_embedding = self.region_embeddings[0]  # first region is the query, core_system.py:657
+        try:
+            search_results = self.vector_db.search(
+                collection_name=self.current_database,
+                query_vector=query_embedding.detach().cpu().numpy(),
+                limit=max_results,
+                score_threshold=similarity_threshold,
+            )
+        except Exception as e:
+            return f"❌ Search error: {e}", []
+        if not search_results:
+            return f"❌ No similar regions found above threshold {similarity_threshold}", []
+
+        results_text = f"🎯 Found {len(search_results)} similar regions:\n\n"
+        items = []
+        for i, result in enumerate(search_results):
+            payload = result.payload or {}
+            filename = payload.get("filename", "Unknown")
+            score = result.score
+            image_path = payload.get("image_source", "")
+            results_text += f"{i + 1}. {filename} (Similarity: {score:.3f})\n"
+            results_text += f"   Source: {image_path}\n"
+            results_text += f"   📍 Bounding box: {str(payload.get('bbox', '[0,0,0,0]'))}\n\n"
+            items.append({"image": self._thumbnail(image_path, score), "score": score, "filename": filename,
+                          "bbox": payload.get("bbox")})
+        print(f"📊 Processed {len(items)} search results for display.")
+        return results_text, items
+
+    def search_similar_batch(self, similarity_threshold=0.7, max_results=5):
+        """New: search with ALL region embeddings of the query image at once.
+        Returns one `search_similar`-shaped hit list per region."""
+        if not self.region_embeddings:
+            return "❌ No query embeddings available. Please detect/process an image first.", []
+        if not self.vector_db or not self.current_database:
+            return "❌ No database loaded. Please create or load a database first.", []
+        q = torch.stack([e.detach().float().cpu() for e in self.region_embeddings]).numpy()
+        ids, scores, counts = self.vector_db.search_batch(self.current_database, q, max_results, similarity_threshold)
+        c = self.vector_db._coll(self.current_database)
+        out = []
+        for r in range(len(q)):
+            hits = []
+            for i, s in zip(ids[r, :counts[r]], scores[r, :counts[r]]):
+                pay = c.payloads[int(i)] or {}
+                hits.append({"image": None, "score": float(s), "filename": pay.get("filename", "Unknown"),
+                             "bbox": pay.get("bbox")})
+            out.append(hits)
+        return f"🎯 Searched {len(q)} regions", out
+
+    def visualize_detections(self, image, selected_region_index=None):
+        """core_system.py:719-757 — rendering, out of scope; returns the image with region boxes drawn."""
+        pil = self._to_pil(image).copy()
+        det = self.detected_regions
+        boxes = getattr(det, "xyxy", None) if det is not None else None
+        if boxes is not None:
+            from PIL import ImageDraw
+            d = ImageDraw.Draw(pil)
+            for i, b in enumerate(boxes):
+                colour = "yellow" if selected_region_index is not None and i == selected_region_index else "lime"
+                d.rectangle([float(b[0]), float(b[1]), float(b[2]), float(b[3])], outline=colour, width=3)
+                d.text((float(b[0]) + 4, float(b[1]) + 4), str(i + 1), fill=colour)
+        return pil
+
+    # ---- helpers -----------------------------------------------------------------------------------
+    @staticmethod
+    def _to_pil(image):
+        from PIL import Image
+        if isinstance(image, np.ndarray):
+            return Image.fromarray(image)
+        if isinstance(image, str):
+            return Image.open(image)
+        return image
+
+    def _class_names(self):
+        try:
+            return list(self.grounded_sam.ontology.classes())
+        except Exception:
+            return ["object"]
+
+    @staticmethod
+    def _fail(msg):
+        print(f"❌ {msg}")
+        return True
+
+    @staticmethod
+    def _thumbnail(image_path, score):
+        if not image_path or not os.path.exists(image_path):
+            return None
+        try:
+            from PIL import Image, ImageDraw
+            img = Image.open(image_path).convert("RGB")
+            d = ImageDraw.Draw(img)
+            text = f"Score: {score:.3f}"
+            box = d.textbbox((5, 5), text)
+            d.rectangle([box[0] - 2, box[1] - 2, box[2] + 2, box[3] + 2], fill="black")
+            d.text((5, 5), text, fill="white")
+            img.thumbnail((400, 400))
+            return img
+        except Exception as e:
+            print(f"❌ Error loading/processing image {image_path}: {e}")
+            return None

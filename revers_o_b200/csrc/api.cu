@@ -1,0 +1,521 @@
+// C-ABI entry points (include/revers_o_b200.h) and the search driver that sequences the kernels.
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "scan_tc.cuh"
+#include "select.cuh"
+#include "prep_scan_small.cuh"
+
+namespace rvo {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::atomic<long long> opt_force_path{0}, opt_m_sub{0}, opt_cand_cap{16384}, opt_final_ratio{48}, opt_time_scan{0};
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static bool g_ev_valid = false;
+
+static int scan_timer(bool start, cudaStream_t stream) {
+    if (!opt_time_scan.load()) return RVO_OK;
+    if (!g_ev0) {
+        RVO_CUDA(cudaEventCreate(&g_ev0));
+        RVO_CUDA(cudaEventCreate(&g_ev1));
+    }
+    RVO_CUDA(cudaEventRecord(start ? g_ev0 : g_ev1, stream));
+    if (!start) g_ev_valid = true;
+    return RVO_OK;
+}
+
+int select_device_of(const void* dev_ptr, int* sm_count) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, dev_ptr);
+    if (e != cudaSuccess) {
+        set_error("cudaPointerGetAttributes failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return RVO_E_NO_DEVICE;
+    }
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
+        set_error("pointer %p is not device memory (type %d)", dev_ptr, (int)at.type);
+        return RVO_E_INVALID;
+    }
+    RVO_CUDA(cudaSetDevice(at.device));
+    static int cached_dev = -1, cached_sm = 0, cached_major = 0;
+    if (cached_dev != at.device) {
+        cudaDeviceProp pr;
+        RVO_CUDA(cudaGetDeviceProperties(&pr, at.device));
+        cached_dev = at.device;
+        cached_sm = pr.multiProcessorCount;
+        cached_major = pr.major;
+    }
+    if (cached_major != 10) {
+        set_error("device %d is sm_%d0, this library is built for sm_100a (B200) only", at.device, cached_major);
+        return RVO_E_NO_DEVICE;
+    }
+    if (sm_count) *sm_count = cached_sm;
+    return RVO_OK;
+}
+
+__global__ void fill_outputs_kernel(int64_t* ids, float* scores, int32_t* counts, long long n, int nq) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        ids[i] = -1;
+        scores[i] = -__int_as_float(0x7f800000);
+    }
+    if (i < nq) counts[i] = 0;
+}
+
+__global__ void init_tau_kernel(float* tau, int nq, int nq_pad, float floor_t, int copies) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq_pad * copies) return;
+    tau[i] = (i % nq_pad) < nq ? floor_t : __int_as_float(0x7f800000);
+}
+
+static int next_pow2_host(int x) {
+    int p = 2;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// ---- chunked top-K reduction: repeat chunk_topk until one chunk per query remains ---------------
+struct TopkSrc {
+    const float* dense;
+    long long dense_ld;
+    const unsigned long long* keys;
+    long long keys_ld;
+    const int* cnt;
+    int cap;
+    long long n;
+};
+
+static size_t reduce_buf_elems(long long n, int K) { return (size_t)((n + kChunk - 1) / kChunk) * (size_t)K; }
+
+static int reduce_topk(TopkSrc src, int nq, int K_mid, int K_final, unsigned long long* bufA, unsigned long long* bufB,
+                       float* tau_out, const float* tau_prev, int tau_k, float tau_margin, float tau_floor,
+                       const unsigned long long** result, long long* result_ld, cudaStream_t stream) {
+    unsigned long long* bufs[2] = {bufA, bufB};
+    int tog = 0;
+    for (;;) {
+        const long long n = src.n;
+        const int chunks = (int)((n + kChunk - 1) / kChunk);
+        const bool last = chunks <= 1;
+        ChunkTopkArgs a;
+        a.dense = src.dense;
+        a.dense_ld = src.dense_ld;
+        a.keys = src.keys;
+        a.keys_ld = src.keys_ld;
+        a.cnt = src.cnt;
+        a.cap = src.cap;
+        a.n_fixed = n;
+        a.K = last ? K_final : K_mid;
+        a.out = bufs[tog];
+        a.out_ld = (long long)(chunks > 0 ? chunks : 1) * a.K;
+        a.tau_out = last ? tau_out : nullptr;
+        a.tau_prev = tau_prev;
+        a.tau_k = tau_k;
+        a.tau_margin = tau_margin;
+        a.tau_floor = tau_floor;
+        int rc = launch_chunk_topk(a, chunks > 0 ? chunks : 1, nq, stream);
+        if (rc) return rc;
+        if (last) {
+            *result = a.out;
+            *result_ld = a.out_ld;
+            return RVO_OK;
+        }
+        src.dense = nullptr;
+        src.keys = a.out;
+        src.keys_ld = a.out_ld;
+        src.cnt = nullptr;
+        src.n = a.out_ld;
+        tog ^= 1;
+    }
+}
+
+// ---- search plan (shared by the workspace query and the driver) --------------------------------
+struct SearchPlan {
+    bool small;
+    int d_pad, K2, cap, n_levels;
+    long long level_stride[8], level_rows[8];
+    long long dense_rows, dense_stride;
+    TcPlan tc;
+    // workspace slices
+    float* qn;
+    uint16_t* qb;
+    float* tau;       // [n_levels+1][nq_pad]
+    int* cnt;         // [n_levels+1][nq_pad]
+    unsigned long long* cand;
+    float* dense;
+    long long dense_ld;
+    unsigned long long *bufA, *bufB;
+    size_t zero_off, zero_bytes;  // region cleared with one memset at the start of a call
+    size_t bytes;
+};
+
+static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws_bytes, SearchPlan* sp) {
+    memset(sp, 0, sizeof(*sp));
+    sp->d_pad = (d + kBlockK - 1) / kBlockK * kBlockK;
+    const long long force = opt_force_path.load();
+    sp->small = (force == 1) || (force != 2 && nq <= RVO_SMALL_Q);
+    if (sp->small && nq > RVO_SMALL_Q) {
+        set_error("force_path=1 needs nq <= %d", RVO_SMALL_Q);
+        return RVO_E_INVALID;
+    }
+    Arena ar(ws, ws_bytes);
+    if (sp->small) {
+        sp->K2 = next_pow2_host(k);
+        const long long ld = (n_rows + 63) / 64 * 64;
+        sp->zero_off = ar.off;
+        sp->qn = ar.take<float>((size_t)RVO_SMALL_Q * sp->d_pad, 1024);
+        sp->zero_bytes = ar.off - sp->zero_off;
+        sp->dense = ar.take<float>((size_t)RVO_SMALL_Q * (size_t)(ld > 0 ? ld : 64));
+        sp->dense_ld = ld > 0 ? ld : 64;
+        const size_t e1 = reduce_buf_elems(n_rows > 0 ? n_rows : 1, k > sp->K2 ? k : sp->K2);
+        sp->bufA = ar.take<unsigned long long>((size_t)nq * e1);
+        sp->bufB = ar.take<unsigned long long>((size_t)nq * reduce_buf_elems((long long)e1, sp->K2));
+    } else {
+        int rc = plan_scan_tc(nq, sp->d_pad, (int)opt_m_sub.load(), &sp->tc);
+        if (rc) return rc;
+        const int nq_pad = sp->tc.nq_pad;
+        sp->K2 = next_pow2_host((2 * k > k + 64) ? 2 * k : k + 64);
+        if (sp->K2 > 1024) sp->K2 = 1024;
+        long long cap = opt_cand_cap.load();
+        if (cap < kChunk) cap = kChunk;
+        cap = (cap + kChunk - 1) / kChunk * kChunk;
+        sp->cap = (int)cap;
+        // levels: dense seed over <=4096 strided rows, then geometric FILTER samples, then the full scan
+        if (n_rows <= kChunk) {
+            sp->dense_rows = n_rows;
+            sp->dense_stride = 1;
+            sp->n_levels = 0;
+        } else {
+            sp->dense_stride = n_rows / kChunk;
+            sp->dense_rows = kChunk;
+            long long ratio = opt_final_ratio.load();
+            if (ratio < 2) ratio = 2;
+            long long sizes[8];
+            int ns = 0;
+            for (long long s = n_rows / ratio; s >= 2 * kChunk && ns < 6; s /= 64) sizes[ns++] = s;
+            int L = 0;
+            for (int i = ns - 1; i >= 0; --i) {
+                const long long r = n_rows / sizes[i];
+                if (r <= 1) continue;
+                sp->level_stride[L] = r;
+                sp->level_rows[L] = n_rows / r;
+                ++L;
+            }
+            sp->level_stride[L] = 1;
+            sp->level_rows[L] = n_rows;
+            sp->n_levels = L + 1;
+        }
+        sp->zero_off = ar.off;
+        sp->qb = ar.take<uint16_t>((size_t)nq_pad * sp->d_pad, 1024);
+        sp->cnt = ar.take<int>((size_t)(sp->n_levels + 1) * nq_pad);
+        sp->zero_bytes = ar.off - sp->zero_off;
+        sp->qn = ar.take<float>((size_t)nq * sp->d_pad, 1024);
+        sp->tau = ar.take<float>((size_t)(sp->n_levels + 1) * nq_pad);
+        sp->dense_ld = kChunk;
+        sp->dense = ar.take<float>((size_t)nq_pad * kChunk);
+        if (sp->n_levels > 0) sp->cand = ar.take<unsigned long long>((size_t)nq_pad * (size_t)sp->cap);
+        const size_t e_list = reduce_buf_elems(sp->cap, sp->K2);
+        const size_t e_dense = reduce_buf_elems(kChunk, sp->K2);
+        const size_t e1 = e_list > e_dense ? e_list : e_dense;
+        sp->bufA = ar.take<unsigned long long>((size_t)nq * e1);
+        sp->bufB = ar.take<unsigned long long>((size_t)nq * reduce_buf_elems((long long)e1, sp->K2));
+    }
+    sp->bytes = ar.off + 1024;
+    if (ws && !ar.ok()) {
+        set_error("search workspace too small: %zu bytes given, %zu needed", ws_bytes, sp->bytes);
+        return RVO_E_WORKSPACE;
+    }
+    return RVO_OK;
+}
+
+static int prep_queries(const SearchPlan& sp, const float* queries, int nq, int d, void* ws, cudaStream_t stream) {
+    RVO_CUDA(cudaMemsetAsync((char*)ws + sp.zero_off, 0, sp.zero_bytes, stream));
+    return launch_normalize_rows(queries, nq, d, d, sp.small ? nullptr : sp.qb, sp.d_pad, sp.qn, sp.d_pad, stream);
+}
+
+}  // namespace rvo
+
+using namespace rvo;
+
+extern "C" {
+
+int rvo_version(void) { return 100; }
+
+const char* rvo_last_error(void) { return g_err; }
+
+int64_t rvo_kernel_launch_count(void) { return (int64_t)g_launches.load(); }
+
+float rvo_last_scan_ms(void) {
+    if (!g_ev_valid) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(g_ev1) != cudaSuccess || cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) {
+        cudaGetLastError();
+        return -1.f;
+    }
+    return ms;
+}
+
+int rvo_device_sm_count(const void* dev_ptr) {
+    int sm = 0;
+    int rc = select_device_of(dev_ptr, &sm);
+    return rc ? rc : sm;
+}
+
+int rvo_set_option(const char* name, int64_t value) {
+    if (!name) return RVO_E_INVALID;
+    if (!strcmp(name, "force_path")) opt_force_path = value;
+    else if (!strcmp(name, "m_sub")) opt_m_sub = value;
+    else if (!strcmp(name, "cand_cap")) opt_cand_cap = value;
+    else if (!strcmp(name, "final_ratio")) opt_final_ratio = value;
+    else if (!strcmp(name, "time_scan")) opt_time_scan = value;
+    else {
+        set_error("unknown option '%s'", name);
+        return RVO_E_INVALID;
+    }
+    return RVO_OK;
+}
+
+int rvo_normalize_rows(const float* src, int64_t n, int32_t d, int64_t src_ld, uint16_t* dst_bf16, int64_t dst_ld,
+                       float* dst_f32, void* stream) {
+    RVO_REQUIRE(src && (dst_bf16 || dst_f32), "normalize_rows: null pointer");
+    RVO_REQUIRE(n >= 0 && d > 0 && src_ld >= d, "normalize_rows: bad shape n=%lld d=%d ld=%lld", (long long)n, d,
+                (long long)src_ld);
+    RVO_REQUIRE(!dst_bf16 || (dst_ld >= d && dst_ld % 8 == 0), "normalize_rows: dst_ld=%lld must be >= d and %% 8 == 0",
+                (long long)dst_ld);
+    int rc = select_device_of(src, nullptr);
+    if (rc) return rc;
+    return launch_normalize_rows(src, n, d, src_ld, dst_bf16, dst_ld, dst_f32, d, (cudaStream_t)stream);
+}
+
+size_t rvo_mask_pool_workspace_bytes(int32_t B, int32_t M, int32_t P, int32_t D) {
+    return mask_pool_workspace_bytes(B, M, P, D);
+}
+
+int rvo_mask_pool(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
+                  int32_t max_regions, float* out, int32_t* out_counts, int32_t* out_src, int32_t* out_total,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    RVO_REQUIRE(feats && masks && out && out_counts && out_total && workspace, "mask_pool: null pointer");
+    RVO_REQUIRE(B > 0 && M > 0 && P > 0 && D > 0, "mask_pool: bad shape B=%d M=%d P=%d D=%d", B, M, P, D);
+    RVO_REQUIRE(((uintptr_t)feats & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)masks & 3) == 0,
+                "mask_pool: feats/out must be 16-byte aligned, masks 4-byte aligned");
+    int sm = 0;
+    int rc = select_device_of(feats, &sm);
+    if (rc) return rc;
+    return launch_mask_pool(feats, masks, B, M, P, D, max_regions, out, out_counts, out_src, out_total, workspace,
+                            workspace_bytes, sm, (cudaStream_t)stream);
+}
+
+size_t rvo_search_workspace_bytes(int64_t n_rows, int32_t d, int32_t nq, int32_t k) {
+    if (n_rows < 0 || d <= 0 || nq <= 0 || k <= 0 || k > RVO_MAX_K) return 0;
+    SearchPlan sp;
+    if (make_plan(n_rows, d, nq, k, nullptr, 0, &sp)) return 0;
+    return sp.bytes;
+}
+
+int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld, const float* queries, int32_t nq,
+                    int32_t k, float score_threshold, int64_t id_offset, int64_t* out_ids, float* out_scores,
+                    int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    RVO_REQUIRE(queries && out_ids && out_scores && out_counts && workspace, "search_topk: null pointer");
+    RVO_REQUIRE(n_rows >= 0 && d > 0 && nq > 0, "search_topk: bad shape n_rows=%lld d=%d nq=%d", (long long)n_rows, d, nq);
+    RVO_REQUIRE(k >= 1 && k <= RVO_MAX_K, "search_topk: k=%d outside 1..%d", k, RVO_MAX_K);
+    RVO_REQUIRE(n_rows == 0 || db, "search_topk: null db");
+    RVO_REQUIRE(db_ld % kBlockK == 0 && db_ld >= d, "search_topk: db_ld=%lld must be a multiple of 64 and >= d",
+                (long long)db_ld);
+    RVO_REQUIRE(((uintptr_t)db & 15) == 0 && ((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)queries & 3) == 0,
+                "search_topk: db must be 16-byte and workspace 1024-byte aligned");
+    RVO_REQUIRE(n_rows < (1ll << 31), "search_topk: shard of %lld rows too large, shard the DB", (long long)n_rows);
+    int sm = 0;
+    int rc = select_device_of(queries, &sm);
+    if (rc) return rc;
+
+    if (n_rows == 0) {
+        const long long n = (long long)nq * k;
+        fill_outputs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(out_ids, out_scores, out_counts, n, nq);
+        RVO_LAUNCHED();
+        return RVO_OK;
+    }
+
+    SearchPlan sp;
+    rc = make_plan(n_rows, d, nq, k, workspace, workspace_bytes, &sp);
+    if (rc) return rc;
+    rc = prep_queries(sp, queries, nq, d, workspace, stream);
+    if (rc) return rc;
+
+    const unsigned long long* top = nullptr;
+    long long top_ld = 0;
+    FinalArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.k = k;
+    fa.K2 = sp.K2;
+    fa.score_threshold = score_threshold;
+    fa.db = db;
+    fa.db_ld = db_ld;
+    fa.d_pad = sp.d_pad;
+    fa.qn = sp.qn;
+    fa.qn_ld = sp.d_pad;
+    fa.id_offset = id_offset;
+    fa.out_ids = out_ids;
+    fa.out_scores = out_scores;
+    fa.out_counts = out_counts;
+
+    if (sp.small) {
+        // exact fp32 scan -> dense scores -> chunked exact top-k (never overflows)
+        if ((rc = scan_timer(true, stream))) return rc;
+        rc = launch_scan_small(db, n_rows, db_ld, sp.d_pad, sp.qn, sp.d_pad, nq, sp.dense, sp.dense_ld, sm, stream);
+        if (rc) return rc;
+        if ((rc = scan_timer(false, stream))) return rc;
+        TopkSrc src = {sp.dense, sp.dense_ld, nullptr, 0, nullptr, 0, n_rows};
+        rc = reduce_topk(src, nq, k, sp.K2, sp.bufA, sp.bufB, nullptr, nullptr, 0, 0.f, 0.f, &top, &top_ld, stream);
+        if (rc) return rc;
+        fa.top = top;
+        fa.top_ld = top_ld;
+        fa.rescore = 0;
+        fa.margin = 0.f;
+        return launch_final(fa, nq, stream);
+    }
+
+    const int nq_pad = sp.tc.nq_pad;
+    const float margin = kBf16QueryMargin;
+    const float floor_t = score_threshold - margin;  // -inf stays -inf
+
+    if (sp.n_levels == 0) {
+        // tiny shard: one DENSE pass over all rows, exact top-K2 of the dense block, fp32 re-score
+        rc = launch_scan_tc(kModeDense, db, n_rows, 1, db_ld, sp.d_pad, sp.qb, sp.tc, nullptr, nullptr, nullptr, 0,
+                            sp.dense, sp.dense_ld, sm, stream);
+        if (rc) return rc;
+        TopkSrc src = {sp.dense, sp.dense_ld, nullptr, 0, nullptr, 0, n_rows};
+        rc = reduce_topk(src, nq, sp.K2, sp.K2, sp.bufA, sp.bufB, nullptr, nullptr, 0, 0.f, 0.f, &top, &top_ld, stream);
+        if (rc) return rc;
+        fa.top = top;
+        fa.top_ld = top_ld;
+        fa.rescore = 1;
+        fa.margin = margin;
+        fa.cnt = nullptr;
+        return launch_final(fa, nq, stream);
+    }
+
+    // level 0: DENSE seed over a strided sample -> tau[0]
+    init_tau_kernel<<<(nq_pad * (sp.n_levels + 1) + 255) / 256, 256, 0, stream>>>(sp.tau, nq, nq_pad, floor_t,
+                                                                                  sp.n_levels + 1);
+    RVO_LAUNCHED();
+    rc = launch_scan_tc(kModeDense, db, sp.dense_rows, sp.dense_stride, db_ld, sp.d_pad, sp.qb, sp.tc, nullptr, nullptr,
+                        nullptr, 0, sp.dense, sp.dense_ld, sm, stream);
+    if (rc) return rc;
+    {
+        TopkSrc src = {sp.dense, sp.dense_ld, nullptr, 0, nullptr, 0, sp.dense_rows};
+        rc = reduce_topk(src, nq, k, k, sp.bufA, sp.bufB, sp.tau, nullptr, k, margin, floor_t, &top, &top_ld, stream);
+        if (rc) return rc;
+    }
+    // FILTER levels: each tightens tau on a larger strided sample; the last one scans every row
+    for (int L = 0; L < sp.n_levels; ++L) {
+        const bool last = L == sp.n_levels - 1;
+        int* cnt = sp.cnt + (size_t)L * nq_pad;
+        const float* tau_in = sp.tau + (size_t)L * nq_pad;
+        if (last && (rc = scan_timer(true, stream))) return rc;
+        rc = launch_scan_tc(kModeFilter, db, sp.level_rows[L], sp.level_stride[L], db_ld, sp.d_pad, sp.qb, sp.tc, tau_in,
+                            sp.cand, cnt, sp.cap, nullptr, 0, sm, stream);
+        if (rc) return rc;
+        if (last && (rc = scan_timer(false, stream))) return rc;
+        TopkSrc src = {nullptr, 0, sp.cand, sp.cap, cnt, sp.cap, sp.cap};
+        if (!last) {
+            rc = reduce_topk(src, nq, k, k, sp.bufA, sp.bufB, sp.tau + (size_t)(L + 1) * nq_pad, tau_in, k, margin, floor_t,
+                             &top, &top_ld, stream);
+            if (rc) return rc;
+        } else {
+            rc = reduce_topk(src, nq, sp.K2, sp.K2, sp.bufA, sp.bufB, nullptr, nullptr, 0, 0.f, 0.f, &top, &top_ld, stream);
+            if (rc) return rc;
+            fa.top = top;
+            fa.top_ld = top_ld;
+            fa.rescore = 1;
+            fa.margin = margin;
+            fa.cnt = cnt;
+            fa.cap = sp.cap;
+            rc = launch_final(fa, nq, stream);
+            if (rc) return rc;
+        }
+    }
+    return RVO_OK;
+}
+
+int rvo_padded_queries(int32_t nq, int32_t d) {
+    TcPlan tc;
+    if (nq <= 0 || d <= 0) return RVO_E_INVALID;
+    int rc = plan_scan_tc(nq, (d + kBlockK - 1) / kBlockK * kBlockK, (int)opt_m_sub.load(), &tc);
+    return rc ? rc : tc.nq_pad;
+}
+
+int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld, const float* queries, int32_t nq,
+                     int64_t row_stride, int64_t n_sample, float* out, int64_t out_ld, void* workspace,
+                     size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    RVO_REQUIRE(db && queries && out && workspace, "scores_dense: null pointer");
+    RVO_REQUIRE(n_rows > 0 && d > 0 && nq > 0 && row_stride >= 1 && n_sample >= 1 && out_ld >= n_sample,
+                "scores_dense: bad shape");
+    RVO_REQUIRE((n_sample - 1) * row_stride < n_rows, "scores_dense: sample exceeds the DB");
+    RVO_REQUIRE(db_ld % kBlockK == 0 && db_ld >= d, "scores_dense: db_ld must be a multiple of 64 and >= d");
+    RVO_REQUIRE(((uintptr_t)workspace & 1023) == 0, "scores_dense: workspace must be 1024-byte aligned");
+    int sm = 0;
+    int rc = select_device_of(db, &sm);
+    if (rc) return rc;
+    const int d_pad = (d + kBlockK - 1) / kBlockK * kBlockK;
+    TcPlan tc;
+    rc = plan_scan_tc(nq, d_pad, (int)opt_m_sub.load(), &tc);
+    if (rc) return rc;
+    Arena ar(workspace, workspace_bytes);
+    uint16_t* qb = ar.take<uint16_t>((size_t)tc.nq_pad * d_pad, 1024);
+    if (!ar.ok()) {
+        set_error("scores_dense: workspace too small (%zu needed)", ar.off);
+        return RVO_E_WORKSPACE;
+    }
+    RVO_CUDA(cudaMemsetAsync(qb, 0, (size_t)tc.nq_pad * d_pad * 2, stream));
+    rc = launch_normalize_rows(queries, nq, d, d, qb, d_pad, nullptr, 0, stream);
+    if (rc) return rc;
+    return launch_scan_tc(kModeDense, db, n_sample, row_stride, db_ld, d_pad, qb, tc, nullptr, nullptr, nullptr, 0, out,
+                          out_ld, sm, stream);
+}
+
+int rvo_merge_topk(const int64_t* ids, const float* scores, const int32_t* counts, int32_t G, int32_t nq, int32_t k,
+                   int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream) {
+    RVO_REQUIRE(ids && scores && counts && out_ids && out_scores && out_counts, "merge_topk: null pointer");
+    RVO_REQUIRE(G >= 1 && nq >= 1 && k >= 1 && (long long)G * k <= 4096, "merge_topk: need G*k <= 4096 (G=%d k=%d)", G, k);
+    int rc = select_device_of(ids, nullptr);
+    if (rc) return rc;
+    return launch_merge(ids, scores, counts, (long long)nq * k, (long long)nq * k, nq, G, nq, k, out_ids, out_scores,
+                        out_counts, (cudaStream_t)stream);
+}
+
+size_t rvo_packed_result_bytes(int32_t nq, int32_t k) {
+    if (nq <= 0 || k <= 0) return 0;
+    return align_up((size_t)nq * k * 12 + (size_t)nq * 4, 8);
+}
+
+int rvo_merge_topk_packed(const void* gathered, int64_t rank_stride_bytes, int32_t G, int32_t nq, int32_t k,
+                          int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream) {
+    RVO_REQUIRE(gathered && out_ids && out_scores && out_counts, "merge_topk_packed: null pointer");
+    RVO_REQUIRE(G >= 1 && nq >= 1 && k >= 1 && (long long)G * k <= 4096, "merge_topk_packed: need G*k <= 4096 (G=%d k=%d)",
+                G, k);
+    RVO_REQUIRE(rank_stride_bytes >= (int64_t)rvo_packed_result_bytes(nq, k) && rank_stride_bytes % 8 == 0 &&
+                    ((uintptr_t)gathered & 7) == 0,
+                "merge_topk_packed: bad stride/alignment");
+    int rc = select_device_of(gathered, nullptr);
+    if (rc) return rc;
+    const char* base = (const char*)gathered;
+    const int64_t* ids = (const int64_t*)base;
+    const float* scores = (const float*)(base + (size_t)nq * k * 8);
+    const int32_t* counts = (const int32_t*)(base + (size_t)nq * k * 12);
+    return launch_merge(ids, scores, counts, rank_stride_bytes / 8, rank_stride_bytes / 4, rank_stride_bytes / 4, G, nq, k,
+                        out_ids, out_scores, out_counts, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// Shared host/device helpers for the revers-o B200 hot-path library.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/revers_o_b200.h"
+
+namespace rvo {
+
+// ---- error plumbing (thread-local text behind rvo_last_error) --------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define RVO_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            rvo::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                           __LINE__);                                                         \
+            return RVO_E_CUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+#define RVO_REQUIRE(cond, ...)          \
+    do {                                \
+        if (!(cond)) {                  \
+            rvo::set_error(__VA_ARGS__); \
+            return RVO_E_INVALID;       \
+        }                               \
+    } while (0)
+
+// every kernel launch of the library goes through this so that bench.py's gpu_launches is a count
+#define RVO_LAUNCHED()                                  \
+    do {                                                \
+        rvo::g_launches.fetch_add(1);                   \
+        RVO_CUDA(cudaGetLastError());                   \
+    } while (0)
+
+int select_device_of(const void* dev_ptr, int* sm_count);
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace
+struct Arena {
+    char* base;
+    size_t size, off;
+    Arena(void* p, size_t n) : base((char*)p), size(n), off(0) {}
+    template <typename T>
+    T* take(size_t count, size_t align = 256) {
+        off = align_up(off, align);
+        T* r = (T*)(base ? base + off : nullptr);
+        off += count * sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= size; }
+};
+
+// ---- ordering keys -----------------------------------------------------------------------------
+// 64-bit key = (orderable(score) << 32) | (0xFFFFFFFF - row): a DESCENDING sort of keys is
+// score-descending with ties broken by LOWER row.  Key 0 is "empty" (below every real key).
+__host__ __device__ __forceinline__ uint32_t f32_orderable(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    uint32_t b;
+    memcpy(&b, &f, 4);
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float orderable_f32(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+__host__ __device__ __forceinline__ unsigned long long make_key(float score, uint32_t row) {
+    return ((unsigned long long)f32_orderable(score) << 32) | (unsigned long long)(0xFFFFFFFFu - row);
+}
+__host__ __device__ __forceinline__ float key_score(unsigned long long k) { return orderable_f32((uint32_t)(k >> 32)); }
+__host__ __device__ __forceinline__ uint32_t key_row(unsigned long long k) { return 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFu); }
+
+// eps = 2^-8 bounds |<bf16(q),d> - <q,d>| for unit q, |d| <= 1 (||q - bf16(q)|| <= 2^-8 ||q||).
+// If t(k) is the k-th best TENSOR score of any subset, every item of the true top-k (ranked by the
+// fp32 re-score f) has f >= t(k) - eps, hence tensor score >= t(k) - 2 eps.  Thresholds taken from
+// tensor-core scores are therefore lowered by 2 eps (+ fp32 accumulation slack) so that no true
+// top-k item can be filtered out.
+constexpr float kBf16QueryMargin = 0.008f;
+
+}  // namespace rvo

@@ -1,0 +1,214 @@
+// (1) Row L2-normalisation (ingest / query preparation) and
+// (2) the exact fp32 CUDA-core scan for batches of <= RVO_SMALL_Q queries — the reference's own
+//     operating point (Q = 1, core_system.py:657): scores[q, r] = <q_hat, db[r]>, fp32 FMA over the
+//     bf16 DB rows, written densely (4 B per 2 KB row read: <0.2 % extra traffic); HBM-bound.
+#include "common.cuh"
+#include "prep_scan_small.cuh"
+
+namespace rvo {
+
+// one warp per row: x / ||x||  (core_system.py:407,447; qdrant COSINE upsert/search normalisation)
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ src, long long n, int d,
+                                                             long long src_ld, uint16_t* __restrict__ dst_bf16,
+                                                             long long dst_ld, float* __restrict__ dst_f32,
+                                                             long long f32_ld) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* s = src + (size_t)row * (size_t)src_ld;
+    float ss = 0.f;
+    for (int i = lane; i < d; i += 32) {
+        const float v = s[i];
+        ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    const float nrm = sqrtf(ss);
+    const float inv = nrm != 0.f ? 1.0f / nrm : 0.f;  // zero rows stay zero
+    if (dst_bf16) {
+        uint16_t* o = dst_bf16 + (size_t)row * (size_t)dst_ld;
+        for (long long i = lane; i < dst_ld; i += 32) {
+            const float v = i < d ? s[i] * inv : 0.f;
+            o[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+        }
+    }
+    if (dst_f32) {
+        float* o = dst_f32 + (size_t)row * (size_t)f32_ld;
+        for (long long i = lane; i < f32_ld; i += 32) o[i] = i < d ? s[i] * inv : 0.f;
+    }
+}
+
+int launch_normalize_rows(const float* src, long long n, int d, long long src_ld, uint16_t* dst_bf16, long long dst_ld,
+                          float* dst_f32, long long f32_ld, cudaStream_t stream) {
+    if (n <= 0) return RVO_OK;
+    const long long blocks = (n + 7) / 8;
+    normalize_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, n, d, src_ld, dst_bf16, dst_ld, dst_f32, f32_ld);
+    RVO_LAUNCHED();
+    return RVO_OK;
+}
+
+// ---- small-Q scan --------------------------------------------------------------------------------
+// One warp per pair of DB rows; lane l owns the 16-byte chunks l, l+32, ... of a row, and keeps the
+// matching slices of all NQ queries in registers (no shared-memory traffic in the loop).
+template <int NQ, int CPL>
+__global__ void __launch_bounds__(256) scan_small_kernel(const uint4* __restrict__ db, long long n_rows,
+                                                         long long ld_u4, int nchunks, const float* __restrict__ qn,
+                                                         long long qn_ld, float* __restrict__ out, long long out_ld) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+
+    float qr[NQ][CPL][8];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int idx = lane + 32 * c;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) qr[q][c][i] = idx < nchunks ? qn[(size_t)q * qn_ld + idx * 8 + i] : 0.f;
+        }
+
+    for (long long r0 = gw * 2; r0 < n_rows; r0 += nw * 2) {
+        const bool two = r0 + 1 < n_rows;
+        uint4 a[2][CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int idx = lane + 32 * c;
+            a[0][c] = make_uint4(0, 0, 0, 0);
+            a[1][c] = make_uint4(0, 0, 0, 0);
+            if (idx < nchunks) {
+                a[0][c] = __ldcs(db + (size_t)r0 * ld_u4 + idx);
+                if (two) a[1][c] = __ldcs(db + (size_t)(r0 + 1) * ld_u4 + idx);
+            }
+        }
+        float acc[2][NQ];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) acc[r][q] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const uint32_t w[4] = {a[r][c].x, a[r][c].y, a[r][c].z, a[r][c].w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const float lo = __uint_as_float(w[h] << 16);
+                    const float hi = __uint_as_float(w[h] & 0xFFFF0000u);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        acc[r][q] = fmaf(lo, qr[q][c][2 * h], acc[r][q]);
+                        acc[r][q] = fmaf(hi, qr[q][c][2 * h + 1], acc[r][q]);
+                    }
+                }
+            }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                float v = acc[r][q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                acc[r][q] = v;
+            }
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                out[(size_t)q * out_ld + r0] = acc[0][q];
+                if (two) out[(size_t)q * out_ld + r0 + 1] = acc[1][q];
+            }
+        }
+    }
+}
+
+// Any row length: queries live in shared memory (slower; rows longer than 2048 elements only).
+__global__ void __launch_bounds__(256) scan_small_generic_kernel(const uint4* __restrict__ db, long long n_rows,
+                                                                 long long ld_u4, int nchunks, int nq,
+                                                                 const float* __restrict__ qn, long long qn_ld,
+                                                                 float* __restrict__ out, long long out_ld) {
+    extern __shared__ float sq[];  // [nq][nchunks*8]
+    const int dq = nchunks * 8;
+    for (int i = threadIdx.x; i < nq * dq; i += blockDim.x) sq[i] = qn[(size_t)(i / dq) * qn_ld + (i % dq)];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = gw; r < n_rows; r += nw) {
+        float acc[RVO_SMALL_Q];
+#pragma unroll
+        for (int q = 0; q < RVO_SMALL_Q; ++q) acc[q] = 0.f;
+        for (int c = lane; c < nchunks; c += 32) {
+            const uint4 v = __ldcs(db + (size_t)r * ld_u4 + c);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < RVO_SMALL_Q; ++q)
+                if (q < nq) {
+                    const float* qq = sq + q * dq + c * 8;
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        acc[q] = fmaf(__uint_as_float(w[h] << 16), qq[2 * h], acc[q]);
+                        acc[q] = fmaf(__uint_as_float(w[h] & 0xFFFF0000u), qq[2 * h + 1], acc[q]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int q = 0; q < RVO_SMALL_Q; ++q) {
+            float v = acc[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            if (lane == 0 && q < nq) out[(size_t)q * out_ld + r] = v;
+        }
+    }
+}
+
+template <int NQ, int CPL>
+static int launch_small_t(const uint16_t* db, long long n_rows, long long db_ld, int d_pad, const float* qn,
+                          long long qn_ld, float* out, long long out_ld, int sm_count, cudaStream_t stream) {
+    int per_sm = 0;
+    RVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_small_kernel<NQ, CPL>, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    long long want = (n_rows + 15) / 16;  // 8 warps x 2 rows per block per iteration
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > want) grid = want;
+    scan_small_kernel<NQ, CPL><<<(unsigned)grid, 256, 0, stream>>>((const uint4*)db, n_rows, db_ld / 8, d_pad / 8, qn,
+                                                                  qn_ld, out, out_ld);
+    RVO_LAUNCHED();
+    return RVO_OK;
+}
+
+// nq in 1..RVO_SMALL_Q; qn rows beyond nq (up to the instantiated NQ) must exist and be zero.
+int launch_scan_small(const uint16_t* db, long long n_rows, long long db_ld, int d_pad, const float* qn, long long qn_ld,
+                      int nq, float* out, long long out_ld, int sm_count, cudaStream_t stream) {
+    if (n_rows <= 0) return RVO_OK;
+    const int cpl = (d_pad / 8 + 31) / 32;
+#define RVO_SMALL_CASE(NQ_, CPL_)                                                                          \
+    return launch_small_t<NQ_, CPL_>(db, n_rows, db_ld, d_pad, qn, qn_ld, out, out_ld, sm_count, stream)
+    if (cpl <= 4) {
+        if (nq == 1) RVO_SMALL_CASE(1, 4);
+        if (nq == 2) RVO_SMALL_CASE(2, 4);
+        RVO_SMALL_CASE(4, 4);
+    }
+    if (cpl == 5) {
+        if (nq == 1) RVO_SMALL_CASE(1, 5);
+        if (nq == 2) RVO_SMALL_CASE(2, 5);
+        RVO_SMALL_CASE(4, 5);
+    }
+#undef RVO_SMALL_CASE
+    // long rows: generic kernel
+    const size_t smem = (size_t)nq * d_pad * 4;
+    if (smem > 200 * 1024) {
+        set_error("scan_small: row length %d too large", d_pad);
+        return RVO_E_INVALID;
+    }
+    if (smem > 48 * 1024)
+        RVO_CUDA(cudaFuncSetAttribute(scan_small_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = (long long)sm_count * 4;
+    long long want = (n_rows + 7) / 8;
+    if (grid > want) grid = want;
+    scan_small_generic_kernel<<<(unsigned)grid, 256, smem, stream>>>((const uint4*)db, n_rows, db_ld / 8, d_pad / 8, nq, qn,
+                                                                    qn_ld, out, out_ld);
+    RVO_LAUNCHED();
+    return RVO_OK;
+}
+
+}  // namespace rvo

@@ -1,0 +1,413 @@
+// K2 — query x database scoring on tcgen05 tensor cores with the threshold select fused in the
+// epilogue.  Replaces the `vectors @ query` + argsort of qdrant-local search behind
+// core_system.py:659-664 for batches of more than RVO_SMALL_Q queries.
+//
+// Roles inside one persistent CTA (192 threads, one CTA per SM):
+//   warp 0 (one elected lane)  TMA producer: DB sub-tiles (128 rows x 64 k, 128B-swizzled) and, unless
+//                              the query block is resident, the query k-chunk, into a smem stage ring
+//   warp 1 (one elected lane)  tcgen05.mma issuer: D[128 rows x NQ] += A(db) * B(queries)^T, fp32
+//                              accumulators in TMEM slots (ring of 512/NQ slots)
+//   warps 2-5                  epilogue: tcgen05.ld one TMEM lane (= one DB row) per thread,
+//                                FILTER: compare the row's NQ scores with the per-query thresholds tau
+//                                        (smem broadcast), queue survivors in smem, then append them
+//                                        as ordering keys to the per-query candidate lists in HBM;
+//                                DENSE : write the scores (threshold-seeding pass over a strided sample).
+// The full score matrix never reaches HBM in FILTER mode.
+//
+// Layout choice: DB rows are the MMA M dimension (TMEM lanes), queries the N dimension
+// (TMEM columns), so that (a) a small query batch costs no padded smem traffic and can stay RESIDENT
+// in smem for the whole scan (HBM-bound regime: smem fill == DB bytes), and (b) `m_sub` DB sub-tiles
+// share one query k-chunk per stage (tensor-bound regime: halves the L2->smem query traffic).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "scan_tc.cuh"
+
+namespace rvo {
+
+using namespace ptx;
+
+template <int MODE>
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constant__ CUtensorMap tmap_q,
+               const ScanParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+    uint8_t* s_res = smem;                                   // resident query block (optional)
+    uint8_t* s_stages = smem + p.off_stages;                 // stage ring
+    unsigned long long* s_queue = (unsigned long long*)(smem + p.off_queue);  // [kQueueCap][128]
+    float* s_tau = (float*)(smem + p.off_tau);               // [4 warps][256]
+    uint64_t* s_bars = (uint64_t*)(smem + p.off_bars);
+    uint64_t* bar_full = s_bars;                             // [kMaxStages] TMA -> MMA
+    uint64_t* bar_empty = s_bars + kMaxStages;               // [kMaxStages] MMA -> TMA
+    uint64_t* bar_tfull = s_bars + 2 * kMaxStages;           // [kMaxSlots]  MMA -> epilogue
+    uint64_t* bar_tempty = s_bars + 2 * kMaxStages + kMaxSlots;  // [kMaxSlots] epilogue -> MMA
+    uint64_t* bar_res = s_bars + 2 * kMaxStages + 2 * kMaxSlots;
+    uint32_t* s_tmem = (uint32_t*)(bar_res + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_k = p.d_pad / kBlockK;
+    const int nq_blk = p.nq_blk;
+    const int m_sub = p.m_sub;
+    const uint32_t q_chunk_bytes = (uint32_t)nq_blk * 128u;
+    const long long total_work = p.num_super * (long long)p.num_qblk;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kMaxStages; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], 1);
+        }
+        for (int i = 0; i < kMaxSlots; ++i) {
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], 4);  // lane 0 of each epilogue warp
+        }
+        mbar_init(bar_res, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_db);
+        prefetch_tmap(&tmap_q);
+    }
+    if (warp == 1) {
+        tmem_alloc(s_tmem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            const uint64_t hint_db = (p.num_qblk > 1) ? kEvictNormal : kEvictFirst;
+            if (p.resident_q) {
+                mbar_expect_tx(bar_res, (uint32_t)num_k * q_chunk_bytes);
+                for (int kc = 0; kc < num_k; ++kc)
+                    tma_load_2d(&tmap_q, bar_res, s_res + (size_t)kc * q_chunk_bytes, kc * kBlockK, 0, kEvictLast);
+            }
+            uint32_t stage = 0, phase = 0;
+            for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const long long st = w / p.num_qblk;
+                const int qb = (int)(w - st * p.num_qblk);
+                const long long row0 = st * (long long)(kBlockM * m_sub);
+                long long left = (p.n_rows - row0 + kBlockM - 1) / kBlockM;
+                const int m_valid = left < m_sub ? (int)left : m_sub;
+                const uint32_t bytes = (uint32_t)m_valid * kSubTileBytes + (p.resident_q ? 0u : q_chunk_bytes);
+                for (int kc = 0; kc < num_k; ++kc) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&bar_full[stage], bytes);
+                    uint8_t* sA = s_stages + (size_t)stage * p.stage_bytes;
+                    for (int j = 0; j < m_valid; ++j)
+                        tma_load_2d(&tmap_db, &bar_full[stage], sA + j * kSubTileBytes, kc * kBlockK,
+                                    (int)(row0 + j * kBlockM), hint_db);
+                    if (!p.resident_q)
+                        tma_load_2d(&tmap_q, &bar_full[stage], sA + m_sub * kSubTileBytes, kc * kBlockK, qb * nq_blk,
+                                    kEvictLast);
+                    if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)nq_blk);
+            const uint32_t ns = (uint32_t)p.num_slots;
+            if (p.resident_q) {
+                mbar_wait(bar_res, 0);
+                tc_fence_after();
+            }
+            uint32_t stage = 0, phase = 0, acc = 0;
+            for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const long long st = w / p.num_qblk;
+                const long long row0 = st * (long long)(kBlockM * m_sub);
+                long long left = (p.n_rows - row0 + kBlockM - 1) / kBlockM;
+                const int m_valid = left < m_sub ? (int)left : m_sub;
+                for (int kc = 0; kc < num_k; ++kc) {
+                    mbar_wait(&bar_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(s_stages + (size_t)stage * p.stage_bytes);
+                    const uint32_t sB = p.resident_q ? smem_u32(s_res + (size_t)kc * q_chunk_bytes)
+                                                     : sA + (uint32_t)m_sub * kSubTileBytes;
+                    for (int j = 0; j < m_valid; ++j) {
+                        const uint32_t pos = acc + (uint32_t)j;
+                        const uint32_t slot = pos % ns;
+                        if (kc == 0) {
+                            mbar_wait(&bar_tempty[slot], ((pos / ns) & 1u) ^ 1u);
+                            tc_fence_after();
+                        }
+                        const uint32_t d_tmem = tmem_base + slot * (uint32_t)p.slot_w;
+                        const uint32_t a0 = sA + (uint32_t)j * kSubTileBytes;
+#pragma unroll
+                        for (int k4 = 0; k4 < kBlockK / 16; ++k4)
+                            umma_bf16(d_tmem, make_kmajor_sw128_desc(a0 + k4 * 32), make_kmajor_sw128_desc(sB + k4 * 32),
+                                      idesc, (uint32_t)((kc | k4) != 0));
+                    }
+                    umma_commit(&bar_empty[stage]);  // frees the smem stage once these MMAs retire
+                    if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+                }
+                for (int j = 0; j < m_valid; ++j) umma_commit(&bar_tfull[(acc + (uint32_t)j) % ns]);
+                acc += (uint32_t)m_valid;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int ew = warp & 3;  // TMEM lane quarter this warp may read
+        const uint32_t lane_base = (uint32_t)ew * 32u;
+        const int et = ew * 32 + lane;  // 0..127 : epilogue thread == TMEM lane == DB row in sub-tile
+        float* tau_w = s_tau + ew * 256;
+        const uint32_t ns = (uint32_t)p.num_slots;
+        const int nchunks = nq_blk / 16;
+        uint32_t acc = 0;
+        int cur_qb = -1;
+
+        for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const long long st = w / p.num_qblk;
+            const int qb = (int)(w - st * p.num_qblk);
+            const long long row0 = st * (long long)(kBlockM * m_sub);
+            long long left = (p.n_rows - row0 + kBlockM - 1) / kBlockM;
+            const int m_valid = left < m_sub ? (int)left : m_sub;
+            const int q0 = qb * nq_blk;
+
+            if (MODE == kModeFilter && qb != cur_qb) {
+                __syncwarp();
+                for (int i = lane; i < nq_blk; i += 32) tau_w[i] = p.tau[q0 + i];
+                __syncwarp();
+                cur_qb = qb;
+            }
+
+            for (int j = 0; j < m_valid; ++j) {
+                const uint32_t pos = acc + (uint32_t)j;
+                const uint32_t slot = pos % ns;
+                mbar_wait(&bar_tfull[slot], (pos / ns) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (lane_base << 16) + slot * (uint32_t)p.slot_w;
+                const long long row = row0 + (long long)j * kBlockM + et;
+                const bool valid = row < p.n_rows;
+
+                if (MODE == kModeDense) {
+                    for (int c = 0; c < nchunks; ++c) {
+                        uint32_t v[16];
+                        __syncwarp();
+                        tmem_ld_x16(taddr + (uint32_t)c * 16u, v);
+                        tmem_ld_wait();
+                        if (valid) {
+                            float* o = p.dense + (size_t)(q0 + c * 16) * (size_t)p.dense_ld + (size_t)row;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[(size_t)i * (size_t)p.dense_ld] = __uint_as_float(v[i]);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_tempty[slot]);
+                } else {
+                    int n = 0;
+                    const uint32_t key_row_bits = 0xFFFFFFFFu - (uint32_t)(row * p.row_stride);
+                    // Append queued survivors (score, query column) of this row to the candidate lists.
+                    auto flush = [&](int cnt) {
+                        for (int e = 0; e < cnt; e += 4) {
+                            int slot_pos[4];
+                            unsigned long long ent[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (e + u < cnt) {
+                                    ent[u] = s_queue[(e + u) * 128 + et];
+                                    slot_pos[u] = atomicAdd(p.cand_cnt + q0 + (int)(ent[u] & 0xFFFFu), 1);
+                                }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (e + u < cnt && slot_pos[u] < p.cap) {
+                                    const int q = q0 + (int)(ent[u] & 0xFFFFu);
+                                    const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(ent[u] >> 32)));
+                                    p.cand[(size_t)q * (size_t)p.cap + (size_t)slot_pos[u]] =
+                                        ((unsigned long long)ob << 32) | (unsigned long long)key_row_bits;
+                                }
+                        }
+                    };
+                    for (int c = 0; c < nchunks; ++c) {
+                        uint32_t v[16];
+                        __syncwarp();
+                        tmem_ld_x16(taddr + (uint32_t)c * 16u, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (n > kQueueCap - 8) {  // rare: keep room for 8 more
+                                flush(n);
+                                n = 0;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int col = c * 16 + h * 8 + i;
+                                const float s = __uint_as_float(v[h * 8 + i]);
+                                if (valid && s >= tau_w[col]) {
+                                    s_queue[n * 128 + et] = ((unsigned long long)v[h * 8 + i] << 32) | (unsigned)col;
+                                    ++n;
+                                }
+                            }
+                        }
+                    }
+                    // TMEM slot is drained: hand it back before paying the atomics' latency.
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_tempty[slot]);
+                    if (n > 0) flush(n);
+                }
+            }
+            acc += (uint32_t)m_valid;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: planning, tensor maps, launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)f;
+    }
+    return fn;
+}
+
+// bf16 [rows, d_pad] matrix viewed through rows `row_stride` apart; box = 64 elements x box_rows.
+static int make_tmap(CUtensorMap* m, const void* base, long long rows, int d_pad, long long pitch_elems,
+                     int box_rows, bool promote) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return RVO_E_NO_DEVICE;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)pitch_elems * 2ull};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     promote ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld d_pad=%d pitch=%lld box_rows=%d", (int)r, rows, d_pad,
+                  pitch_elems, box_rows);
+        return RVO_E_CUDA;
+    }
+    return RVO_OK;
+}
+
+int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl) {
+    if (nq < 1 || d_pad < kBlockK || d_pad % kBlockK != 0) {
+        set_error("plan_scan_tc: bad nq=%d d_pad=%d", nq, d_pad);
+        return RVO_E_INVALID;
+    }
+    const int nq16 = (nq + 15) / 16 * 16;
+    if (nq16 <= 256) {
+        pl->num_qblk = 1;
+        pl->nq_blk = nq16;
+    } else {
+        pl->num_qblk = (nq + 255) / 256;
+        const int per = (nq + pl->num_qblk - 1) / pl->num_qblk;
+        pl->nq_blk = (per + 15) / 16 * 16;
+    }
+    pl->nq_pad = pl->num_qblk * pl->nq_blk;
+    pl->slot_w = (pl->nq_blk + 31) / 32 * 32;
+    pl->num_slots = 512 / pl->slot_w;
+    if (pl->num_slots > kMaxSlots) pl->num_slots = kMaxSlots;
+
+    const size_t fixed = (size_t)kQueueCap * 128 * 8 + 4 * 256 * 4 + 512;
+    const size_t budget = (size_t)kSmemLimit - 1024 - fixed;
+    const size_t res_bytes = (size_t)pl->nq_blk * d_pad * 2;
+
+    pl->resident = 0;
+    pl->m_sub = 1;
+    if (pl->num_qblk == 1 && res_bytes + 3 * (size_t)kSubTileBytes <= budget && force_m_sub <= 0) pl->resident = 1;
+    if (!pl->resident) {
+        pl->m_sub = 2;
+        if (force_m_sub == 1 || force_m_sub == 2 || force_m_sub == 4) pl->m_sub = force_m_sub;
+        while (pl->m_sub > pl->num_slots) pl->m_sub >>= 1;
+    }
+    pl->stage_bytes = (size_t)pl->m_sub * kSubTileBytes + (pl->resident ? 0 : (size_t)pl->nq_blk * 128);
+    const size_t res = pl->resident ? res_bytes : 0;
+    size_t stages = (budget - res) / pl->stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) {
+        set_error("plan_scan_tc: not enough shared memory (nq_blk=%d d_pad=%d)", pl->nq_blk, d_pad);
+        return RVO_E_INVALID;
+    }
+    pl->num_stages = (int)stages;
+    pl->off_stages = res;  // multiple of 1024: nq_blk % 16 == 0 and d_pad % 64 == 0
+    pl->off_queue = pl->off_stages + stages * pl->stage_bytes;
+    pl->off_tau = pl->off_queue + (size_t)kQueueCap * 128 * 8;
+    pl->off_bars = pl->off_tau + 4 * 256 * 4;
+    pl->smem_bytes = pl->off_bars + 512 + 1024;
+    return RVO_OK;
+}
+
+int launch_scan_tc(int mode, const uint16_t* db, long long n_sample, long long row_stride, long long db_ld, int d_pad,
+                   const uint16_t* q_bf16, const TcPlan& pl, const float* tau, unsigned long long* cand,
+                   int* cand_cnt, int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream) {
+    if (n_sample <= 0) return RVO_OK;
+    if (n_sample >= (1ll << 31) || n_sample * row_stride >= (1ll << 32)) {
+        set_error("launch_scan_tc: shard too large (%lld rows, stride %lld); shard the DB", n_sample, row_stride);
+        return RVO_E_INVALID;
+    }
+    CUtensorMap tm_db, tm_q;
+    int rc = make_tmap(&tm_db, db, n_sample, d_pad, db_ld * row_stride, kBlockM, row_stride == 1);
+    if (rc) return rc;
+    rc = make_tmap(&tm_q, q_bf16, pl.nq_pad, d_pad, d_pad, pl.nq_blk, false);
+    if (rc) return rc;
+
+    ScanParams p;
+    p.n_rows = n_sample;
+    p.row_stride = row_stride;
+    p.d_pad = d_pad;
+    p.nq_blk = pl.nq_blk;
+    p.num_qblk = pl.num_qblk;
+    p.m_sub = pl.m_sub;
+    p.num_stages = pl.num_stages;
+    p.resident_q = pl.resident;
+    p.slot_w = pl.slot_w;
+    p.num_slots = pl.num_slots;
+    p.stage_bytes = (uint32_t)pl.stage_bytes;
+    p.off_stages = (uint32_t)pl.off_stages;
+    p.off_queue = (uint32_t)pl.off_queue;
+    p.off_tau = (uint32_t)pl.off_tau;
+    p.off_bars = (uint32_t)pl.off_bars;
+    p.num_super = (n_sample + (long long)kBlockM * pl.m_sub - 1) / ((long long)kBlockM * pl.m_sub);
+    p.tau = tau;
+    p.cand = cand;
+    p.cand_cnt = cand_cnt;
+    p.cap = cap;
+    p.dense = dense;
+    p.dense_ld = dense_ld;
+
+    const long long total = p.num_super * pl.num_qblk;
+    const int grid = (int)(total < sm_count ? total : sm_count);
+    if (mode == kModeDense) {
+        RVO_CUDA(cudaFuncSetAttribute(scan_tc_kernel<kModeDense>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)pl.smem_bytes));
+        scan_tc_kernel<kModeDense><<<grid, kScanThreads, pl.smem_bytes, stream>>>(tm_db, tm_q, p);
+    } else {
+        RVO_CUDA(cudaFuncSetAttribute(scan_tc_kernel<kModeFilter>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)pl.smem_bytes));
+        scan_tc_kernel<kModeFilter><<<grid, kScanThreads, pl.smem_bytes, stream>>>(tm_db, tm_q, p);
+    }
+    RVO_LAUNCHED();
+    return RVO_OK;
+}
+
+}  // namespace rvo

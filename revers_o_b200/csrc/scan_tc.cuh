@@ -1,0 +1,46 @@
+// Declarations shared between the tcgen05 scan kernel (scan_tc.cu) and the search driver (api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace rvo {
+
+constexpr int kBlockM = 128;                              // DB rows per sub-tile == TMEM lanes
+constexpr int kBlockK = 64;                               // bf16 per k-chunk == one 128-B swizzle span
+constexpr int kSubTileBytes = kBlockM * kBlockK * 2;      // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr int kMaxSlots = 8;
+constexpr int kScanThreads = 192;                         // TMA warp + MMA warp + 4 epilogue warps
+constexpr int kQueueCap = 16;                             // smem survivor queue entries per DB row
+constexpr int kSmemLimit = 232448;                        // 227 KiB opt-in dynamic smem per CTA
+constexpr int kModeDense = 0;
+constexpr int kModeFilter = 1;
+
+struct ScanParams {
+    long long n_rows;      // rows visible through the DB tensor map (sample rows when strided)
+    long long row_stride;  // DB row = sample row * row_stride
+    long long num_super;   // super-tiles of 128*m_sub rows
+    int d_pad, nq_blk, num_qblk, m_sub, num_stages, resident_q, slot_w, num_slots;
+    uint32_t stage_bytes, off_stages, off_queue, off_tau, off_bars;
+    // FILTER
+    const float* tau;              // [nq_pad] per-query admission thresholds
+    unsigned long long* cand;      // [nq_pad][cap] candidate ordering keys
+    int* cand_cnt;                 // [nq_pad]
+    int cap;
+    // DENSE
+    float* dense;                  // [nq_pad][dense_ld]
+    long long dense_ld;
+};
+
+struct TcPlan {
+    int nq_blk, num_qblk, nq_pad, m_sub, num_stages, resident, slot_w, num_slots;
+    size_t stage_bytes, off_stages, off_queue, off_tau, off_bars, smem_bytes;
+};
+
+int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl);
+int launch_scan_tc(int mode, const uint16_t* db, long long n_sample, long long row_stride, long long db_ld, int d_pad,
+                   const uint16_t* q_bf16, const TcPlan& pl, const float* tau, unsigned long long* cand,
+                   int* cand_cnt, int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream);
+
+}  // namespace rvo

@@ -1,0 +1,266 @@
+// Exact selection kernels around the scan: chunked top-K of ordering keys (bitonic, smem),
+// threshold derivation, fp32 re-score + final ordering, and the cross-shard merge (K3).
+// Together they replace the `np.argsort(scores)[::-1]` + threshold walk + `limit` cut of
+// qdrant-local search behind core_system.py:659-664.
+#include "common.cuh"
+#include "select.cuh"
+
+namespace rvo {
+
+// Bitonic sort, descending, n a power of two, keys in shared memory, whole block cooperates.
+__device__ __forceinline__ void bitonic_desc_u64(unsigned long long* s, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int ixj = i | j;
+                const bool desc = (i & k) == 0;
+                const unsigned long long a = s[i], b = s[ixj];
+                if ((a < b) == desc) {
+                    s[i] = b;
+                    s[ixj] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int x) {
+    int p = 2;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// grid (num_chunks, nq): chunk c of query q -> its K best keys, sorted descending, zero padded.
+__global__ void __launch_bounds__(kSelThreads) chunk_topk_kernel(const ChunkTopkArgs a) {
+    __shared__ unsigned long long s[kChunk];
+    const int q = blockIdx.y;
+    const long long c0 = (long long)blockIdx.x * kChunk;
+    long long n = a.n_fixed;
+    if (a.cnt) {
+        const int raw = a.cnt[q];
+        n = raw < a.cap ? raw : a.cap;
+    }
+    long long m = n - c0;
+    if (m > kChunk) m = kChunk;
+    unsigned long long* out = a.out + (size_t)q * (size_t)a.out_ld + (size_t)blockIdx.x * (size_t)a.K;
+    if (m <= 0) {
+        for (int i = threadIdx.x; i < a.K; i += blockDim.x) out[i] = 0ull;
+        return;
+    }
+    const int ns = next_pow2((int)m);
+    if (a.dense) {
+        const float* src = a.dense + (size_t)q * (size_t)a.dense_ld + (size_t)c0;
+        for (int i = threadIdx.x; i < ns; i += blockDim.x)
+            s[i] = i < m ? make_key(src[i], (uint32_t)(c0 + i)) : 0ull;
+    } else {
+        const unsigned long long* src = a.keys + (size_t)q * (size_t)a.keys_ld + (size_t)c0;
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) s[i] = i < m ? src[i] : 0ull;
+    }
+    __syncthreads();
+    bitonic_desc_u64(s, ns);
+    for (int i = threadIdx.x; i < a.K; i += blockDim.x) out[i] = i < ns ? s[i] : 0ull;
+    // The k-th best of ANY subset of the DB is a lower bound of the k-th best of the whole DB, so
+    // admitting `score >= tau` in the next scan level never drops a true top-k item.
+    if (a.tau_out && threadIdx.x == 0 && gridDim.x == 1) {
+        float t = a.tau_floor;
+        if (a.tau_prev && a.tau_prev[q] > t) t = a.tau_prev[q];
+        const unsigned long long key = (a.tau_k - 1) < ns ? s[a.tau_k - 1] : 0ull;
+        if (key) {
+            const float c = key_score(key) - a.tau_margin;
+            if (c > t) t = c;
+        }
+        a.tau_out[q] = t;
+    }
+}
+
+// grid (nq), 256 threads.  `top` holds the K2 best candidates of the query by tensor-core score.
+__global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
+    __shared__ unsigned long long s[1024];
+    __shared__ int s_flag;
+    const int q = blockIdx.x;
+    const int K2 = a.K2;
+    const unsigned long long* src = a.top + (size_t)q * (size_t)a.top_ld;
+    int have_local = 0;
+    for (int i = threadIdx.x; i < K2; i += blockDim.x) {
+        const unsigned long long key = src[i];
+        s[i] = key;
+        have_local += key != 0ull;
+    }
+    // count non-empty keys (they form a prefix because `top` is sorted descending)
+    __shared__ int s_have;
+    if (threadIdx.x == 0) {
+        s_flag = 0;
+        s_have = 0;
+    }
+    __syncthreads();
+    if (have_local) atomicAdd(&s_have, have_local);
+    __syncthreads();
+    const int have = s_have;
+
+    int64_t* oid = a.out_ids + (size_t)q * (size_t)a.k;
+    float* osc = a.out_scores + (size_t)q * (size_t)a.k;
+
+    bool overflow = false;
+    const int raw = a.cnt ? a.cnt[q] : have;
+    if (a.cnt && raw > a.cap) overflow = true;
+    float cut = -__int_as_float(0x7f800000);
+    if (a.rescore && have >= a.k) {
+        cut = key_score(s[a.k - 1]) - a.margin;
+        // K2 list is full, more survivors exist, and the worst kept one is still inside the margin:
+        // a survivor we did not keep could out-rank a kept one after the fp32 re-score.
+        if (have == K2 && raw > K2 && key_score(s[K2 - 1]) >= cut) overflow = true;
+    }
+    if (overflow) {
+        for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
+            oid[i] = -1;
+            osc[i] = -__int_as_float(0x7f800000);
+        }
+        if (threadIdx.x == 0) a.out_counts[q] = -1;
+        return;
+    }
+
+    if (a.rescore) {
+        // fp32 re-score of every kept candidate that can still reach the top-k: one warp per candidate,
+        // fp32 query (normalised) x bf16 DB row, fp32 FMA.
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        const int nchunk = a.d_pad >> 3;
+        const float* qv = a.qn + (size_t)q * (size_t)a.qn_ld;
+        for (int e = warp; e < have; e += nwarps) {
+            const unsigned long long key = s[e];
+            unsigned long long nk = 0ull;
+            if (key_score(key) >= cut) {
+                const uint32_t row = key_row(key);
+                const uint4* r = (const uint4*)(a.db + (size_t)row * (size_t)a.db_ld);
+                float acc = 0.f;
+                for (int c = lane; c < nchunk; c += 32) {
+                    const uint4 v = __ldg(r + c);
+                    const float4 q0 = __ldg((const float4*)(qv + c * 8));
+                    const float4 q1 = __ldg((const float4*)(qv + c * 8 + 4));
+                    acc = fmaf(__uint_as_float(v.x << 16), q0.x, acc);
+                    acc = fmaf(__uint_as_float(v.x & 0xFFFF0000u), q0.y, acc);
+                    acc = fmaf(__uint_as_float(v.y << 16), q0.z, acc);
+                    acc = fmaf(__uint_as_float(v.y & 0xFFFF0000u), q0.w, acc);
+                    acc = fmaf(__uint_as_float(v.z << 16), q1.x, acc);
+                    acc = fmaf(__uint_as_float(v.z & 0xFFFF0000u), q1.y, acc);
+                    acc = fmaf(__uint_as_float(v.w << 16), q1.z, acc);
+                    acc = fmaf(__uint_as_float(v.w & 0xFFFF0000u), q1.w, acc);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+                nk = make_key(acc, row);
+            }
+            __syncwarp();
+            if (lane == 0) s[e] = nk;
+        }
+        __syncthreads();
+        bitonic_desc_u64(s, K2);
+    }
+
+    // emit: first k keys with score >= score_threshold (the walk stops at the first score below it)
+    int n_out_local = 0;
+    for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
+        const unsigned long long key = i < K2 ? s[i] : 0ull;
+        const bool ok = key != 0ull && key_score(key) >= a.score_threshold;
+        oid[i] = ok ? (int64_t)key_row(key) + a.id_offset : -1;
+        osc[i] = ok ? key_score(key) : -__int_as_float(0x7f800000);
+        n_out_local += ok;
+    }
+    if (n_out_local) atomicAdd(&s_flag, n_out_local);
+    __syncthreads();
+    if (threadIdx.x == 0) a.out_counts[q] = s_flag;
+}
+
+// ---- K3: merge of per-shard lists -------------------------------------------------------------
+__device__ __forceinline__ bool before(float sa, long long ia, float sb, long long ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+// per-shard blocks are `*_gs` elements apart (contiguous [G,nq,k] arrays or the packed all-gather buffer)
+__global__ void __launch_bounds__(256) merge_kernel(const int64_t* ids, const float* scores, const int32_t* counts,
+                                                    long long ids_gs, long long scores_gs, long long counts_gs,
+                                                    int G, int nq, int k, int n_pow2, int64_t* out_ids,
+                                                    float* out_scores, int32_t* out_counts) {
+    extern __shared__ unsigned char sm[];
+    long long* sid = (long long*)sm;
+    float* ssc = (float*)(sid + n_pow2);
+    __shared__ int s_total, s_bad;
+    const int q = blockIdx.x;
+    if (threadIdx.x == 0) { s_total = 0; s_bad = 0; }
+    __syncthreads();
+    int local = 0;
+    for (int e = threadIdx.x; e < n_pow2; e += blockDim.x) {
+        float sc = -__int_as_float(0x7f800000);
+        long long id = 0x7FFFFFFFFFFFFFFFll;
+        if (e < G * k) {
+            const int g = e / k, i = e - g * k;
+            const int c = counts[(size_t)g * counts_gs + q];
+            if (c < 0 && i == 0) s_bad = 1;
+            if (i < c) {
+                sc = scores[(size_t)g * scores_gs + (size_t)q * k + i];
+                id = ids[(size_t)g * ids_gs + (size_t)q * k + i];
+                ++local;
+            }
+        }
+        ssc[e] = sc;
+        sid[e] = id;
+    }
+    if (local) atomicAdd(&s_total, local);
+    __syncthreads();
+    for (int kk = 2; kk <= n_pow2; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int ixj = i | j;
+                const bool desc = (i & kk) == 0;
+                const float sa = ssc[i], sb = ssc[ixj];
+                const long long ia = sid[i], ib = sid[ixj];
+                // descending block: element that ranks first must sit at i
+                const bool swap = desc ? before(sb, ib, sa, ia) : before(sa, ia, sb, ib);
+                if (swap) {
+                    ssc[i] = sb; ssc[ixj] = sa;
+                    sid[i] = ib; sid[ixj] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int total = s_total < k ? s_total : k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const bool ok = i < total && !s_bad;
+        out_ids[(size_t)q * k + i] = ok ? sid[i] : -1;
+        out_scores[(size_t)q * k + i] = ok ? ssc[i] : -__int_as_float(0x7f800000);
+    }
+    if (threadIdx.x == 0) out_counts[q] = s_bad ? -1 : total;
+}
+
+// ---- host wrappers ------------------------------------------------------------------------------
+int launch_chunk_topk(const ChunkTopkArgs& a, int num_chunks, int nq, cudaStream_t stream) {
+    if (num_chunks <= 0 || nq <= 0) return RVO_OK;
+    chunk_topk_kernel<<<dim3(num_chunks, nq), kSelThreads, 0, stream>>>(a);
+    RVO_LAUNCHED();
+    return RVO_OK;
+}
+
+int launch_final(const FinalArgs& a, int nq, cudaStream_t stream) {
+    final_kernel<<<nq, 256, 0, stream>>>(a);
+    RVO_LAUNCHED();
+    return RVO_OK;
+}
+
+int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts, long long ids_gs, long long scores_gs,
+                 long long counts_gs, int G, int nq, int k, int64_t* out_ids, float* out_scores, int32_t* out_counts,
+                 cudaStream_t stream) {
+    int n_pow2 = 2;
+    while (n_pow2 < G * k) n_pow2 <<= 1;
+    const size_t smem = (size_t)n_pow2 * 12;
+    if (smem > 48 * 1024)
+        RVO_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_kernel<<<nq, 256, smem, stream>>>(ids, scores, counts, ids_gs, scores_gs, counts_gs, G, nq, k, n_pow2, out_ids,
+                                            out_scores, out_counts);
+    RVO_LAUNCHED();
+    return RVO_OK;
+}
+
+}  // namespace rvo

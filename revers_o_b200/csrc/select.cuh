@@ -1,0 +1,54 @@
+// Declarations of the selection kernels (select.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rvo {
+
+constexpr int kChunk = 4096;      // keys sorted per CTA in shared memory
+constexpr int kSelThreads = 512;
+
+struct ChunkTopkArgs {
+    const float* dense;                 // dense mode: scores [nq][dense_ld]  (keys == nullptr)
+    long long dense_ld;
+    const unsigned long long* keys;     // list mode: keys [nq][keys_ld]
+    long long keys_ld;
+    const int* cnt;                     // per-query element count (clipped to cap) or nullptr
+    int cap;
+    long long n_fixed;                  // element count when cnt == nullptr
+    int K;                              // keys kept per chunk
+    unsigned long long* out;            // [nq][out_ld]; chunk c writes [c*K, c*K+K)
+    long long out_ld;
+    // optional (single-chunk launches only): derive the next admission threshold of query q,
+    //   tau_out[q] = max(tau_prev[q], score(key[tau_k-1]) - tau_margin, tau_floor)
+    float* tau_out;
+    const float* tau_prev;
+    int tau_k;
+    float tau_margin, tau_floor;
+};
+
+struct FinalArgs {
+    const unsigned long long* top;      // [nq][top_ld], first K2 sorted descending
+    long long top_ld;
+    const int* cnt;                     // raw candidate counts (overflow detection) or nullptr
+    int cap, K2, k;
+    float score_threshold, margin;
+    int rescore;                        // 1: keys carry bf16-query tensor scores -> fp32 re-score
+    const uint16_t* db;
+    long long db_ld;
+    int d_pad;
+    const float* qn;                    // normalised fp32 queries [nq][qn_ld], zero padded to d_pad
+    long long qn_ld;
+    long long id_offset;
+    int64_t* out_ids;
+    float* out_scores;
+    int32_t* out_counts;
+};
+
+int launch_chunk_topk(const ChunkTopkArgs& a, int num_chunks, int nq, cudaStream_t stream);
+int launch_final(const FinalArgs& a, int nq, cudaStream_t stream);
+int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts, long long ids_gs, long long scores_gs,
+                 long long counts_gs, int G, int nq, int k, int64_t* out_ids, float* out_scores, int32_t* out_counts,
+                 cudaStream_t stream);
+
+}  // namespace rvo

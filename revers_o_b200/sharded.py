@@ -1,0 +1,83 @@
+"""Row-sharded search across the GPUs of one box.
+
+One process per GPU.  Rank r owns the contiguous rows [lo_r, hi_r) of the DB; queries are replicated;
+every rank scans its shard (K2), the per-shard top-k lists are exchanged with ONE all-gather of a
+packed [ids | scores | counts] blob per rank over NCCL/NVLink, and K3 merges them (every rank
+computes the same answer).  No other collective is on the data path.
+
+`shard_bounds`, `pack_results`, `unpack_results` and `allgather_packed` are backend-agnostic host
+logic (exercised with gloo on CPU in tests/test_sharded_gloo.py); `ShardedIndex.search` is the CUDA
+product path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import check
+
+
+def shard_bounds(n_rows: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous row range of `rank`: first (n_rows % world) ranks get one extra row."""
+    base, extra = divmod(n_rows, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def packed_bytes(nq: int, k: int) -> int:
+    return (nq * k * 12 + nq * 4 + 7) // 8 * 8
+
+
+def pack_results(ids: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """[ids int64 nq*k | scores f32 nq*k | counts int32 nq] as one uint8 blob (pure byte copies)."""
+    nq, k = ids.shape
+    blob = torch.zeros(packed_bytes(nq, k), dtype=torch.uint8, device=ids.device)
+    blob[: nq * k * 8].copy_(ids.contiguous().view(torch.uint8).flatten())
+    blob[nq * k * 8: nq * k * 12].copy_(scores.contiguous().view(torch.uint8).flatten())
+    blob[nq * k * 12: nq * k * 12 + nq * 4].copy_(counts.contiguous().view(torch.uint8).flatten())
+    return blob
+
+
+def unpack_results(gathered: torch.Tensor, nq: int, k: int):
+    """gathered uint8 [G, packed_bytes] -> (ids [G,nq,k], scores [G,nq,k], counts [G,nq]) (copies)."""
+    G = gathered.shape[0]
+    ids = gathered[:, : nq * k * 8].contiguous().view(torch.int64).view(G, nq, k)
+    scores = gathered[:, nq * k * 8: nq * k * 12].contiguous().view(torch.float32).view(G, nq, k)
+    counts = gathered[:, nq * k * 12: nq * k * 12 + nq * 4].contiguous().view(torch.int32).view(G, nq)
+    return ids, scores, counts
+
+
+def allgather_packed(blob: torch.Tensor, group=None) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    out = torch.empty((world, blob.numel()), dtype=torch.uint8, device=blob.device)
+    dist.all_gather_into_tensor(out.view(-1), blob, group=group)
+    return out
+
+
+class ShardedIndex:
+    """The local shard of a row-sharded bf16 DB plus the exchange/merge step."""
+
+    def __init__(self, local_db: torch.Tensor, n_local: int, d: int, id_offset: int, group=None):
+        ops.require_cuda(local_db, "local_db")
+        self.db, self.n_local, self.d, self.id_offset, self.group = local_db, int(n_local), int(d), int(id_offset), group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def search_local(self, queries: torch.Tensor, k: int, score_threshold=None):
+        return ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset)
+
+    def search(self, queries: torch.Tensor, k: int, score_threshold=None):
+        """queries: f32 [Q, d] on this rank's GPU (replicated).  Returns merged (ids, scores, counts)."""
+        ids, scores, counts = self.search_local(queries, k, score_threshold)
+        if self.world == 1:
+            return ids, scores, counts
+        nq = queries.shape[0]
+        gathered = allgather_packed(pack_results(ids, scores, counts), self.group)
+        oi = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+        os_ = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+        oc = torch.empty((nq,), dtype=torch.int32, device=queries.device)
+        check(_lib.load().rvo_merge_topk_packed(gathered.data_ptr(), gathered.stride(0), self.world, nq, k, oi.data_ptr(),
+                                                os_.data_ptr(), oc.data_ptr(),
+                                                torch.cuda.current_stream(queries.device).cuda_stream),
+              "rvo_merge_topk_packed")
+        return oi, os_, oc

@@ -1,0 +1,82 @@
+"""Synthetic workloads of the BASELINE.json shapes.  Input generation only — torch ops here
+produce TEST/BENCH INPUTS (random unit vectors, planted neighbours, rectangle masks); none of this is on
+the product path.
+
+Search DB: rows x ~ N(0, I_D), L2-normalised in fp32, rounded to bf16 (the DB is defined as its bf16
+values).  Random unit vectors in 1024-d all score ~0 +- 0.03 against a query, so for each query `n_plant`
+near neighbours `a*q + sqrt(1-a^2)*n_perp` with `a` spread over [0.5, 0.99] are planted at random rows to
+make the top-k non-degenerate.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def make_queries(nq: int, d: int, seed: int = 7, device="cpu") -> torch.Tensor:
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    q = torch.randn((nq, d), generator=g, dtype=torch.float32)
+    q = q / q.norm(dim=1, keepdim=True)
+    # queries are handed over UN-normalised (scaled) on purpose: the path must normalise them
+    scale = 0.5 + torch.rand((nq, 1), generator=g)
+    return (q * scale).to(device)
+
+
+def make_db(n: int, d: int, queries: torch.Tensor | None = None, n_plant: int = 128, seed: int = 1000,
+            device="cpu", chunk: int = 1 << 18) -> torch.Tensor:
+    """bf16 [n, d_pad] (d_pad = d rounded up to 64, zero padded), generated on `device` chunk by chunk."""
+    d_pad = (d + 63) // 64 * 64
+    dev = torch.device(device)
+    db = torch.zeros((n, d_pad), dtype=torch.bfloat16, device=dev)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        x = torch.randn((hi - lo, d), generator=g, dtype=torch.float32, device=dev)
+        x = x / x.norm(dim=1, keepdim=True)
+        db[lo:hi, :d] = x.to(torch.bfloat16)
+    if queries is not None and n_plant > 0 and n > 0:
+        nq = queries.shape[0]
+        qn = (queries.float() / queries.float().norm(dim=1, keepdim=True)).to(dev)
+        gp = torch.Generator(device="cpu").manual_seed(seed + 1)
+        per = min(n_plant, max(1, n // max(nq, 1)))
+        rows = torch.randperm(n, generator=gp)[: nq * per].view(nq, per).to(dev)
+        alpha = torch.linspace(0.5, 0.99, per, device=dev).view(1, per, 1)
+        for lo in range(0, nq, 64):
+            hi = min(nq, lo + 64)
+            noise = torch.randn((hi - lo, per, d), generator=g, dtype=torch.float32, device=dev)
+            qq = qn[lo:hi].unsqueeze(1)
+            noise = noise - (noise * qq).sum(-1, keepdim=True) * qq
+            noise = noise / noise.norm(dim=-1, keepdim=True)
+            v = alpha * qq + torch.sqrt(1 - alpha * alpha) * noise
+            v = v / v.norm(dim=-1, keepdim=True)
+            db[rows[lo:hi].reshape(-1), :d] = v.reshape(-1, d).to(torch.bfloat16)
+    return db
+
+
+def make_maskpool_inputs(B: int, M: int, grid: int, D: int, seed: int = 11, device="cpu", n_empty: int = 2):
+    """cfg3: feats [B, grid*grid, D] ~ N(0,1) bf16 (stand-in for random-init PE patch features), masks
+    [B, M, grid*grid] uint8 random axis-aligned rectangles with area fraction ~ U(0.02, 0.30); `n_empty`
+    regions per image are forced empty to exercise the skip (core_system.py:402-404)."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    P = grid * grid
+    feats = torch.randn((B, P, D), generator=g, dtype=torch.float32, device=dev).to(torch.bfloat16)
+    rs = np.random.RandomState(seed)
+    masks = np.zeros((B, M, grid, grid), dtype=np.uint8)
+    frac = rs.uniform(0.02, 0.30, size=(B, M))
+    aspect = rs.uniform(0.5, 2.0, size=(B, M))
+    h = np.clip(np.round(np.sqrt(frac * P * aspect)), 1, grid).astype(int)
+    w = np.clip(np.round(frac * P / h), 1, grid).astype(int)
+    y0 = (rs.uniform(size=(B, M)) * (grid - h + 1)).astype(int)
+    x0 = (rs.uniform(size=(B, M)) * (grid - w + 1)).astype(int)
+    for b in range(B):
+        empty = set(rs.choice(M, size=min(n_empty, M), replace=False).tolist()) if n_empty else set()
+        for m in range(M):
+            if m in empty:
+                continue
+            masks[b, m, y0[b, m]: y0[b, m] + h[b, m], x0[b, m]: x0[b, m] + w[b, m]] = 1
+    return feats, torch.from_numpy(masks.reshape(B, M, P)).to(dev)
+
+
+def bf16_to_f32_numpy(t: torch.Tensor) -> np.ndarray:
+    return t.detach().float().cpu().numpy()

@@ -1,0 +1,309 @@
+"""B200VectorDB — the object `SimpleReverso.vector_db` holds instead of `QdrantClient(path=...)`.
+
+It duck-types exactly the five qdrant-client methods core_system.py uses:
+  QdrantClient(path=str)                         core_system.py:100,521
+  .get_collections().collections[i].name         core_system.py:104-107
+  .recreate_collection(collection_name, vectors_config=VectorParams(size, distance=COSINE))   :600-603
+  .upsert(collection_name, points=[PointStruct(id, vector, payload)])                          :621
+  .search(collection_name, query_vector, limit, score_threshold) -> [obj(.score,.payload)]     :659-664
+plus the batched entry point `search_batch` (new; reduces to `search` row by row).
+
+Vectors live on the GPU as an L2-normalised bf16 matrix [capacity, d_pad] (the DB is DEFINED as its
+bf16 values); ids (uuid strings) and payload dicts stay in host lists indexed by row.  All arithmetic
+(normalise, scan, select, re-score) runs in the CUDA library; there is no CPU fallback.
+
+On-disk format: <path>/meta.json + <path>/<collection>.bf16 (raw row-major
+[n, d_pad] bf16, mmap-able, loadable shard-wise) + <path>/<collection>.payload.jsonl.
+"""
+from __future__ import annotations
+
+import json
+import os
+import threading
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Any, Iterable
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import RVO_MAX_K, RvoError
+
+
+class Distance:
+    COSINE = "Cosine"
+
+
+@dataclass
+class VectorParams:
+    size: int
+    distance: str = Distance.COSINE
+
+
+@dataclass
+class PointStruct:
+    id: Any
+    vector: Any
+    payload: dict | None = None
+
+
+@dataclass
+class ScoredPoint:
+    """What core_system.py:671-676 consumes: `.payload` (dict) and `.score` (float)."""
+    id: Any
+    version: int
+    score: float
+    payload: dict | None
+    vector: Any = None
+
+
+# `from qdrant_client.http import models` replacement: models.VectorParams / Distance / PointStruct
+models = SimpleNamespace(Distance=Distance, VectorParams=VectorParams, PointStruct=PointStruct,
+                         ScoredPoint=ScoredPoint)
+
+
+class _Collection:
+    def __init__(self, name: str, dim: int, device: torch.device):
+        self.name, self.dim, self.device = name, int(dim), device
+        self.d_pad = ops.d_pad_of(self.dim)
+        self.n = 0
+        self.vectors = torch.zeros((0, self.d_pad), dtype=torch.bfloat16, device=device)
+        self.ids: list = []
+        self.payloads: list = []
+        self.row_of: dict = {}
+
+    def reserve(self, rows: int) -> None:
+        if rows <= self.vectors.shape[0]:
+            return
+        cap = max(rows, int(self.vectors.shape[0] * 1.5), 1024)
+        new = torch.zeros((cap, self.d_pad), dtype=torch.bfloat16, device=self.device)
+        if self.n:
+            new[: self.n].copy_(self.vectors[: self.n])  # device-to-device memcpy, no arithmetic
+        self.vectors = new
+
+
+class B200VectorDB:
+    def __init__(self, path: str | None = None, device: str | torch.device | None = None, **_):
+        if not torch.cuda.is_available():
+            raise RvoError("B200VectorDB needs a CUDA (sm_100) device: there is no CPU fallback")
+        self.path = path
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._lock = threading.RLock()  # Gradio callbacks share one instance across threads (ui.py:20)
+        self._collections: dict[str, _Collection] = {}
+        self._staging: dict = {}
+        if path and os.path.exists(os.path.join(path, "meta.json")):
+            self._load(path)
+
+    # ---- qdrant-client surface ---------------------------------------------------------------
+    def get_collections(self):
+        with self._lock:
+            return SimpleNamespace(collections=[SimpleNamespace(name=n) for n in self._collections])
+
+    def recreate_collection(self, collection_name: str, vectors_config: VectorParams | None = None, **kw):
+        size = vectors_config.size if vectors_config is not None else kw["size"]
+        distance = getattr(vectors_config, "distance", Distance.COSINE)
+        if str(getattr(distance, "value", distance)).lower() != "cosine":
+            raise RvoError("only Distance.COSINE is supported (the reference uses no other, core_system.py:602)")
+        with self._lock:
+            self._collections[collection_name] = _Collection(collection_name, size, self.device)
+        return True
+
+    def upsert(self, collection_name: str, points: Iterable):
+        """Normalise (qdrant COSINE semantics) and append/overwrite rows.  `vector` may be a python list
+        (core_system.py:608), a numpy array or a torch tensor."""
+        with self._lock:
+            c = self._coll(collection_name)
+            pts = list(points)
+            if not pts:
+                return SimpleNamespace(status="completed")
+            vecs = np.asarray([np.asarray(_get(p, "vector"), dtype=np.float32) for p in pts], dtype=np.float32)
+            if vecs.ndim != 2 or vecs.shape[1] != c.dim:
+                raise RvoError(f"Wrong input: Vector dimension error: expected dim: {c.dim}, got {vecs.shape[-1]}")
+            rows = []
+            for p in pts:
+                pid = _get(p, "id")
+                r = c.row_of.get(pid)
+                if r is None:
+                    r = len(c.ids)
+                    c.ids.append(pid)
+                    c.payloads.append(_get(p, "payload"))
+                    c.row_of[pid] = r
+                else:
+                    c.payloads[r] = _get(p, "payload")
+                rows.append(r)
+            c.reserve(len(c.ids))
+            self._write_rows(c, rows, torch.from_numpy(vecs))
+            c.n = len(c.ids)
+            return SimpleNamespace(status="completed")
+
+    def search(self, collection_name: str, query_vector, limit: int = 10, score_threshold: float | None = None, **_):
+        """core_system.py:659-664.  One query; returns ScoredPoint-like hits, score descending."""
+        q = np.asarray(query_vector, dtype=np.float32).reshape(1, -1)
+        ids, scores, counts = self.search_batch(collection_name, q, limit, score_threshold)
+        c = self._coll(collection_name)
+        n = int(counts[0])
+        return [ScoredPoint(id=c.ids[int(i)], version=0, score=float(s), payload=c.payloads[int(i)])
+                for i, s in zip(ids[0, :n], scores[0, :n])]
+
+    # ---- batched entry point (new) -------------------------------------------------------------
+    def search_batch(self, collection_name: str, queries, limit: int = 10, score_threshold: float | None = None,
+                     as_device: bool = False):
+        """queries: [Q, D] float32 (numpy / torch, host or device).  Returns (ids [Q,k] int64 row numbers,
+        scores [Q,k] float32, counts [Q] int32); numpy unless `as_device`."""
+        with self._lock:
+            c = self._coll(collection_name)
+            n = c.n
+            vectors = c.vectors
+        k = int(limit)
+        if k > RVO_MAX_K:
+            raise RvoError(f"limit={k} above the supported maximum {RVO_MAX_K}")
+        if isinstance(queries, torch.Tensor) and queries.is_cuda:
+            qd = queries.to(dtype=torch.float32).contiguous()
+            if qd.dim() == 1:
+                qd = qd.unsqueeze(0)
+        else:
+            qh = queries.detach().cpu().numpy() if isinstance(queries, torch.Tensor) else queries
+            qh = np.ascontiguousarray(qh, dtype=np.float32)
+            if qh.ndim == 1:
+                qh = qh[None]
+            # host -> pinned staging -> device, all on the current stream
+            stage = self._pinned("q", qh.size * 4).view(torch.float32)[: qh.size].view(qh.shape)
+            stage.numpy()[...] = qh
+            qd = self._device_buf("q", qh.size * 4).view(torch.float32)[: qh.size].view(qh.shape)
+            qd.copy_(stage, non_blocking=True)
+        if qd.shape[1] != c.dim:
+            raise RvoError(f"Wrong input: Vector dimension error: expected dim: {c.dim}, got {qd.shape[1]}")
+        nq = qd.shape[0]
+        if as_device:
+            return ops.search_topk_exact(vectors, n, c.dim, qd, k, score_threshold)
+        ids, scores, counts = ops.search_topk(vectors, n, c.dim, qd, k, score_threshold)
+        hi = self._pinned("ids", nq * k * 8).view(torch.int64)[: nq * k].view(nq, k)
+        hs = self._pinned("sc", nq * k * 4).view(torch.float32)[: nq * k].view(nq, k)
+        hc = self._pinned("cnt", nq * 4).view(torch.int32)[:nq]
+        hi.copy_(ids, non_blocking=True)
+        hs.copy_(scores, non_blocking=True)
+        hc.copy_(counts, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        out_i, out_s, out_c = hi.numpy().copy(), hs.numpy().copy(), hc.numpy().copy()
+        bad = np.nonzero(out_c < 0)[0]
+        if len(bad):  # overflow protocol of rvo_search_topk: exact fp32 scan in batches of <= RVO_SMALL_Q
+            a, b, cc = ops.search_topk_exact(vectors, n, c.dim, qd[torch.from_numpy(bad).to(self.device)].contiguous(), k,
+                                             score_threshold)
+            out_i[bad], out_s[bad], out_c[bad] = a.cpu().numpy(), b.cpu().numpy(), cc.cpu().numpy()
+        return out_i, out_s, out_c
+
+    # ---- bulk ingest: tensors in, no python float lists --------------------
+    def upsert_batch(self, collection_name: str, ids: list, vectors, payloads: list | None = None):
+        with self._lock:
+            c = self._coll(collection_name)
+            v = vectors if isinstance(vectors, torch.Tensor) else torch.from_numpy(np.asarray(vectors, np.float32))
+            if v.dim() != 2 or v.shape[1] != c.dim or v.shape[0] != len(ids):
+                raise RvoError(f"upsert_batch: bad shape {tuple(v.shape)} for {len(ids)} ids, dim {c.dim}")
+            payloads = payloads if payloads is not None else [None] * len(ids)
+            rows = []
+            for pid, pay in zip(ids, payloads):
+                r = c.row_of.get(pid)
+                if r is None:
+                    r = len(c.ids)
+                    c.ids.append(pid)
+                    c.payloads.append(pay)
+                    c.row_of[pid] = r
+                else:
+                    c.payloads[r] = pay
+                rows.append(r)
+            c.reserve(len(c.ids))
+            self._write_rows(c, rows, v)
+            c.n = len(c.ids)
+
+    def count(self, collection_name: str) -> int:
+        return self._coll(collection_name).n
+
+    # ---- persistence -----------------------------------------------------------------------------
+    def save(self, path: str | None = None) -> None:
+        path = path or self.path
+        if not path:
+            raise RvoError("no path to save to")
+        os.makedirs(path, exist_ok=True)
+        with self._lock:
+            meta = {"format": "revers_o_b200/1", "collections": {}}
+            for name, c in self._collections.items():
+                meta["collections"][name] = {"dim": c.dim, "d_pad": c.d_pad, "n": c.n, "distance": "Cosine"}
+                raw = c.vectors[: c.n].contiguous().view(torch.int16).cpu().numpy()
+                raw.tofile(os.path.join(path, f"{name}.bf16"))
+                with open(os.path.join(path, f"{name}.payload.jsonl"), "w") as f:
+                    for pid, pay in zip(c.ids, c.payloads):
+                        f.write(json.dumps({"id": pid, "payload": pay}, default=str) + "\n")
+            with open(os.path.join(path, "meta.json"), "w") as f:
+                json.dump(meta, f)
+
+    def _load(self, path: str) -> None:
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        for name, m in meta.get("collections", {}).items():
+            c = _Collection(name, m["dim"], self.device)
+            n = int(m["n"])
+            if n:
+                raw = np.fromfile(os.path.join(path, f"{name}.bf16"), dtype=np.int16).reshape(n, c.d_pad)
+                c.reserve(n)
+                c.vectors[:n].copy_(torch.from_numpy(raw).view(torch.bfloat16))
+            with open(os.path.join(path, f"{name}.payload.jsonl")) as f:
+                for line in f:
+                    rec = json.loads(line)
+                    c.row_of[rec["id"]] = len(c.ids)
+                    c.ids.append(rec["id"])
+                    c.payloads.append(rec["payload"])
+            c.n = n
+            self._collections[name] = c
+
+    def close(self) -> None:
+        pass
+
+    def _pinned(self, name: str, nbytes: int) -> torch.Tensor:
+        """Persistent pinned host staging buffers, one set per calling thread (Gradio worker threads)."""
+        key = (name, threading.get_ident())
+        buf = self._staging.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 4096) * 2, dtype=torch.uint8).pin_memory()
+            self._staging[key] = buf
+        return buf[: (nbytes + 7) // 8 * 8]
+
+    def _device_buf(self, name: str, nbytes: int) -> torch.Tensor:
+        key = ("dev_" + name, threading.get_ident())
+        buf = self._staging.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 4096) * 2, dtype=torch.uint8, device=self.device)
+            self._staging[key] = buf
+        return buf[: (nbytes + 7) // 8 * 8]
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _coll(self, name: str) -> _Collection:
+        c = self._collections.get(name)
+        if c is None:
+            raise RvoError(f"Collection {name} not found")
+        return c
+
+    def _to_device_f32(self, x) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            t = x.to(dtype=torch.float32)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        if t.dim() == 1:
+            t = t.unsqueeze(0)
+        if not t.is_cuda:
+            t = t.pin_memory().to(self.device, non_blocking=True) if t.numel() > 4096 else t.to(self.device)
+        return t.contiguous()
+
+    def _write_rows(self, c: _Collection, rows: list, host_or_dev: torch.Tensor) -> None:
+        src = self._to_device_f32(host_or_dev)
+        contiguous = rows == list(range(rows[0], rows[0] + len(rows)))
+        if contiguous:
+            ops.normalize_rows(src, c.vectors[rows[0]: rows[0] + len(rows)])
+        else:  # overwrites of existing ids: normalise into a staging block, then scatter rows (memcpy only)
+            stage, _ = ops.normalize_rows(src)
+            idx = torch.tensor(rows, dtype=torch.long, device=self.device)
+            c.vectors.index_copy_(0, idx, stage)
+
+
+def _get(p, name):
+    return getattr(p, name) if hasattr(p, name) else p[name]

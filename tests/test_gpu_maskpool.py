@@ -1,0 +1,99 @@
+"""GPU parity tests for K1 (segmented mask pooling + L2 normalise) against the CPU oracle: pooled embeddings
+within 1e-3 relative (north_star), identical kept-region counts and order."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reverso_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch.device("cuda:0")
+
+
+def _check(feats, masks, max_regions=0):
+    from revers_o_b200 import ops
+    out, counts, src, total = ops.mask_pool(feats, masks, max_regions)
+    torch.cuda.synchronize()
+    B, M, P = masks.shape
+    emb, rc, rsrc = O.mask_pool(feats.float().cpu().numpy(), masks.cpu().numpy(), max_regions if max_regions > 0 else None)
+    t = int(total.item())
+    assert t == emb.shape[0] and np.array_equal(counts.cpu().numpy(), rc)
+    got = out[:t].cpu().numpy()
+    assert np.array_equal(src[:t].cpu().numpy(), rsrc[:, 0] * M + rsrc[:, 1])
+    rel = np.abs(got - emb) / np.maximum(np.abs(emb), 1e-3)
+    assert np.max(np.abs(got - emb)) < 1e-5 and rel.max() < 1e-3
+    assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    return got
+
+
+def test_golden_fixture(dev, golden):
+    feats = torch.from_numpy(golden["pool_feats_bf16_bits"].astype(np.int16)).view(torch.bfloat16).to(dev)
+    masks = torch.from_numpy(golden["pool_masks"]).to(dev)
+    got = _check(feats, masks)
+    assert np.allclose(got, golden["pool_emb"], atol=1e-5)
+    from revers_o_b200 import ops
+    out, counts, _, total = ops.mask_pool(feats, masks, 4)
+    assert np.array_equal(counts.cpu().numpy(), golden["pool_counts_cap4"])
+    assert np.allclose(out[: int(total.item())].cpu().numpy(), golden["pool_emb_cap4"], atol=1e-5)
+
+
+@pytest.mark.parametrize("B,M,grid,D", [(2, 8, 24, 1024), (5, 64, 24, 1024), (3, 50, 16, 1280), (1, 1, 7, 32), (4, 33, 23, 96)])
+def test_random_rectangles(dev, B, M, grid, D):
+    from revers_o_b200 import synth
+    feats, masks = synth.make_maskpool_inputs(B, M, grid, D, seed=11 + B, device=dev, n_empty=min(2, M - 1))
+    _check(feats, masks)
+
+
+def test_known_answers(dev):
+    """KA7 all-ones mask == token mean (core_system.py:345-346), KA8 single patch, KA9 empty dropped, cap (:363)."""
+    from revers_o_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    feats = torch.randn((1, 577, 1024), generator=g).to(torch.bfloat16).to(dev)       # 577 tokens: cls + 24*24
+    masks = torch.zeros((1, 4, 577), dtype=torch.uint8, device=dev)
+    masks[0, 0] = 1
+    masks[0, 2, 100] = 1
+    masks[0, 3, 10:20] = 1
+    out, counts, src, total = ops.mask_pool(feats, masks)
+    assert int(total.item()) == 3 and counts.tolist() == [3] and src[:3].tolist() == [0, 2, 3]
+    f = feats.float()
+    ref0 = f[0].mean(0); ref0 = ref0 / ref0.norm()
+    ref1 = f[0, 100] / f[0, 100].norm()
+    assert torch.allclose(out[0], ref0, atol=1e-5) and torch.allclose(out[1], ref1, atol=1e-6)
+    masks = torch.ones((1, 64, 577), dtype=torch.uint8, device=dev)
+    out, counts, _, total = ops.mask_pool(feats, masks, 50)
+    assert counts.tolist() == [50] and int(total.item()) == 50
+
+
+def test_dense_random_masks_and_all_empty_image(dev):
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn((3, 576, 256), generator=g).to(torch.bfloat16).to(dev)
+    masks = (torch.rand((3, 20, 576), generator=g) < 0.4).to(torch.uint8)
+    masks[1] = 0                                                                       # image with no region at all
+    _check(feats, masks.to(dev))
+
+
+def test_config2_full_shape(dev):
+    """BASELINE config 2: 256 images x 64 masks x 24x24 patches x 1024-d; oracle parity on a sample of images,
+    unit norms and counts on all."""
+    from revers_o_b200 import ops, synth
+    B, M, grid, D = 256, 64, 24, 1024
+    feats, masks = synth.make_maskpool_inputs(B, M, grid, D, seed=11, device=dev)
+    out, counts, src, total = ops.mask_pool(feats, masks)
+    torch.cuda.synchronize()
+    t = int(total.item())
+    assert t == B * (M - 2) and torch.all(counts == M - 2)
+    assert torch.allclose(out[:t].norm(dim=1), torch.ones(t, device=dev), atol=1e-5)
+    sel = [0, 100, 255]
+    emb, rc, _ = O.mask_pool(feats[sel].float().cpu().numpy(), masks[sel].cpu().numpy())
+    offs = torch.cumsum(counts, 0).cpu().numpy()
+    for j, b in enumerate(sel):
+        lo = offs[b] - counts[b].item()
+        got = out[lo: lo + rc[j]].cpu().numpy()
+        ref = emb[sum(rc[:j]): sum(rc[:j]) + rc[j]]
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)) < 1e-3

@@ -1,0 +1,236 @@
+"""GPU parity tests for K2 (search) and K3 (merge): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Tolerances are the north_star's: scores within 1e-3 absolute, identical
+top-k id sets except ties within 1e-3."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reverso_oracle as O
+from conftest import assert_topk_match
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch.device("cuda:0")
+
+
+def _oracle(db_bf16: torch.Tensor, n, d, queries: torch.Tensor, k, thr=None):
+    dbf = db_bf16[:n, :d].float().cpu().numpy()
+    return O.search_batch(dbf, queries.float().cpu().numpy(), k, thr, db_is_normalized=True)
+
+
+def _run(db, n, d, q, k, thr=None, id_offset=0):
+    from revers_o_b200 import ops
+    ids, sc, cnt = ops.search_topk(db, n, d, q, k, thr, id_offset)
+    torch.cuda.synchronize()
+    return ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+
+
+# ---- the tcgen05 mainloop by itself ---------------------------------------------------------------
+@pytest.mark.parametrize("n,d,nq,stride", [(1000, 64, 5, 1), (4096, 1024, 16, 1), (5000, 1024, 37, 1),
+                                            (3000, 1280, 256, 1), (20000, 1024, 300, 7), (777, 96, 130, 1)])
+def test_dense_scores_match_fp32_reference(dev, n, d, nq, stride):
+    from revers_o_b200 import ops, synth
+    q = synth.make_queries(nq, d, seed=3, device=dev)
+    db = synth.make_db(n, d, q, n_plant=8, seed=5, device=dev)
+    ns = (n + stride - 1) // stride
+    got = ops.scores_dense(db, n, d, q, row_stride=stride, n_sample=ns)
+    torch.cuda.synchronize()
+    qn = (q / q.norm(dim=1, keepdim=True)).to(torch.bfloat16).float()          # tensor path rounds the query
+    ref = qn @ db[: n: stride, :d].float().T
+    assert got.shape == ref.shape
+    assert torch.max(torch.abs(got - ref)).item() < 2e-5
+
+
+# ---- full search, both paths ------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,nq,k", [
+    (10_000, 1024, 1, 10),      # BASELINE config 0: the reference's own operating point
+    (10_000, 1024, 3, 10),
+    (50_000, 1280, 4, 100),
+    (3_000, 96, 2, 10),
+    (2_500, 1024, 16, 10),      # tensor path, shard below one chunk (single DENSE level)
+    (10_000, 1024, 9, 10),      # tensor path, resident queries
+    (60_000, 1024, 64, 100),
+    (120_000, 1024, 256, 100),  # config 1 shape at reduced N
+    (70_000, 1280, 300, 50),    # two query blocks
+    (33_333, 2048, 40, 7),
+])
+def test_search_matches_oracle(dev, n, d, nq, k):
+    from revers_o_b200 import synth
+    q = synth.make_queries(nq, d, seed=7, device=dev)
+    db = synth.make_db(n, d, q, n_plant=min(128, 2 * k), seed=1000, device=dev)
+    ids, sc, cnt = _run(db, n, d, q, k)
+    assert_topk_match(ids, sc, cnt, _oracle(db, n, d, q, k), k, TOL, f"n{n}d{d}q{nq}k{k}")
+    assert np.all(cnt == min(k, n))
+
+
+def test_scores_also_within_tolerance_of_unrounded_fp32_db(dev):
+    """The GPU DB is bf16; the reference's is fp32.  North-star tolerance (1e-3) must hold against the fp32 DB too."""
+    from revers_o_b200 import ops
+    rs = np.random.RandomState(0)
+    n, d, nq, k = 20_000, 1024, 32, 50
+    dbf = O._cosine_prepare(rs.randn(n, d).astype(np.float32))
+    qf = rs.randn(nq, d).astype(np.float32)
+    for i in range(nq):
+        for j, a in enumerate(np.linspace(0.5, 0.99, 60)):
+            v = a * qf[i] / np.linalg.norm(qf[i]) + math.sqrt(1 - a * a) * rs.randn(d).astype(np.float32) / math.sqrt(d)
+            dbf[(i * 601 + j * 7) % n] = v / np.linalg.norm(v)
+    src = torch.from_numpy(dbf).to(dev)
+    db, _ = ops.normalize_rows(src)
+    ids, sc, cnt = _run(db, n, d, torch.from_numpy(qf).to(dev), k)
+    ref = O.search_batch(dbf, qf, k, None, db_is_normalized=True)
+    assert_topk_match(ids, sc, cnt, ref, k, TOL, "fp32db")
+
+
+@pytest.mark.parametrize("nq", [1, 24])
+def test_score_threshold_semantics(dev, nq):
+    from revers_o_b200 import synth
+    n, d, k = 30_000, 1024, 50
+    q = synth.make_queries(nq, d, seed=11, device=dev)
+    db = synth.make_db(n, d, q, n_plant=64, seed=12, device=dev)
+    for thr in (0.7, 0.95, 0.999, -1.0):
+        ids, sc, cnt = _run(db, n, d, q, k, thr)
+        ref = _oracle(db, n, d, q, k, thr)
+        assert_topk_match(ids, sc, cnt, ref, k, TOL, f"thr{thr}")
+        for qi in range(nq):
+            assert np.all(sc[qi, : cnt[qi]] >= thr) and np.all(ids[qi, cnt[qi]:] == -1)
+
+
+@pytest.mark.parametrize("nq", [1, 8])
+def test_known_answers_identity_duplicates_limit(dev, nq):
+    """KA1/KA2/KA4/KA5 through the CUDA path."""
+    from revers_o_b200 import ops
+    d = 128
+    eye = torch.eye(d, dtype=torch.float32, device=dev)
+    src = torch.cat([eye, eye[5:6], eye[5:6]], 0)                 # rows 128,129 duplicate row 5
+    db, _ = ops.normalize_rows(src)
+    n = src.shape[0]
+    q = eye[[5] + list(range(1, nq))].contiguous() * 3.0
+    ids, sc, cnt = _run(db, n, d, q, 3)
+    assert ids[0].tolist() == [5, 128, 129] and np.allclose(sc[0], 1.0, atol=1e-6)   # ties -> lower id first
+    ids, sc, cnt = _run(db, n, d, q, 200)                          # limit > N
+    assert cnt[0] == n and np.all(ids[0, n:] == -1) and sorted(ids[0, :n].tolist()) == list(range(n))
+    ids, sc, cnt = _run(db, n, d, -q, 5, 0.5)                      # nothing above the threshold
+    assert np.all(cnt == 0) and np.all(ids == -1) and np.all(np.isneginf(sc))
+    ids, sc, cnt = _run(db, 0, d, q, 5)                            # empty collection
+    assert np.all(cnt == 0) and np.all(ids == -1)
+
+
+def test_id_offset_and_virtual_shards_merge(dev, golden):
+    """K3 on one GPU: split the DB into G virtual shards, search each with its id_offset, merge; the result must
+    equal the unsharded search (merge is a pure function of the gathered lists) and the oracle's merge."""
+    from revers_o_b200 import ops, synth
+    from revers_o_b200.sharded import shard_bounds, pack_results
+    n, d, nq, k, G = 90_000, 1024, 40, 100, 4
+    q = synth.make_queries(nq, d, seed=21, device=dev)
+    db = synth.make_db(n, d, q, n_plant=160, seed=22, device=dev)
+    full = _run(db, n, d, q, k)
+    parts = []
+    for r in range(G):
+        lo, hi = shard_bounds(n, G, r)
+        parts.append(ops.search_topk(db[lo:hi], hi - lo, d, q, k, None, lo))
+    ids = torch.stack([p[0] for p in parts]); sc = torch.stack([p[1] for p in parts]); cnt = torch.stack([p[2] for p in parts])
+    mi, ms, mc = ops.merge_topk(ids.contiguous(), sc.contiguous(), cnt.contiguous(), k)
+    torch.cuda.synchronize()
+    assert np.array_equal(mi.cpu().numpy(), full[0]) and np.allclose(ms.cpu().numpy(), full[1], atol=1e-6)
+    oi, os_, oc = O.merge_topk(ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy(), k)
+    assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(mc.cpu().numpy(), oc)
+    # packed layout (what one all-gather delivers)
+    from revers_o_b200 import _lib
+    blob = torch.stack([pack_results(*p) for p in parts])
+    pi = torch.empty_like(mi); ps = torch.empty_like(ms); pc = torch.empty_like(mc)
+    _lib.check(_lib.load().rvo_merge_topk_packed(blob.data_ptr(), blob.stride(0), G, nq, k, pi.data_ptr(), ps.data_ptr(),
+                                                 pc.data_ptr(), torch.cuda.current_stream().cuda_stream), "packed")
+    torch.cuda.synchronize()
+    assert torch.equal(pi, mi) and torch.equal(ps, ms) and torch.equal(pc, mc)
+    # golden merge fixture
+    gi, gs, gc = (torch.from_numpy(golden[f"merge_{x}"]).to(dev) for x in ("ids", "scores", "counts"))
+    a, b, c = ops.merge_topk(gi, gs, gc, 5)
+    assert np.array_equal(a.cpu().numpy(), golden["merge_out_ids"]) and np.array_equal(c.cpu().numpy(), golden["merge_out_counts"])
+
+
+def test_golden_search_fixture(dev, golden):
+    db = torch.from_numpy(golden["search_db_bf16_bits"].astype(np.int16)).view(torch.bfloat16)
+    n, d = db.shape
+    dbp = torch.zeros((n, 128), dtype=torch.bfloat16)
+    dbp[:, :d] = db
+    dbp = dbp.to(dev)
+    q = torch.from_numpy(golden["search_queries"]).to(dev)
+    for tag, k, thr in (("k10", 10, None), ("k10_t07", 10, 0.7), ("k100", 100, None)):   # nq=9 -> tensor path
+        ids, sc, cnt = _run(dbp, n, d, q, k, thr)
+        assert np.array_equal(cnt, golden[f"search_{tag}_counts"])
+        for i in range(q.shape[0]):
+            c = cnt[i]
+            assert np.allclose(sc[i, :c], golden[f"search_{tag}_scores"][i, :c], atol=2e-6)
+            assert set(ids[i, :c].tolist()) == set(golden[f"search_{tag}_ids"][i, :c].tolist())
+    for i in range(0, 9, 4):                                      # small-q path on the same fixture
+        ids, sc, cnt = _run(dbp, n, d, q[i:i + 4].contiguous(), 10)
+        for j in range(cnt.shape[0]):
+            assert np.allclose(sc[j, :10], golden["search_k10_scores"][i + j], atol=2e-6)
+
+
+def test_overflow_flag_and_exact_fallback(dev):
+    """A DB made of >cap exact duplicates of the query overflows the fused path's candidate buffers: the ABI must
+    flag it (-1), and the documented protocol (re-run in batches of <= RVO_SMALL_Q) must return the exact answer."""
+    from revers_o_b200 import ops, synth
+    n, d, nq, k = 40_000, 256, 8, 20
+    q = synth.make_queries(nq, d, seed=31, device=dev)
+    db = synth.make_db(n, d, None, seed=32, device=dev)
+    qn = (q[0] / q[0].norm()).to(torch.bfloat16)
+    db[5000:30000, :d] = qn                                          # 25k identical rows, all score ~1.0 for query 0
+    ids, sc, cnt = ops.search_topk(db, n, d, q, k)
+    torch.cuda.synchronize()
+    assert cnt[0].item() == -1 and torch.all(cnt[1:] == k)
+    ids, sc, cnt = ops.search_topk_exact(db, n, d, q, k)
+    torch.cuda.synchronize()
+    assert cnt[0].item() == k and ids[0].tolist() == list(range(5000, 5000 + k))      # ties -> lowest ids
+    ref = _oracle(db, n, d, q, k)
+    assert_topk_match(ids.cpu().numpy()[1:], sc.cpu().numpy()[1:], cnt.cpu().numpy()[1:], ref[1:], k, TOL, "ovf")
+
+
+def test_clustered_ingest_order_is_still_exact(dev):
+    """Adversarial row order for the strided threshold samples: all near neighbours sit in one contiguous run."""
+    from revers_o_b200 import synth
+    n, d, nq, k = 150_000, 1024, 32, 100
+    q = synth.make_queries(nq, d, seed=41, device=dev)
+    db = synth.make_db(n, d, None, seed=42, device=dev)
+    qn = q / q.norm(dim=1, keepdim=True)
+    g = torch.Generator(device=dev).manual_seed(43)
+    for i in range(nq):
+        noise = torch.randn((300, d), generator=g, device=dev) / math.sqrt(d)
+        a = torch.linspace(0.6, 0.99, 300, device=dev).view(-1, 1)
+        v = a * qn[i] + torch.sqrt(1 - a * a) * noise
+        db[70_000 + i * 300: 70_000 + (i + 1) * 300, :d] = (v / v.norm(dim=1, keepdim=True)).to(torch.bfloat16)
+    ids, sc, cnt = _run(db, n, d, q, k)
+    assert_topk_match(ids, sc, cnt, _oracle(db, n, d, q, k), k, TOL, "clustered")
+
+
+def test_config1_full_size_properties_and_sampled_parity(dev):
+    """BASELINE config 1 at full size (1M x 1024, Q=256, k=100): size-independent properties on every query
+    (descending, in-range unique ids, every returned score reproduced by an fp32 dot with the stored row, the
+    planted >=0.99 neighbour found first) plus oracle parity on a sample of queries."""
+    from revers_o_b200 import synth
+    n, d, nq, k = 1_000_000, 1024, 256, 100
+    q = synth.make_queries(nq, d, seed=7, device=dev)
+    db = synth.make_db(n, d, q, n_plant=128, seed=1000, device=dev)
+    ids, sc, cnt = _run(db, n, d, q, k)
+    assert np.all(cnt == k)
+    assert np.all(np.diff(sc, axis=1) <= 1e-7) and ids.min() >= 0 and ids.max() < n
+    assert all(len(set(r.tolist())) == k for r in ids)
+    qn = (q / q.norm(dim=1, keepdim=True))
+    rows = db[torch.from_numpy(ids).to(dev).view(-1), :d].float().view(nq, k, d)
+    redo = torch.einsum("qkd,qd->qk", rows, qn).cpu().numpy()
+    assert np.max(np.abs(redo - sc)) < 1e-5
+    assert np.all(sc[:, 0] > 0.98)
+    sel = list(range(0, nq, 16))
+    dbf = db[:, :d].float().cpu().numpy()
+    ref = O.search_batch(dbf, q[sel].cpu().numpy(), k, None, db_is_normalized=True)
+    assert_topk_match(ids[sel], sc[sel], cnt[sel], ref, k, TOL, "cfg1")

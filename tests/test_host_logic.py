@@ -1,0 +1,64 @@
+"""CPU: host-side logic of the drop-in (no GPU, no compute calls): patch-grid reduction vs the oracle's rule,
+sharding maths, result packing, status-string convention of the boundary."""
+import numpy as np
+import torch
+
+from oracle import reverso_oracle as O
+from revers_o_b200.core_system import SimpleReverso, binarize_mask, mask_to_patch_grid
+from revers_o_b200.sharded import pack_results, packed_bytes, shard_bounds, unpack_results
+
+
+def test_patch_grid_matches_oracle_rule():
+    rs = np.random.RandomState(0)
+    for H, W, g in ((336, 336, 24), (480, 640, 24), (97, 61, 16), (20, 20, 24)):
+        for _ in range(4):
+            m = np.zeros((H, W), bool)
+            y0, x0 = rs.randint(0, H - 1), rs.randint(0, W - 1)
+            m[y0: y0 + rs.randint(1, H), x0: x0 + rs.randint(1, W)] = True
+            assert np.array_equal(mask_to_patch_grid(m, g), O.mask_to_patch_grid(m, g))
+    f = rs.rand(50, 70).astype(np.float32)
+    assert np.array_equal(binarize_mask(f), O.binarize_mask(f))
+    assert np.array_equal(mask_to_patch_grid(f, 8), O.mask_to_patch_grid(f, 8))
+
+
+def test_shard_bounds_cover_exactly():
+    for n in (0, 1, 7, 100, 100_000_000):
+        for w in (1, 2, 3, 4, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_bounds(100_000_000, 8, 3) == (37_500_000, 50_000_000)
+
+
+def test_pack_unpack_roundtrip():
+    nq, k, G = 5, 7, 3
+    g = torch.Generator().manual_seed(0)
+    parts = []
+    for r in range(G):
+        ids = torch.randint(0, 1 << 40, (nq, k), generator=g)
+        sc = torch.randn((nq, k), generator=g)
+        cnt = torch.randint(-1, k + 1, (nq,), generator=g, dtype=torch.int32)
+        parts.append((ids, sc, cnt))
+    blobs = torch.stack([pack_results(*p) for p in parts])
+    assert blobs.shape == (G, packed_bytes(nq, k)) and packed_bytes(nq, k) % 8 == 0
+    ids, sc, cnt = unpack_results(blobs, nq, k)
+    for r in range(G):
+        assert torch.equal(ids[r], parts[r][0]) and torch.equal(sc[r], parts[r][1]) and torch.equal(cnt[r], parts[r][2])
+
+
+def test_status_string_convention_without_gpu(tmp_path):
+    """Guards of core_system.py:93-97,322-324,652-653: status strings / empty results, never exceptions."""
+    r = SimpleReverso(db_root=str(tmp_path / "db"), device="cpu")
+    assert r.list_databases() == []
+    assert r.load_database("") == "❌ Please provide a database name"
+    assert r.load_database("missing") == "❌ Database not found: missing"
+    assert r.delete_database("missing").startswith("❌") and r.unlock_database("").startswith("❌")
+    assert r.search_similar()[0].startswith("❌ No query embeddings")
+    r.region_embeddings = [torch.zeros(4)]
+    assert r.search_similar()[0].startswith("❌ No database loaded")
+    assert r.extract_embeddings(None) == ([], [])
+    assert r.detect_regions(np.zeros((4, 4, 3), np.uint8), "x") == 0
+    assert r.create_database(str(tmp_path / "nope"), "d").startswith("❌ Folder not found")
+    r.request_stop()
+    assert r._stop_requested is True
