@@ -47,19 +47,31 @@ const char* rvo_last_error(void);
 int rvo_device_sm_count(const void* dev_ptr);
 
 /* ------------------------------------------------------------------------------------------------
- * Ingest: L2-normalise float32 rows and store them as bf16 DB rows.
+ * DB storage layout ("tiled"): bf16, rows padded to a multiple of 128, columns to d_pad = d rounded up
+ * to 64 (pad columns/rows are zero):
+ *        db[row / 128][col / 64][row % 128][col % 64]
+ * i.e. every (128-row block, 64-column chunk) tile is one contiguous 16 KiB block, which is exactly one
+ * TMA box of the scan kernel: the scan streams HBM in long contiguous bursts.  Bytes needed for n rows:
+ * rvo_db_bytes(n, d).  Element offset: ((row/128)*(d_pad/64) + col/64)*8192 + (row%128)*64 + col%64.
+ * ---------------------------------------------------------------------------------------------- */
+size_t rvo_db_bytes(int64_t n_rows, int32_t d);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ingest: L2-normalise float32 rows and store them as bf16.
  * Replaces: qdrant-local upsert into a COSINE collection (vector normalised, appended to the
  *           collection matrix) behind core_system.py:608-621, and the `e / e.norm()` of
- *           core_system.py:407,447 when called with out_f32.
+ *           core_system.py:407,447 when called with dst_f32.
  *   src      [dev] float32 [n, d], row pitch src_ld elements
- *   dst_bf16 [dev] bf16    [n, d_pad] row pitch dst_ld elements (dst_ld % 8 == 0, >= d); columns
- *            d..dst_ld-1 are written as zero.  May be NULL.
+ *   dst_bf16 [dev] may be NULL.
+ *            tiled_row0 >= 0: base of a tiled DB (see above) with d_pad == dst_ld; the n rows are
+ *                             written at DB rows tiled_row0 .. tiled_row0 + n - 1 (append / overwrite);
+ *            tiled_row0 <  0: plain row-major [n, dst_ld] (dst_ld % 8 == 0, >= d), pad columns zeroed.
  *   dst_f32  [dev] float32 [n, d] row pitch d: the normalised rows in float32.  May be NULL.
  * A zero row stays zero (qdrant divides by eps; the reference never stores one, see
  * core_system.py:402-404).
  * ---------------------------------------------------------------------------------------------- */
 int rvo_normalize_rows(const float* src, int64_t n, int32_t d, int64_t src_ld,
-                       uint16_t* dst_bf16, int64_t dst_ld, float* dst_f32, void* stream);
+                       uint16_t* dst_bf16, int64_t dst_ld, int64_t tiled_row0, float* dst_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1 — segmented mask pooling + L2 normalise.
@@ -87,7 +99,8 @@ int rvo_mask_pool(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_
  *           mode behind core_system.py:659-664 (normalise query, scores = vectors @ q over the
  *           whole collection, descending argsort, stop at first score < score_threshold, first
  *           `limit` hits), batched over nq queries row by row.
- *   db      [dev] bf16 [n_rows, db_ld] L2-normalised rows (db_ld % 64 == 0, columns >= d zero)
+ *   db      [dev] bf16 tiled DB storage (see "DB storage layout") of L2-normalised rows; d_pad = d
+ *           rounded up to 64
  *   queries [dev] float32 [nq, d] row pitch d; NOT required to be normalised
  *   k       1..RVO_MAX_K  (`limit`)
  *   score_threshold   hits with score < threshold are dropped; pass -INFINITY for "None"
@@ -103,7 +116,7 @@ int rvo_mask_pool(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_
  * with the threshold-select fused in its epilogue, candidates re-scored in fp32.
  * ---------------------------------------------------------------------------------------------- */
 size_t rvo_search_workspace_bytes(int64_t n_rows, int32_t d, int32_t nq, int32_t k);
-int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld,
+int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad,
                     const float* queries, int32_t nq, int32_t k, float score_threshold, int64_t id_offset,
                     int64_t* out_ids, float* out_scores, int32_t* out_counts,
                     void* workspace, size_t workspace_bytes, void* stream);
@@ -111,11 +124,16 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld
 /* Rows the tcgen05 path pads a batch of nq queries to (query blocks of <=256, multiples of 16). */
 int rvo_padded_queries(int32_t nq, int32_t d);
 
-/* Dense score block (diagnostics / tests): scores[q, r] = <bf16(q_hat), db[r]> computed by the
- * tcgen05 scan in DENSE mode over rows r = i*row_stride, i < n_sample.
- *   out [dev] float32 [rvo_padded_queries(nq, d), out_ld], out_ld >= n_sample */
-int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld,
-                     const float* queries, int32_t nq, int64_t row_stride, int64_t n_sample,
+/* DB rows per scan tile (128 or 256) for a batch of nq queries of dimension d. */
+int rvo_scan_tile_rows(int32_t nq, int32_t d);
+
+/* Dense score block (diagnostics / tests; this is the threshold-seeding pass of the fused path):
+ * scores[q, c] = <bf16(q_hat), db[r]> computed by the tcgen05 scan in DENSE mode over every
+ * tile_stride-th tile of T = rvo_scan_tile_rows(nq, d) rows: column c = t*T + i is row
+ * r = t*tile_stride*T + i.  Rows past n_rows are written as -inf.
+ *   out [dev] float32 [rvo_padded_queries(nq, d), out_ld], out_ld >= ceil(ceil(n_rows/T)/tile_stride)*T */
+int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad,
+                     const float* queries, int32_t nq, int64_t tile_stride,
                      float* out, int64_t out_ld, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -19,8 +19,9 @@ PROTOTYPES = {
     "rvo_version": (C.c_int, []),
     "rvo_last_error": (C.c_char_p, []),
     "rvo_device_sm_count": (C.c_int, [C.c_void_p]),
-    "rvo_normalize_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
-                                     C.c_void_p]),
+    "rvo_db_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "rvo_normalize_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                     C.c_void_p, C.c_void_p]),
     "rvo_mask_pool_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "rvo_mask_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -29,8 +30,9 @@ PROTOTYPES = {
                                   C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p]),
     "rvo_padded_queries": (C.c_int, [C.c_int32, C.c_int32]),
+    "rvo_scan_tile_rows": (C.c_int, [C.c_int32, C.c_int32]),
     "rvo_scores_dense": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
-                                   C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rvo_packed_result_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rvo_merge_topk_packed": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),

@@ -139,12 +139,15 @@ static int reduce_topk(TopkSrc src, int nq, int K_mid, int K_final, unsigned lon
     }
 }
 
+
 // ---- search plan (shared by the workspace query and the driver) --------------------------------
+constexpr long long kSeedRows = 16384;  // rows of the DENSE threshold-seeding sample
+
 struct SearchPlan {
     bool small;
     int d_pad, K2, cap, n_levels;
-    long long level_stride[8], level_rows[8];
-    long long dense_rows, dense_stride;
+    long long level_stride[8];       // super-tile stride of each FILTER level (last one is 1)
+    long long seed_stride, seed_cols;
     TcPlan tc;
     // workspace slices
     float* qn;
@@ -184,51 +187,47 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
         int rc = plan_scan_tc(nq, sp->d_pad, (int)opt_m_sub.load(), &sp->tc);
         if (rc) return rc;
         const int nq_pad = sp->tc.nq_pad;
+        const long long T = (long long)kBlockM * sp->tc.m_sub;
+        const long long supers = (n_rows + T - 1) / T;
         sp->K2 = next_pow2_host((2 * k > k + 64) ? 2 * k : k + 64);
         if (sp->K2 > 1024) sp->K2 = 1024;
         long long cap = opt_cand_cap.load();
-        if (cap < kChunk) cap = kChunk;
-        cap = (cap + kChunk - 1) / kChunk * kChunk;
+        if (cap < 1024) cap = 1024;
         sp->cap = (int)cap;
-        // levels: dense seed over <=4096 strided rows, then geometric FILTER samples, then the full scan
-        if (n_rows <= kChunk) {
-            sp->dense_rows = n_rows;
-            sp->dense_stride = 1;
+        // levels: DENSE seed over ~16k rows (every seed_stride-th super-tile), then geometric FILTER samples,
+        // then the full scan.  Any sample gives a valid threshold (k-th best of a subset <= k-th best overall).
+        if (supers * T <= kSeedRows) {
+            sp->seed_stride = 1;
             sp->n_levels = 0;
         } else {
-            sp->dense_stride = n_rows / kChunk;
-            sp->dense_rows = kChunk;
+            sp->seed_stride = supers / (kSeedRows / T);
+            if (sp->seed_stride < 1) sp->seed_stride = 1;
             long long ratio = opt_final_ratio.load();
             if (ratio < 2) ratio = 2;
             long long sizes[8];
             int ns = 0;
-            for (long long s = n_rows / ratio; s >= 2 * kChunk && ns < 6; s /= 64) sizes[ns++] = s;
+            for (long long s = n_rows / ratio; s >= 2 * kSeedRows && ns < 6; s /= 64) sizes[ns++] = s;
             int L = 0;
             for (int i = ns - 1; i >= 0; --i) {
-                const long long r = n_rows / sizes[i];
-                if (r <= 1) continue;
-                sp->level_stride[L] = r;
-                sp->level_rows[L] = n_rows / r;
-                ++L;
+                const long long r = supers / ((sizes[i] + T - 1) / T);
+                if (r <= 1 || r >= sp->seed_stride) continue;
+                sp->level_stride[L++] = r;
             }
             sp->level_stride[L] = 1;
-            sp->level_rows[L] = n_rows;
             sp->n_levels = L + 1;
         }
+        sp->seed_cols = scan_tc_sample_rows(n_rows, sp->tc, sp->seed_stride);
         sp->zero_off = ar.off;
         sp->qb = ar.take<uint16_t>((size_t)nq_pad * sp->d_pad, 1024);
         sp->cnt = ar.take<int>((size_t)(sp->n_levels + 1) * nq_pad);
         sp->zero_bytes = ar.off - sp->zero_off;
         sp->qn = ar.take<float>((size_t)nq * sp->d_pad, 1024);
         sp->tau = ar.take<float>((size_t)(sp->n_levels + 1) * nq_pad);
-        sp->dense_ld = kChunk;
-        sp->dense = ar.take<float>((size_t)nq_pad * kChunk);
+        sp->dense_ld = (sp->seed_cols + 63) / 64 * 64;
+        sp->dense = ar.take<float>((size_t)nq_pad * (size_t)sp->dense_ld);
         if (sp->n_levels > 0) sp->cand = ar.take<unsigned long long>((size_t)nq_pad * (size_t)sp->cap);
-        const size_t e_list = reduce_buf_elems(sp->cap, sp->K2);
-        const size_t e_dense = reduce_buf_elems(kChunk, sp->K2);
-        const size_t e1 = e_list > e_dense ? e_list : e_dense;
-        sp->bufA = ar.take<unsigned long long>((size_t)nq * e1);
-        sp->bufB = ar.take<unsigned long long>((size_t)nq * reduce_buf_elems((long long)e1, sp->K2));
+        sp->bufA = ar.take<unsigned long long>((size_t)nq * sp->K2);
+        sp->bufB = nullptr;
     }
     sp->bytes = ar.off + 1024;
     if (ws && !ar.ok()) {
@@ -240,7 +239,7 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
 
 static int prep_queries(const SearchPlan& sp, const float* queries, int nq, int d, void* ws, cudaStream_t stream) {
     RVO_CUDA(cudaMemsetAsync((char*)ws + sp.zero_off, 0, sp.zero_bytes, stream));
-    return launch_normalize_rows(queries, nq, d, d, sp.small ? nullptr : sp.qb, sp.d_pad, sp.qn, sp.d_pad, stream);
+    return launch_normalize_rows(queries, nq, d, d, sp.small ? nullptr : sp.qb, sp.d_pad, -1, sp.qn, sp.d_pad, stream);
 }
 
 }  // namespace rvo
@@ -285,8 +284,14 @@ int rvo_set_option(const char* name, int64_t value) {
     return RVO_OK;
 }
 
+size_t rvo_db_bytes(int64_t n_rows, int32_t d) {
+    if (n_rows < 0 || d <= 0) return 0;
+    const size_t d_pad = (size_t)(d + kBlockK - 1) / kBlockK * kBlockK;
+    return (size_t)((n_rows + kTileRows - 1) / kTileRows) * kTileRows * d_pad * 2;
+}
+
 int rvo_normalize_rows(const float* src, int64_t n, int32_t d, int64_t src_ld, uint16_t* dst_bf16, int64_t dst_ld,
-                       float* dst_f32, void* stream) {
+                       int64_t tiled_row0, float* dst_f32, void* stream) {
     RVO_REQUIRE(src && (dst_bf16 || dst_f32), "normalize_rows: null pointer");
     RVO_REQUIRE(n >= 0 && d > 0 && src_ld >= d, "normalize_rows: bad shape n=%lld d=%d ld=%lld", (long long)n, d,
                 (long long)src_ld);
@@ -294,7 +299,8 @@ int rvo_normalize_rows(const float* src, int64_t n, int32_t d, int64_t src_ld, u
                 (long long)dst_ld);
     int rc = select_device_of(src, nullptr);
     if (rc) return rc;
-    return launch_normalize_rows(src, n, d, src_ld, dst_bf16, dst_ld, dst_f32, d, (cudaStream_t)stream);
+    RVO_REQUIRE(tiled_row0 < 0 || !dst_bf16 || dst_ld % kBlockK == 0, "normalize_rows: tiled storage needs d_pad %% 64 == 0");
+    return launch_normalize_rows(src, n, d, src_ld, dst_bf16, dst_ld, tiled_row0, dst_f32, d, (cudaStream_t)stream);
 }
 
 size_t rvo_mask_pool_workspace_bytes(int32_t B, int32_t M, int32_t P, int32_t D) {
@@ -322,7 +328,7 @@ size_t rvo_search_workspace_bytes(int64_t n_rows, int32_t d, int32_t nq, int32_t
     return sp.bytes;
 }
 
-int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld, const float* queries, int32_t nq,
+int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad_in, const float* queries, int32_t nq,
                     int32_t k, float score_threshold, int64_t id_offset, int64_t* out_ids, float* out_scores,
                     int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -330,8 +336,8 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld
     RVO_REQUIRE(n_rows >= 0 && d > 0 && nq > 0, "search_topk: bad shape n_rows=%lld d=%d nq=%d", (long long)n_rows, d, nq);
     RVO_REQUIRE(k >= 1 && k <= RVO_MAX_K, "search_topk: k=%d outside 1..%d", k, RVO_MAX_K);
     RVO_REQUIRE(n_rows == 0 || db, "search_topk: null db");
-    RVO_REQUIRE(db_ld % kBlockK == 0 && db_ld >= d, "search_topk: db_ld=%lld must be a multiple of 64 and >= d",
-                (long long)db_ld);
+    RVO_REQUIRE(d_pad_in == (d + kBlockK - 1) / kBlockK * kBlockK, "search_topk: d_pad=%lld must be d rounded up to 64",
+                (long long)d_pad_in);
     RVO_REQUIRE(((uintptr_t)db & 15) == 0 && ((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)queries & 3) == 0,
                 "search_topk: db must be 16-byte and workspace 1024-byte aligned");
     RVO_REQUIRE(n_rows < (1ll << 31), "search_topk: shard of %lld rows too large, shard the DB", (long long)n_rows);
@@ -352,15 +358,12 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld
     rc = prep_queries(sp, queries, nq, d, workspace, stream);
     if (rc) return rc;
 
-    const unsigned long long* top = nullptr;
-    long long top_ld = 0;
     FinalArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.k = k;
     fa.K2 = sp.K2;
     fa.score_threshold = score_threshold;
     fa.db = db;
-    fa.db_ld = db_ld;
     fa.d_pad = sp.d_pad;
     fa.qn = sp.qn;
     fa.qn_ld = sp.d_pad;
@@ -371,8 +374,10 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld
 
     if (sp.small) {
         // exact fp32 scan -> dense scores -> chunked exact top-k (never overflows)
+        const unsigned long long* top = nullptr;
+        long long top_ld = 0;
         if ((rc = scan_timer(true, stream))) return rc;
-        rc = launch_scan_small(db, n_rows, db_ld, sp.d_pad, sp.qn, sp.d_pad, nq, sp.dense, sp.dense_ld, sm, stream);
+        rc = launch_scan_small(db, n_rows, sp.d_pad, sp.qn, sp.d_pad, nq, sp.dense, sp.dense_ld, sm, stream);
         if (rc) return rc;
         if ((rc = scan_timer(false, stream))) return rc;
         TopkSrc src = {sp.dense, sp.dense_ld, nullptr, 0, nullptr, 0, n_rows};
@@ -389,54 +394,72 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld
     const float margin = kBf16QueryMargin;
     const float floor_t = score_threshold - margin;  // -inf stays -inf
 
+    SelectArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.nq = nq;
+    sa.tau_margin = margin;
+    sa.tau_floor = floor_t;
+    sa.tau_k = k;
+
+    // level 0: DENSE pass over the seed sample (or the whole shard when it is small)
+    rc = launch_scan_tc(kModeDense, db, n_rows, sp.seed_stride, sp.d_pad, sp.qb, sp.tc, nullptr, nullptr, nullptr, 0,
+                        sp.dense, sp.dense_ld, sm, stream);
+    if (rc) return rc;
+    sa.dense = sp.dense;
+    sa.dense_ld = sp.dense_ld;
+    sa.n_dense = sp.seed_cols;
     if (sp.n_levels == 0) {
-        // tiny shard: one DENSE pass over all rows, exact top-K2 of the dense block, fp32 re-score
-        rc = launch_scan_tc(kModeDense, db, n_rows, 1, db_ld, sp.d_pad, sp.qb, sp.tc, nullptr, nullptr, nullptr, 0,
-                            sp.dense, sp.dense_ld, sm, stream);
+        // the sample IS the shard (dense column == row): exact top-K2 by tensor score, then fp32 re-score
+        sa.K = sp.K2;
+        sa.out = sp.bufA;
+        sa.out_ld = sp.K2;
+        rc = launch_select(sa, nq, stream);
         if (rc) return rc;
-        TopkSrc src = {sp.dense, sp.dense_ld, nullptr, 0, nullptr, 0, n_rows};
-        rc = reduce_topk(src, nq, sp.K2, sp.K2, sp.bufA, sp.bufB, nullptr, nullptr, 0, 0.f, 0.f, &top, &top_ld, stream);
-        if (rc) return rc;
-        fa.top = top;
-        fa.top_ld = top_ld;
+        fa.top = sp.bufA;
+        fa.top_ld = sp.K2;
         fa.rescore = 1;
         fa.margin = margin;
         fa.cnt = nullptr;
         return launch_final(fa, nq, stream);
     }
-
-    // level 0: DENSE seed over a strided sample -> tau[0]
-    init_tau_kernel<<<(nq_pad * (sp.n_levels + 1) + 255) / 256, 256, 0, stream>>>(sp.tau, nq, nq_pad, floor_t,
-                                                                                  sp.n_levels + 1);
-    RVO_LAUNCHED();
-    rc = launch_scan_tc(kModeDense, db, sp.dense_rows, sp.dense_stride, db_ld, sp.d_pad, sp.qb, sp.tc, nullptr, nullptr,
-                        nullptr, 0, sp.dense, sp.dense_ld, sm, stream);
+    sa.K = k;
+    sa.tau_out = sp.tau;
+    rc = launch_select(sa, nq_pad, stream);
     if (rc) return rc;
-    {
-        TopkSrc src = {sp.dense, sp.dense_ld, nullptr, 0, nullptr, 0, sp.dense_rows};
-        rc = reduce_topk(src, nq, k, k, sp.bufA, sp.bufB, sp.tau, nullptr, k, margin, floor_t, &top, &top_ld, stream);
-        if (rc) return rc;
-    }
-    // FILTER levels: each tightens tau on a larger strided sample; the last one scans every row
+
+    // FILTER levels: each tightens tau on a larger tile sample; the last one scans every row
     for (int L = 0; L < sp.n_levels; ++L) {
         const bool last = L == sp.n_levels - 1;
         int* cnt = sp.cnt + (size_t)L * nq_pad;
         const float* tau_in = sp.tau + (size_t)L * nq_pad;
         if (last && (rc = scan_timer(true, stream))) return rc;
-        rc = launch_scan_tc(kModeFilter, db, sp.level_rows[L], sp.level_stride[L], db_ld, sp.d_pad, sp.qb, sp.tc, tau_in,
-                            sp.cand, cnt, sp.cap, nullptr, 0, sm, stream);
+        rc = launch_scan_tc(kModeFilter, db, n_rows, sp.level_stride[L], sp.d_pad, sp.qb, sp.tc, tau_in, sp.cand, cnt, sp.cap,
+                            nullptr, 0, sm, stream);
         if (rc) return rc;
         if (last && (rc = scan_timer(false, stream))) return rc;
-        TopkSrc src = {nullptr, 0, sp.cand, sp.cap, cnt, sp.cap, sp.cap};
+        memset(&sa, 0, sizeof(sa));
+        sa.nq = nq;
+        sa.keys = sp.cand;
+        sa.keys_ld = sp.cap;
+        sa.cnt = cnt;
+        sa.cap = sp.cap;
         if (!last) {
-            rc = reduce_topk(src, nq, k, k, sp.bufA, sp.bufB, sp.tau + (size_t)(L + 1) * nq_pad, tau_in, k, margin, floor_t,
-                             &top, &top_ld, stream);
+            sa.K = k;
+            sa.tau_out = sp.tau + (size_t)(L + 1) * nq_pad;
+            sa.tau_prev = tau_in;
+            sa.tau_k = k;
+            sa.tau_margin = margin;
+            sa.tau_floor = floor_t;
+            rc = launch_select(sa, nq_pad, stream);
             if (rc) return rc;
         } else {
-            rc = reduce_topk(src, nq, sp.K2, sp.K2, sp.bufA, sp.bufB, nullptr, nullptr, 0, 0.f, 0.f, &top, &top_ld, stream);
+            sa.K = sp.K2;
+            sa.out = sp.bufA;
+            sa.out_ld = sp.K2;
+            rc = launch_select(sa, nq, stream);
             if (rc) return rc;
-            fa.top = top;
-            fa.top_ld = top_ld;
+            fa.top = sp.bufA;
+            fa.top_ld = sp.K2;
             fa.rescore = 1;
             fa.margin = margin;
             fa.cnt = cnt;
@@ -455,15 +478,20 @@ int rvo_padded_queries(int32_t nq, int32_t d) {
     return rc ? rc : tc.nq_pad;
 }
 
-int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_ld, const float* queries, int32_t nq,
-                     int64_t row_stride, int64_t n_sample, float* out, int64_t out_ld, void* workspace,
-                     size_t workspace_bytes, void* stream_) {
+int rvo_scan_tile_rows(int32_t nq, int32_t d) {
+    TcPlan tc;
+    if (nq <= 0 || d <= 0) return RVO_E_INVALID;
+    int rc = plan_scan_tc(nq, (d + kBlockK - 1) / kBlockK * kBlockK, (int)opt_m_sub.load(), &tc);
+    return rc ? rc : kBlockM * tc.m_sub;
+}
+
+int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad_in, const float* queries, int32_t nq,
+                     int64_t tile_stride, float* out, int64_t out_ld, void* workspace, size_t workspace_bytes,
+                     void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     RVO_REQUIRE(db && queries && out && workspace, "scores_dense: null pointer");
-    RVO_REQUIRE(n_rows > 0 && d > 0 && nq > 0 && row_stride >= 1 && n_sample >= 1 && out_ld >= n_sample,
-                "scores_dense: bad shape");
-    RVO_REQUIRE((n_sample - 1) * row_stride < n_rows, "scores_dense: sample exceeds the DB");
-    RVO_REQUIRE(db_ld % kBlockK == 0 && db_ld >= d, "scores_dense: db_ld must be a multiple of 64 and >= d");
+    RVO_REQUIRE(n_rows > 0 && d > 0 && nq > 0 && tile_stride >= 1, "scores_dense: bad shape");
+    RVO_REQUIRE(d_pad_in == (d + kBlockK - 1) / kBlockK * kBlockK, "scores_dense: d_pad must be d rounded up to 64");
     RVO_REQUIRE(((uintptr_t)workspace & 1023) == 0, "scores_dense: workspace must be 1024-byte aligned");
     int sm = 0;
     int rc = select_device_of(db, &sm);
@@ -472,6 +500,8 @@ int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_l
     TcPlan tc;
     rc = plan_scan_tc(nq, d_pad, (int)opt_m_sub.load(), &tc);
     if (rc) return rc;
+    RVO_REQUIRE(out_ld >= scan_tc_sample_rows(n_rows, tc, tile_stride), "scores_dense: out_ld=%lld too small",
+                (long long)out_ld);
     Arena ar(workspace, workspace_bytes);
     uint16_t* qb = ar.take<uint16_t>((size_t)tc.nq_pad * d_pad, 1024);
     if (!ar.ok()) {
@@ -479,10 +509,10 @@ int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t db_l
         return RVO_E_WORKSPACE;
     }
     RVO_CUDA(cudaMemsetAsync(qb, 0, (size_t)tc.nq_pad * d_pad * 2, stream));
-    rc = launch_normalize_rows(queries, nq, d, d, qb, d_pad, nullptr, 0, stream);
+    rc = launch_normalize_rows(queries, nq, d, d, qb, d_pad, -1, nullptr, 0, stream);
     if (rc) return rc;
-    return launch_scan_tc(kModeDense, db, n_sample, row_stride, db_ld, d_pad, qb, tc, nullptr, nullptr, nullptr, 0, out,
-                          out_ld, sm, stream);
+    return launch_scan_tc(kModeDense, db, n_rows, tile_stride, d_pad, qb, tc, nullptr, nullptr, nullptr, 0, out, out_ld, sm,
+                          stream);
 }
 
 int rvo_merge_topk(const int64_t* ids, const float* scores, const int32_t* counts, int32_t G, int32_t nq, int32_t k,

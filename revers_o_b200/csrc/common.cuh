@@ -87,6 +87,17 @@ __host__ __device__ __forceinline__ unsigned long long make_key(float score, uin
 __host__ __device__ __forceinline__ float key_score(unsigned long long k) { return orderable_f32((uint32_t)(k >> 32)); }
 __host__ __device__ __forceinline__ uint32_t key_row(unsigned long long k) { return 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFu); }
 
+// ---- tiled DB storage ------------------------------------------------------------------------------
+// bf16 element (row, col) of a DB stored as [row / 128][d_pad / 64][128][64]: every (row block, k-chunk)
+// tile is one contiguous 16 KiB block, which is exactly one TMA box of the scan kernel, so the scan
+// streams HBM in long contiguous bursts instead of 128-byte pieces 2 KiB apart.
+constexpr int kTileRows = 128;
+constexpr int kTileCols = 64;
+__host__ __device__ __forceinline__ size_t tiled_offset(long long row, int col, int nk) {
+    return ((size_t)(row >> 7) * (size_t)nk + (size_t)(col >> 6)) * (size_t)(kTileRows * kTileCols) +
+           (size_t)(row & 127) * kTileCols + (size_t)(col & 63);
+}
+
 // eps = 2^-8 bounds |<bf16(q),d> - <q,d>| for unit q, |d| <= 1 (||q - bf16(q)|| <= 2^-8 ||q||).
 // If t(k) is the k-th best TENSOR score of any subset, every item of the true top-k (ranked by the
 // fp32 re-score f) has f >= t(k) - eps, hence tensor score >= t(k) - 2 eps.  Thresholds taken from

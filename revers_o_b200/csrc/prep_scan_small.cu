@@ -8,10 +8,12 @@
 namespace rvo {
 
 // one warp per row: x / ||x||  (core_system.py:407,447; qdrant COSINE upsert/search normalisation)
+// dst_bf16: row-major [n, dst_ld] when tiled_row0 < 0, else the tiled DB storage (common.cuh) in which this
+// launch writes rows tiled_row0 .. tiled_row0 + n - 1 (dst_ld == d_pad).
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ src, long long n, int d,
                                                              long long src_ld, uint16_t* __restrict__ dst_bf16,
-                                                             long long dst_ld, float* __restrict__ dst_f32,
-                                                             long long f32_ld) {
+                                                             long long dst_ld, long long tiled_row0,
+                                                             float* __restrict__ dst_f32, long long f32_ld) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -26,10 +28,18 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
     const float nrm = sqrtf(ss);
     const float inv = nrm != 0.f ? 1.0f / nrm : 0.f;  // zero rows stay zero
     if (dst_bf16) {
-        uint16_t* o = dst_bf16 + (size_t)row * (size_t)dst_ld;
-        for (long long i = lane; i < dst_ld; i += 32) {
-            const float v = i < d ? s[i] * inv : 0.f;
-            o[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+        if (tiled_row0 < 0) {
+            uint16_t* o = dst_bf16 + (size_t)row * (size_t)dst_ld;
+            for (long long i = lane; i < dst_ld; i += 32) {
+                const float v = i < d ? s[i] * inv : 0.f;
+                o[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+            }
+        } else {
+            const int nk = (int)(dst_ld / kTileCols);
+            for (int i = lane; i < (int)dst_ld; i += 32) {
+                const float v = i < d ? s[i] * inv : 0.f;
+                dst_bf16[tiled_offset(tiled_row0 + row, i, nk)] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+            }
         }
     }
     if (dst_f32) {
@@ -39,10 +49,11 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
 }
 
 int launch_normalize_rows(const float* src, long long n, int d, long long src_ld, uint16_t* dst_bf16, long long dst_ld,
-                          float* dst_f32, long long f32_ld, cudaStream_t stream) {
+                          long long tiled_row0, float* dst_f32, long long f32_ld, cudaStream_t stream) {
     if (n <= 0) return RVO_OK;
     const long long blocks = (n + 7) / 8;
-    normalize_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, n, d, src_ld, dst_bf16, dst_ld, dst_f32, f32_ld);
+    normalize_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, n, d, src_ld, dst_bf16, dst_ld, tiled_row0, dst_f32,
+                                                                f32_ld);
     RVO_LAUNCHED();
     return RVO_OK;
 }
@@ -50,9 +61,14 @@ int launch_normalize_rows(const float* src, long long n, int d, long long src_ld
 // ---- small-Q scan --------------------------------------------------------------------------------
 // One warp per pair of DB rows; lane l owns the 16-byte chunks l, l+32, ... of a row, and keeps the
 // matching slices of all NQ queries in registers (no shared-memory traffic in the loop).
+// uint4 index of the 16-byte chunk `idx` (0 .. d_pad/8) of row `r` in the tiled DB storage
+__device__ __forceinline__ size_t tiled_u4(long long r, int idx, int nk) {
+    return (((size_t)(r >> 7) * (size_t)nk + (size_t)(idx >> 3)) * kTileRows + (size_t)(r & 127)) * 8 + (size_t)(idx & 7);
+}
+
 template <int NQ, int CPL>
 __global__ void __launch_bounds__(256) scan_small_kernel(const uint4* __restrict__ db, long long n_rows,
-                                                         long long ld_u4, int nchunks, const float* __restrict__ qn,
+                                                         int nk, int nchunks, const float* __restrict__ qn,
                                                          long long qn_ld, float* __restrict__ out, long long out_ld) {
     const int lane = threadIdx.x & 31;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -77,8 +93,8 @@ __global__ void __launch_bounds__(256) scan_small_kernel(const uint4* __restrict
             a[0][c] = make_uint4(0, 0, 0, 0);
             a[1][c] = make_uint4(0, 0, 0, 0);
             if (idx < nchunks) {
-                a[0][c] = __ldcs(db + (size_t)r0 * ld_u4 + idx);
-                if (two) a[1][c] = __ldcs(db + (size_t)(r0 + 1) * ld_u4 + idx);
+                a[0][c] = __ldcs(db + tiled_u4(r0, idx, nk));
+                if (two) a[1][c] = __ldcs(db + tiled_u4(r0 + 1, idx, nk));
             }
         }
         float acc[2][NQ];
@@ -123,7 +139,7 @@ __global__ void __launch_bounds__(256) scan_small_kernel(const uint4* __restrict
 
 // Any row length: queries live in shared memory (slower; rows longer than 2048 elements only).
 __global__ void __launch_bounds__(256) scan_small_generic_kernel(const uint4* __restrict__ db, long long n_rows,
-                                                                 long long ld_u4, int nchunks, int nq,
+                                                                 int nk, int nchunks, int nq,
                                                                  const float* __restrict__ qn, long long qn_ld,
                                                                  float* __restrict__ out, long long out_ld) {
     extern __shared__ float sq[];  // [nq][nchunks*8]
@@ -138,7 +154,7 @@ __global__ void __launch_bounds__(256) scan_small_generic_kernel(const uint4* __
 #pragma unroll
         for (int q = 0; q < RVO_SMALL_Q; ++q) acc[q] = 0.f;
         for (int c = lane; c < nchunks; c += 32) {
-            const uint4 v = __ldcs(db + (size_t)r * ld_u4 + c);
+            const uint4 v = __ldcs(db + tiled_u4(r, c, nk));
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int q = 0; q < RVO_SMALL_Q; ++q)
@@ -162,7 +178,7 @@ __global__ void __launch_bounds__(256) scan_small_generic_kernel(const uint4* __
 }
 
 template <int NQ, int CPL>
-static int launch_small_t(const uint16_t* db, long long n_rows, long long db_ld, int d_pad, const float* qn,
+static int launch_small_t(const uint16_t* db, long long n_rows, int d_pad, const float* qn,
                           long long qn_ld, float* out, long long out_ld, int sm_count, cudaStream_t stream) {
     int per_sm = 0;
     RVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_small_kernel<NQ, CPL>, 256, 0));
@@ -170,19 +186,19 @@ static int launch_small_t(const uint16_t* db, long long n_rows, long long db_ld,
     long long want = (n_rows + 15) / 16;  // 8 warps x 2 rows per block per iteration
     long long grid = (long long)sm_count * per_sm;
     if (grid > want) grid = want;
-    scan_small_kernel<NQ, CPL><<<(unsigned)grid, 256, 0, stream>>>((const uint4*)db, n_rows, db_ld / 8, d_pad / 8, qn,
-                                                                  qn_ld, out, out_ld);
+    scan_small_kernel<NQ, CPL><<<(unsigned)grid, 256, 0, stream>>>((const uint4*)db, n_rows, d_pad / kTileCols, d_pad / 8,
+                                                                  qn, qn_ld, out, out_ld);
     RVO_LAUNCHED();
     return RVO_OK;
 }
 
 // nq in 1..RVO_SMALL_Q; qn rows beyond nq (up to the instantiated NQ) must exist and be zero.
-int launch_scan_small(const uint16_t* db, long long n_rows, long long db_ld, int d_pad, const float* qn, long long qn_ld,
+int launch_scan_small(const uint16_t* db, long long n_rows, int d_pad, const float* qn, long long qn_ld,
                       int nq, float* out, long long out_ld, int sm_count, cudaStream_t stream) {
     if (n_rows <= 0) return RVO_OK;
     const int cpl = (d_pad / 8 + 31) / 32;
 #define RVO_SMALL_CASE(NQ_, CPL_)                                                                          \
-    return launch_small_t<NQ_, CPL_>(db, n_rows, db_ld, d_pad, qn, qn_ld, out, out_ld, sm_count, stream)
+    return launch_small_t<NQ_, CPL_>(db, n_rows, d_pad, qn, qn_ld, out, out_ld, sm_count, stream)
     if (cpl <= 4) {
         if (nq == 1) RVO_SMALL_CASE(1, 4);
         if (nq == 2) RVO_SMALL_CASE(2, 4);
@@ -205,8 +221,8 @@ int launch_scan_small(const uint16_t* db, long long n_rows, long long db_ld, int
     long long grid = (long long)sm_count * 4;
     long long want = (n_rows + 7) / 8;
     if (grid > want) grid = want;
-    scan_small_generic_kernel<<<(unsigned)grid, 256, smem, stream>>>((const uint4*)db, n_rows, db_ld / 8, d_pad / 8, nq, qn,
-                                                                    qn_ld, out, out_ld);
+    scan_small_generic_kernel<<<(unsigned)grid, 256, smem, stream>>>((const uint4*)db, n_rows, d_pad / kTileCols, d_pad / 8,
+                                                                    nq, qn, qn_ld, out, out_ld);
     RVO_LAUNCHED();
     return RVO_OK;
 }

@@ -6,9 +6,9 @@
 namespace rvo {
 
 int launch_normalize_rows(const float* src, long long n, int d, long long src_ld, uint16_t* dst_bf16, long long dst_ld,
-                          float* dst_f32, long long f32_ld, cudaStream_t stream);
+                          long long tiled_row0, float* dst_f32, long long f32_ld, cudaStream_t stream);
 
-int launch_scan_small(const uint16_t* db, long long n_rows, long long db_ld, int d_pad, const float* qn, long long qn_ld,
+int launch_scan_small(const uint16_t* db, long long n_rows, int d_pad, const float* qn, long long qn_ld,
                       int nq, float* out, long long out_ld, int sm_count, cudaStream_t stream);
 
 size_t mask_pool_workspace_bytes(int B, int M, int P, int D);

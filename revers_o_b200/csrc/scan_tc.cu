@@ -2,16 +2,17 @@
 // epilogue.  Replaces the `vectors @ query` + argsort of qdrant-local search behind
 // core_system.py:659-664 for batches of more than RVO_SMALL_Q queries.
 //
-// Roles inside one persistent CTA (192 threads, one CTA per SM):
+// Roles inside one persistent CTA (320 threads, one CTA per SM):
 //   warp 0 (one elected lane)  TMA producer: DB sub-tiles (128 rows x 64 k, 128B-swizzled) and, unless
 //                              the query block is resident, the query k-chunk, into a smem stage ring
 //   warp 1 (one elected lane)  tcgen05.mma issuer: D[128 rows x NQ] += A(db) * B(queries)^T, fp32
 //                              accumulators in TMEM slots (ring of 512/NQ slots)
-//   warps 2-5                  epilogue: tcgen05.ld one TMEM lane (= one DB row) per thread,
-//                                FILTER: compare the row's NQ scores with the per-query thresholds tau
-//                                        (smem broadcast), queue survivors in smem, then append them
-//                                        as ordering keys to the per-query candidate lists in HBM;
-//                                DENSE : write the scores (threshold-seeding pass over a strided sample).
+//   warps 2-9                  epilogue, two warps per TMEM lane quarter (interleaved 16-column chunks):
+//                              tcgen05.ld one TMEM lane (= one DB row) per thread,
+//                                FILTER: compare the row's scores with the per-query thresholds tau
+//                                        (smem, 128-bit broadcast loads), queue survivors in smem, then
+//                                        append them as ordering keys to the per-query candidate lists;
+//                                DENSE : write the scores (threshold-seeding pass over sampled tiles).
 // The full score matrix never reaches HBM in FILTER mode.
 //
 // Layout choice: DB rows are the MMA M dimension (TMEM lanes), queries the N dimension
@@ -26,17 +27,18 @@ namespace rvo {
 
 using namespace ptx;
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
 template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constant__ CUtensorMap tmap_q,
                const ScanParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];  // no static smem in this kernel: base is 1024-aligned
 
     uint8_t* s_res = smem;                                   // resident query block (optional)
     uint8_t* s_stages = smem + p.off_stages;                 // stage ring
-    unsigned long long* s_queue = (unsigned long long*)(smem + p.off_queue);  // [kQueueCap][128]
-    float* s_tau = (float*)(smem + p.off_tau);               // [4 warps][256]
+    unsigned long long* s_queue = (unsigned long long*)(smem + p.off_queue);  // [kQueueCap][kEpiThreads]
+    float* s_tau = (float*)(smem + p.off_tau);               // [2][256] double-buffered by work item
     uint64_t* s_bars = (uint64_t*)(smem + p.off_bars);
     uint64_t* bar_full = s_bars;                             // [kMaxStages] TMA -> MMA
     uint64_t* bar_empty = s_bars + kMaxStages;               // [kMaxStages] MMA -> TMA
@@ -50,17 +52,22 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
     const int num_k = p.d_pad / kBlockK;
     const int nq_blk = p.nq_blk;
     const int m_sub = p.m_sub;
+    const int tile_rows = kBlockM * m_sub;
     const uint32_t q_chunk_bytes = (uint32_t)nq_blk * 128u;
     const long long total_work = p.num_super * (long long)p.num_qblk;
 
     if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) {
+            printf("rvo: dynamic shared memory base not 1024-byte aligned\n");
+            __trap();
+        }
         for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], 1);
         }
         for (int i = 0; i < kMaxSlots; ++i) {
             mbar_init(&bar_tfull[i], 1);
-            mbar_init(&bar_tempty[i], 4);  // lane 0 of each epilogue warp
+            mbar_init(&bar_tempty[i], kEpiWarps);  // lane 0 of each epilogue warp
         }
         mbar_init(bar_res, 1);
         fence_mbar_init();
@@ -92,7 +99,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
             for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const long long st = w / p.num_qblk;
                 const int qb = (int)(w - st * p.num_qblk);
-                const long long row0 = st * (long long)(kBlockM * m_sub);
+                const long long row0 = st * p.super_stride * tile_rows;
                 long long left = (p.n_rows - row0 + kBlockM - 1) / kBlockM;
                 const int m_valid = left < m_sub ? (int)left : m_sub;
                 const uint32_t bytes = (uint32_t)m_valid * kSubTileBytes + (p.resident_q ? 0u : q_chunk_bytes);
@@ -101,8 +108,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                     mbar_expect_tx(&bar_full[stage], bytes);
                     uint8_t* sA = s_stages + (size_t)stage * p.stage_bytes;
                     for (int j = 0; j < m_valid; ++j)
-                        tma_load_2d(&tmap_db, &bar_full[stage], sA + j * kSubTileBytes, kc * kBlockK,
-                                    (int)(row0 + j * kBlockM), hint_db);
+                        // tiled DB: tile (row block, k-chunk) is one contiguous 16 KiB box of 128 "virtual rows"
+                        tma_load_2d(&tmap_db, &bar_full[stage], sA + j * kSubTileBytes, 0,
+                                    (int)(((row0 / kBlockM + j) * num_k + kc) * kBlockM), hint_db);
                     if (!p.resident_q)
                         tma_load_2d(&tmap_q, &bar_full[stage], sA + m_sub * kSubTileBytes, kc * kBlockK, qb * nq_blk,
                                     kEvictLast);
@@ -122,7 +130,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
             uint32_t stage = 0, phase = 0, acc = 0;
             for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const long long st = w / p.num_qblk;
-                const long long row0 = st * (long long)(kBlockM * m_sub);
+                const long long row0 = st * p.super_stride * tile_rows;
                 long long left = (p.n_rows - row0 + kBlockM - 1) / kBlockM;
                 const int m_valid = left < m_sub ? (int)left : m_sub;
                 for (int kc = 0; kc < num_k; ++kc) {
@@ -153,29 +161,35 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int ew = warp & 3;  // TMEM lane quarter this warp may read
-        const uint32_t lane_base = (uint32_t)ew * 32u;
-        const int et = ew * 32 + lane;  // 0..127 : epilogue thread == TMEM lane == DB row in sub-tile
-        float* tau_w = s_tau + ew * 256;
+        // ===================== epilogue (warps 2..9) =====================
+        const int ew = warp - 2;                         // 0..7
+        const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;  // TMEM lane quarter this warp may read
+        const int half = ew >> 2;                        // which interleaved set of 16-column chunks
+        const int et = (int)lane_base + lane;            // 0..127: TMEM lane == DB row inside the sub-tile
+        const int qt = half * kBlockM + et;              // 0..255: private queue column
         const uint32_t ns = (uint32_t)p.num_slots;
         const int nchunks = nq_blk / 16;
         uint32_t acc = 0;
+        uint32_t wcount = 0;
         int cur_qb = -1;
 
-        for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (long long w = blockIdx.x; w < total_work; w += gridDim.x, ++wcount) {
             const long long st = w / p.num_qblk;
             const int qb = (int)(w - st * p.num_qblk);
-            const long long row0 = st * (long long)(kBlockM * m_sub);
+            const long long row0 = st * p.super_stride * tile_rows;
             long long left = (p.n_rows - row0 + kBlockM - 1) / kBlockM;
             const int m_valid = left < m_sub ? (int)left : m_sub;
             const int q0 = qb * nq_blk;
+            const uint32_t tbuf = p.num_qblk > 1 ? (wcount & 1u) : 0u;
+            const float* tau_s = s_tau + tbuf * 256;
 
             if (MODE == kModeFilter && qb != cur_qb) {
-                __syncwarp();
-                for (int i = lane; i < nq_blk; i += 32) tau_w[i] = p.tau[q0 + i];
-                __syncwarp();
-                cur_qb = qb;
+                // double-buffered by work item; the barrier also orders "everyone left work w-1" before
+                // anyone overwrites that buffer at work w+1
+                const int i = ew * 32 + lane;
+                if (i < nq_blk) s_tau[tbuf * 256 + i] = p.tau[q0 + i];
+                epi_bar_sync();
+                cur_qb = p.num_qblk > 1 ? -1 : qb;       // several query blocks: reload every work item
             }
 
             for (int j = 0; j < m_valid; ++j) {
@@ -188,15 +202,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                 const bool valid = row < p.n_rows;
 
                 if (MODE == kModeDense) {
-                    for (int c = 0; c < nchunks; ++c) {
+                    const long long col = st * tile_rows + (long long)j * kBlockM + et;  // sample index
+                    for (int c = half; c < nchunks; c += 2) {
                         uint32_t v[16];
-                        __syncwarp();
                         tmem_ld_x16(taddr + (uint32_t)c * 16u, v);
                         tmem_ld_wait();
-                        if (valid) {
-                            float* o = p.dense + (size_t)(q0 + c * 16) * (size_t)p.dense_ld + (size_t)row;
+                        {   // rows past the end of the DB (zero-filled by TMA) must never rank: -inf
+                            float* o = p.dense + (size_t)(q0 + c * 16) * (size_t)p.dense_ld + (size_t)col;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) o[(size_t)i * (size_t)p.dense_ld] = __uint_as_float(v[i]);
+                            for (int i = 0; i < 16; ++i)
+                                o[(size_t)i * (size_t)p.dense_ld] = valid ? __uint_as_float(v[i]) : -__int_as_float(0x7f800000);
                         }
                     }
                     tc_fence_before();
@@ -204,7 +219,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                     if (lane == 0) mbar_arrive(&bar_tempty[slot]);
                 } else {
                     int n = 0;
-                    const uint32_t key_row_bits = 0xFFFFFFFFu - (uint32_t)(row * p.row_stride);
+                    const uint32_t key_row_bits = 0xFFFFFFFFu - (uint32_t)row;
                     // Append queued survivors (score, query column) of this row to the candidate lists.
                     auto flush = [&](int cnt) {
                         for (int e = 0; e < cnt; e += 4) {
@@ -213,7 +228,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
                                 if (e + u < cnt) {
-                                    ent[u] = s_queue[(e + u) * 128 + et];
+                                    ent[u] = s_queue[(e + u) * kEpiThreads + qt];
                                     slot_pos[u] = atomicAdd(p.cand_cnt + q0 + (int)(ent[u] & 0xFFFFu), 1);
                                 }
 #pragma unroll
@@ -226,27 +241,31 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                                 }
                         }
                     };
-                    for (int c = 0; c < nchunks; ++c) {
+                    for (int c = half; c < nchunks; c += 2) {
                         uint32_t v[16];
-                        __syncwarp();
                         tmem_ld_x16(taddr + (uint32_t)c * 16u, v);
                         tmem_ld_wait();
+                        if (valid) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (n > kQueueCap - 8) {  // rare: keep room for 8 more
-                                flush(n);
-                                n = 0;
-                            }
+                            for (int h = 0; h < 2; ++h) {
+                                if (n > kQueueCap - 8) {  // rare: keep room for 8 more
+                                    flush(n);
+                                    n = 0;
+                                }
+                                const float4 t0 = *(const float4*)(tau_s + c * 16 + h * 8);
+                                const float4 t1 = *(const float4*)(tau_s + c * 16 + h * 8 + 4);
+                                const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int col = c * 16 + h * 8 + i;
-                                const float s = __uint_as_float(v[h * 8 + i]);
-                                if (valid && s >= tau_w[col]) {
-                                    s_queue[n * 128 + et] = ((unsigned long long)v[h * 8 + i] << 32) | (unsigned)col;
-                                    ++n;
+                                for (int i = 0; i < 8; ++i) {
+                                    if (__uint_as_float(v[h * 8 + i]) >= tt[i]) {
+                                        s_queue[n * kEpiThreads + qt] =
+                                            ((unsigned long long)v[h * 8 + i] << 32) | (unsigned)(c * 16 + h * 8 + i);
+                                        ++n;
+                                    }
                                 }
                             }
                         }
+                        __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next one
                     }
                     // TMEM slot is drained: hand it back before paying the atomics' latency.
                     tc_fence_before();
@@ -285,7 +304,7 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// bf16 [rows, d_pad] matrix viewed through rows `row_stride` apart; box = 64 elements x box_rows.
+// bf16 [rows, d_pad] row-major matrix; box = 64 elements x box_rows, 128-byte swizzle.
 static int make_tmap(CUtensorMap* m, const void* base, long long rows, int d_pad, long long pitch_elems,
                      int box_rows, bool promote) {
     PFN_encodeTiled enc = get_encode();
@@ -328,8 +347,8 @@ int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl) {
     pl->num_slots = 512 / pl->slot_w;
     if (pl->num_slots > kMaxSlots) pl->num_slots = kMaxSlots;
 
-    const size_t fixed = (size_t)kQueueCap * 128 * 8 + 4 * 256 * 4 + 512;
-    const size_t budget = (size_t)kSmemLimit - 1024 - fixed;
+    const size_t fixed = (size_t)kQueueCap * kEpiThreads * 8 + 2 * 256 * 4 + 512;
+    const size_t budget = (size_t)kSmemLimit - fixed;
     const size_t res_bytes = (size_t)pl->nq_blk * d_pad * 2;
 
     pl->resident = 0;
@@ -351,29 +370,45 @@ int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl) {
     pl->num_stages = (int)stages;
     pl->off_stages = res;  // multiple of 1024: nq_blk % 16 == 0 and d_pad % 64 == 0
     pl->off_queue = pl->off_stages + stages * pl->stage_bytes;
-    pl->off_tau = pl->off_queue + (size_t)kQueueCap * 128 * 8;
-    pl->off_bars = pl->off_tau + 4 * 256 * 4;
-    pl->smem_bytes = pl->off_bars + 512 + 1024;
+    pl->off_tau = pl->off_queue + (size_t)kQueueCap * kEpiThreads * 8;
+    pl->off_bars = pl->off_tau + 2 * 256 * 4;
+    pl->smem_bytes = pl->off_bars + 512;
     return RVO_OK;
 }
 
-int launch_scan_tc(int mode, const uint16_t* db, long long n_sample, long long row_stride, long long db_ld, int d_pad,
+long long scan_tc_sample_rows(long long n_rows, const TcPlan& pl, long long super_stride) {
+    const long long T = (long long)kBlockM * pl.m_sub;
+    const long long supers = (n_rows + T - 1) / T;
+    return (supers + super_stride - 1) / super_stride * T;
+}
+
+int launch_scan_tc(int mode, const uint16_t* db, long long n_rows, long long super_stride, int d_pad,
                    const uint16_t* q_bf16, const TcPlan& pl, const float* tau, unsigned long long* cand,
                    int* cand_cnt, int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream) {
-    if (n_sample <= 0) return RVO_OK;
-    if (n_sample >= (1ll << 31) || n_sample * row_stride >= (1ll << 32)) {
-        set_error("launch_scan_tc: shard too large (%lld rows, stride %lld); shard the DB", n_sample, row_stride);
+    if (n_rows <= 0) return RVO_OK;
+    if (n_rows >= (1ll << 31)) {
+        set_error("launch_scan_tc: shard too large (%lld rows); shard the DB", n_rows);
         return RVO_E_INVALID;
     }
+    if (super_stride < 1) super_stride = 1;
     CUtensorMap tm_db, tm_q;
-    int rc = make_tmap(&tm_db, db, n_sample, d_pad, db_ld * row_stride, kBlockM, row_stride == 1);
+    // DB storage is tiled [row block of 128][k-chunk][128 rows][64 elements]: as a 2-D tensor of 128-byte
+    // "virtual rows" every (row block, k-chunk) box is one contiguous 16 KiB read
+    const long long row_blocks = (n_rows + kBlockM - 1) / kBlockM;
+    const long long vrows = row_blocks * (d_pad / kBlockK) * kBlockM;
+    if (vrows >= (1ll << 31)) {
+        set_error("launch_scan_tc: shard too large (%lld rows x %d); shard the DB", n_rows, d_pad);
+        return RVO_E_INVALID;
+    }
+    int rc = make_tmap(&tm_db, db, vrows, kBlockK, kBlockK, kBlockM, false);
     if (rc) return rc;
     rc = make_tmap(&tm_q, q_bf16, pl.nq_pad, d_pad, d_pad, pl.nq_blk, false);
     if (rc) return rc;
 
     ScanParams p;
-    p.n_rows = n_sample;
-    p.row_stride = row_stride;
+    const long long T = (long long)kBlockM * pl.m_sub;
+    p.n_rows = n_rows;
+    p.super_stride = super_stride;
     p.d_pad = d_pad;
     p.nq_blk = pl.nq_blk;
     p.num_qblk = pl.num_qblk;
@@ -387,7 +422,7 @@ int launch_scan_tc(int mode, const uint16_t* db, long long n_sample, long long r
     p.off_queue = (uint32_t)pl.off_queue;
     p.off_tau = (uint32_t)pl.off_tau;
     p.off_bars = (uint32_t)pl.off_bars;
-    p.num_super = (n_sample + (long long)kBlockM * pl.m_sub - 1) / ((long long)kBlockM * pl.m_sub);
+    p.num_super = ((n_rows + T - 1) / T + super_stride - 1) / super_stride;
     p.tau = tau;
     p.cand = cand;
     p.cand_cnt = cand_cnt;

@@ -11,16 +11,18 @@ constexpr int kBlockK = 64;                               // bf16 per k-chunk ==
 constexpr int kSubTileBytes = kBlockM * kBlockK * 2;      // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kMaxSlots = 8;
-constexpr int kScanThreads = 192;                         // TMA warp + MMA warp + 4 epilogue warps
-constexpr int kQueueCap = 16;                             // smem survivor queue entries per DB row
+constexpr int kEpiWarps = 8;                              // two epilogue warps per TMEM lane quarter
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kScanThreads = 64 + kEpiThreads;            // TMA warp + MMA warp + epilogue warps
+constexpr int kQueueCap = 12;                             // smem survivor queue entries per epilogue thread
 constexpr int kSmemLimit = 232448;                        // 227 KiB opt-in dynamic smem per CTA
 constexpr int kModeDense = 0;
 constexpr int kModeFilter = 1;
 
 struct ScanParams {
-    long long n_rows;      // rows visible through the DB tensor map (sample rows when strided)
-    long long row_stride;  // DB row = sample row * row_stride
-    long long num_super;   // super-tiles of 128*m_sub rows
+    long long n_rows;        // DB rows
+    long long super_stride;  // tile sampling: only every super_stride-th super-tile is visited (1 = all)
+    long long num_super;     // visited super-tiles of 128*m_sub rows
     int d_pad, nq_blk, num_qblk, m_sub, num_stages, resident_q, slot_w, num_slots;
     uint32_t stage_bytes, off_stages, off_queue, off_tau, off_bars;
     // FILTER
@@ -39,7 +41,9 @@ struct TcPlan {
 };
 
 int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl);
-int launch_scan_tc(int mode, const uint16_t* db, long long n_sample, long long row_stride, long long db_ld, int d_pad,
+// columns of the DENSE output / rows visited when only every super_stride-th super-tile is scanned
+long long scan_tc_sample_rows(long long n_rows, const TcPlan& pl, long long super_stride);
+int launch_scan_tc(int mode, const uint16_t* db, long long n_rows, long long super_stride, int d_pad,
                    const uint16_t* q_bf16, const TcPlan& pl, const float* tau, unsigned long long* cand,
                    int* cand_cnt, int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream);
 

@@ -132,10 +132,12 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
             unsigned long long nk = 0ull;
             if (key_score(key) >= cut) {
                 const uint32_t row = key_row(key);
-                const uint4* r = (const uint4*)(a.db + (size_t)row * (size_t)a.db_ld);
+                // tiled DB storage: 16-byte chunk c of the row lives in tile (row/128, c/8)
+                const uint4* base = (const uint4*)a.db;
+                const int ntk = a.d_pad / kTileCols;
                 float acc = 0.f;
                 for (int c = lane; c < nchunk; c += 32) {
-                    const uint4 v = __ldg(r + c);
+                    const uint4 v = __ldg(base + (((size_t)(row >> 7) * ntk + (c >> 3)) * kTileRows + (row & 127)) * 8 + (c & 7));
                     const float4 q0 = __ldg((const float4*)(qv + c * 8));
                     const float4 q1 = __ldg((const float4*)(qv + c * 8 + 4));
                     acc = fmaf(__uint_as_float(v.x << 16), q0.x, acc);
@@ -170,6 +172,157 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
     if (n_out_local) atomicAdd(&s_flag, n_out_local);
     __syncthreads();
     if (threadIdx.x == 0) a.out_counts[q] = s_flag;
+}
+
+// ---- exact top-K of one query's candidates by histogram refinement ---------------------------------
+// One CTA per query.  The 64-bit ordering keys are unique (score, row), so the K-th largest key is
+// found by narrowing a key range with 2048-bin histograms until at most kSelSort keys lie at or above
+// the range's lower bound; those are compacted into shared memory and sorted.  Work is O(n) per
+// round (1-2 rounds in practice) instead of the O(n log^2 n) of sorting every candidate.
+__device__ __forceinline__ unsigned long long select_load(const SelectArgs& a, int q, long long i) {
+    if (a.dense) {  // -inf marks rows past the end of the DB: empty key
+        const float v = a.dense[(size_t)q * (size_t)a.dense_ld + (size_t)i];
+        return v == -__int_as_float(0x7f800000) ? 0ull : make_key(v, (uint32_t)i);
+    }
+    return a.keys[(size_t)q * (size_t)a.keys_ld + (size_t)i];
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a) {
+    __shared__ int hist[kSelBins];
+    __shared__ unsigned long long sbuf[kSelSort];
+    __shared__ unsigned long long s_red[2 * (kSelThreads / 32)];
+    __shared__ unsigned long long s_lo, s_hi;
+    __shared__ int s_above, s_count, s_done, s_shift;
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float INF = __int_as_float(0x7f800000);
+    if (q >= a.nq) {  // padded query rows of the tensor path never admit anything
+        if (a.tau_out && tid == 0) a.tau_out[q] = INF;
+        return;
+    }
+    long long n = a.dense ? a.n_dense : (long long)(a.cnt[q] < a.cap ? a.cnt[q] : a.cap);
+    int C = 0;  // keys in sbuf
+    if (n <= kSelSort) {
+        const int ns = next_pow2((int)(n > 2 ? n : 2));
+        for (int i = tid; i < ns; i += blockDim.x) sbuf[i] = i < n ? select_load(a, q, i) : 0ull;
+        __syncthreads();
+        bitonic_desc_u64(sbuf, ns);
+        C = (int)n;
+    } else {
+        // round 0: key range
+        unsigned long long lmin = ~0ull, lmax = 0ull;
+        for (long long i = tid; i < n; i += blockDim.x) {
+            const unsigned long long k = select_load(a, q, i);
+            lmin = k < lmin ? k : lmin;
+            lmax = k > lmax ? k : lmax;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long x = __shfl_xor_sync(0xFFFFFFFFu, lmin, o), y = __shfl_xor_sync(0xFFFFFFFFu, lmax, o);
+            lmin = x < lmin ? x : lmin;
+            lmax = y > lmax ? y : lmax;
+        }
+        if (lane == 0) { s_red[warp] = lmin; s_red[kSelThreads / 32 + warp] = lmax; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long mn = ~0ull, mx = 0ull;
+            for (int w = 0; w < kSelThreads / 32; ++w) {
+                mn = s_red[w] < mn ? s_red[w] : mn;
+                mx = s_red[kSelThreads / 32 + w] > mx ? s_red[kSelThreads / 32 + w] : mx;
+            }
+            s_lo = mn; s_hi = mx; s_above = 0; s_done = 0;
+        }
+        __syncthreads();
+        const int want = (int)(a.K < n ? a.K : n);
+        for (int round = 0; round < 8; ++round) {
+            const unsigned long long lo = s_lo, hi = s_hi;
+            int shift = 0;
+            while (((hi - lo) >> shift) >= (unsigned long long)kSelBins) ++shift;
+            for (int i = tid; i < kSelBins; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            for (long long i = tid; i < n; i += blockDim.x) {
+                const unsigned long long k = select_load(a, q, i);
+                if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // suffix sums from the top bin: lane l owns bins [64 l, 64 l + 64)
+                constexpr int per = kSelBins / 32;
+                int mine = 0;
+                for (int b = 0; b < per; ++b) mine += hist[lane * per + b];
+                int suffix = mine;  // inclusive suffix over lanes >= lane
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_down_sync(0xFFFFFFFFu, suffix, o);
+                    if (lane + o < 32) suffix += t;
+                }
+                const int need = want - s_above;
+                // the crossing lane: suffix >= need while the suffix of the next lane is < need
+                const int next = suffix - mine;
+                const bool crossing = suffix >= need && next < need;
+                if (crossing) {
+                    int run = next, b = per - 1;
+                    for (; b >= 0; --b) {
+                        run += hist[lane * per + b];
+                        if (run >= need) break;
+                    }
+                    const int bstar = lane * per + b;
+                    const int cge = s_above + run;                       // keys >= lower bound of bin bstar
+                    if (cge <= kSelSort || shift == 0) {
+                        s_lo = lo + ((unsigned long long)bstar << shift);
+                        s_done = 1;
+                    } else {
+                        s_above = s_above + run - hist[bstar];          // keys strictly above the bin
+                        s_lo = lo + ((unsigned long long)bstar << shift);
+                        s_hi = s_lo + ((1ull << shift) - 1ull);
+                    }
+                    s_shift = shift;
+                }
+            }
+            __syncthreads();
+            if (s_done) break;
+        }
+        // compaction of every key >= T, then a small sort
+        const unsigned long long T = s_lo;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        for (long long i = tid; i < n; i += blockDim.x) {
+            const unsigned long long k = select_load(a, q, i);
+            if (k >= T) {
+                const int at = atomicAdd(&s_count, 1);
+                if (at < kSelSort) sbuf[at] = k;
+            }
+        }
+        __syncthreads();
+        C = s_count < kSelSort ? s_count : kSelSort;
+        const int ns = next_pow2(C > 2 ? C : 2);
+        for (int i = C + tid; i < ns; i += blockDim.x) sbuf[i] = 0ull;
+        __syncthreads();
+        bitonic_desc_u64(sbuf, ns);
+    }
+    if (a.out) {
+        unsigned long long* out = a.out + (size_t)q * (size_t)a.out_ld;
+        for (int i = tid; i < a.K; i += blockDim.x) out[i] = i < C ? sbuf[i] : 0ull;
+    }
+    // The k-th best of ANY subset of the DB is a lower bound of the k-th best of the whole DB, so
+    // admitting `score >= tau` in the next scan level never drops a true top-k item.
+    if (a.tau_out && tid == 0) {
+        float t = a.tau_floor;
+        if (a.tau_prev && a.tau_prev[q] > t) t = a.tau_prev[q];
+        const unsigned long long key = (a.tau_k - 1) < C ? sbuf[a.tau_k - 1] : 0ull;
+        if (key) {
+            const float c = key_score(key) - a.tau_margin;
+            if (c > t) t = c;
+        }
+        a.tau_out[q] = t;
+    }
+}
+
+int launch_select(const SelectArgs& a, int grid_q, cudaStream_t stream) {
+    if (grid_q <= 0) return RVO_OK;
+    select_kernel<<<grid_q, kSelThreads, 0, stream>>>(a);
+    RVO_LAUNCHED();
+    return RVO_OK;
 }
 
 // ---- K3: merge of per-shard lists -------------------------------------------------------------

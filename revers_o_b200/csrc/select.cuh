@@ -27,6 +27,26 @@ struct ChunkTopkArgs {
     float tau_margin, tau_floor;
 };
 
+constexpr int kSelBins = 2048;    // histogram bins per refinement round
+constexpr int kSelSort = 2048;    // keys compacted and sorted in shared memory
+
+struct SelectArgs {
+    const float* dense;                 // dense mode: scores [nq][dense_ld], n_dense valid per query
+    long long dense_ld, n_dense;
+    const unsigned long long* keys;     // list mode: keys [nq][keys_ld], min(cnt[q], cap) valid
+    long long keys_ld;
+    const int* cnt;
+    int cap;
+    int K;                              // top keys wanted (<= 1024)
+    unsigned long long* out;            // [nq][out_ld] top-K keys, sorted descending, zero padded (or nullptr)
+    long long out_ld;
+    float* tau_out;                     // optional: tau_out[q] = max(tau_prev[q], score(key[tau_k-1]) - margin, floor)
+    const float* tau_prev;
+    int tau_k;
+    float tau_margin, tau_floor;
+    int nq;                             // CTAs q >= nq only write tau_out[q] = +inf (padded query rows)
+};
+
 struct FinalArgs {
     const unsigned long long* top;      // [nq][top_ld], first K2 sorted descending
     long long top_ld;
@@ -34,8 +54,7 @@ struct FinalArgs {
     int cap, K2, k;
     float score_threshold, margin;
     int rescore;                        // 1: keys carry bf16-query tensor scores -> fp32 re-score
-    const uint16_t* db;
-    long long db_ld;
+    const uint16_t* db;                 // tiled DB storage (common.cuh)
     int d_pad;
     const float* qn;                    // normalised fp32 queries [nq][qn_ld], zero padded to d_pad
     long long qn_ld;
@@ -46,6 +65,7 @@ struct FinalArgs {
 };
 
 int launch_chunk_topk(const ChunkTopkArgs& a, int num_chunks, int nq, cudaStream_t stream);
+int launch_select(const SelectArgs& a, int grid_q, cudaStream_t stream);
 int launch_final(const FinalArgs& a, int nq, cudaStream_t stream);
 int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts, long long ids_gs, long long scores_gs,
                  long long counts_gs, int G, int nq, int k, int64_t* out_ids, float* out_scores, int32_t* out_counts,

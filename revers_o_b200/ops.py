@@ -44,17 +44,59 @@ def d_pad_of(d: int) -> int:
     return (d + 63) // 64 * 64
 
 
-def normalize_rows(src: torch.Tensor, dst_bf16: torch.Tensor | None = None, want_f32: bool = False):
-    """L2-normalise fp32 rows (core_system.py:407,447; qdrant COSINE upsert).  Returns (bf16 [n,d_pad], f32|None)."""
+TILE_ROWS, TILE_COLS = 128, 64
+
+
+def db_alloc(n_rows: int, d: int, device) -> torch.Tensor:
+    """Zeroed tiled DB storage for n_rows rows: bf16 [ceil(n/128), d_pad/64, 128, 64] (include/revers_o_b200.h,
+    "DB storage layout"): every (row block, k-chunk) tile is one contiguous 16 KiB TMA box."""
+    return torch.zeros(((n_rows + TILE_ROWS - 1) // TILE_ROWS, d_pad_of(d) // TILE_COLS, TILE_ROWS, TILE_COLS),
+                       dtype=torch.bfloat16, device=device)
+
+
+def db_capacity(db: torch.Tensor) -> int:
+    return db.shape[0] * TILE_ROWS
+
+
+def tile_rows(x: torch.Tensor) -> torch.Tensor:
+    """Row-major bf16 [n, d] -> tiled storage (layout conversion for inputs/IO; a pure permutation)."""
+    n, d = x.shape
+    out = db_alloc(n, d, x.device)
+    nb, nk = out.shape[0], out.shape[1]
+    pad = torch.zeros((nb * TILE_ROWS, nk * TILE_COLS), dtype=torch.bfloat16, device=x.device)
+    pad[:n, :d] = x
+    out.copy_(pad.view(nb, TILE_ROWS, nk, TILE_COLS).permute(0, 2, 1, 3))
+    return out
+
+
+def untile_rows(db: torch.Tensor, n: int, d: int, rows: torch.Tensor | None = None) -> torch.Tensor:
+    """Tiled storage -> row-major bf16 [n, d] (or the given rows).  Checker/IO utility, not on the product path."""
+    nb, nk = db.shape[0], db.shape[1]
+    if rows is not None:
+        return db[rows // TILE_ROWS, :, rows % TILE_ROWS, :].reshape(rows.numel(), nk * TILE_COLS)[:, :d]
+    return db.permute(0, 2, 1, 3).reshape(nb * TILE_ROWS, nk * TILE_COLS)[:n, :d]
+
+
+def normalize_rows(src: torch.Tensor, dst_bf16: torch.Tensor | None = None, want_f32: bool = False,
+                   db: torch.Tensor | None = None, row0: int = 0):
+    """L2-normalise fp32 rows (core_system.py:407,447; qdrant COSINE upsert).
+    `db` given: write the rows into the tiled DB at rows row0..row0+n-1 and return (db, f32|None);
+    otherwise return (row-major bf16 [n, d_pad], f32|None)."""
     require_cuda(src, "src")
     assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
     n, d = src.shape
+    f32 = torch.empty((n, d), dtype=torch.float32, device=src.device) if want_f32 else None
+    lib = _lib.load()
+    if db is not None:
+        assert db.dtype == torch.bfloat16 and db.is_contiguous() and db.dim() == 4 and row0 + n <= db_capacity(db)
+        assert db.shape[1] * TILE_COLS == d_pad_of(d)
+        check(lib.rvo_normalize_rows(_ptr(src), n, d, src.stride(0), _ptr(db), d_pad_of(d), int(row0), _ptr(f32),
+                                     _stream(src.device)), "rvo_normalize_rows")
+        return db, f32
     if dst_bf16 is None:
         dst_bf16 = torch.empty((n, d_pad_of(d)), dtype=torch.bfloat16, device=src.device)
     assert dst_bf16.dtype == torch.bfloat16 and dst_bf16.shape[0] >= n and dst_bf16.stride(1) == 1
-    f32 = torch.empty((n, d), dtype=torch.float32, device=src.device) if want_f32 else None
-    lib = _lib.load()
-    check(lib.rvo_normalize_rows(_ptr(src), n, d, src.stride(0), _ptr(dst_bf16), dst_bf16.stride(0), _ptr(f32),
+    check(lib.rvo_normalize_rows(_ptr(src), n, d, src.stride(0), _ptr(dst_bf16), dst_bf16.stride(0), -1, _ptr(f32),
                                  _stream(src.device)), "rvo_normalize_rows")
     return dst_bf16, f32
 
@@ -84,15 +126,15 @@ def mask_pool(feats: torch.Tensor, masks: torch.Tensor, max_regions: int = 0):
 
 def search_topk(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, k: int,
                 score_threshold: float | None = None, id_offset: int = 0, out=None):
-    """K2.  db bf16 [>=n_rows, d_pad] normalised rows, queries f32 [nq, d].
+    """K2.  db: tiled bf16 DB storage (`db_alloc`) holding >= n_rows normalised rows, queries f32 [nq, d].
     Returns device tensors (ids int64 [nq,k], scores f32 [nq,k], counts int32 [nq]); async on the current stream.
     counts[q] == -1 marks an overflowed query (see `search_topk_exact`)."""
     require_cuda(db, "db")
     require_cuda(queries, "queries")
-    assert db.dtype == torch.bfloat16 and db.dim() == 2 and db.stride(1) == 1
+    assert db.dtype == torch.bfloat16 and db.dim() == 4 and db.is_contiguous() and db.shape[2:] == (TILE_ROWS, TILE_COLS)
     assert queries.dtype == torch.float32 and queries.dim() == 2 and queries.is_contiguous()
     nq = queries.shape[0]
-    assert queries.shape[1] == d and n_rows <= db.shape[0]
+    assert queries.shape[1] == d and n_rows <= db_capacity(db) and db.shape[1] * TILE_COLS == d_pad_of(d)
     if not (1 <= k <= RVO_MAX_K):
         raise RvoError(f"k={k} outside 1..{RVO_MAX_K}")
     dev = queries.device
@@ -109,7 +151,7 @@ def search_topk(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, k:
                        + lib.rvo_last_error().decode())
     ws = workspace(dev, nbytes)
     thr = -math.inf if score_threshold is None else float(score_threshold)
-    check(lib.rvo_search_topk(_ptr(db), n_rows, d, db.stride(0), _ptr(queries), nq, k, thr, int(id_offset), _ptr(ids),
+    check(lib.rvo_search_topk(_ptr(db), n_rows, d, d_pad_of(d), _ptr(queries), nq, k, thr, int(id_offset), _ptr(ids),
                               _ptr(scores), _ptr(counts), _ptr(ws), nbytes, _stream(dev)), "rvo_search_topk")
     return ids, scores, counts
 
@@ -137,19 +179,27 @@ def padded_queries(nq: int, d: int) -> int:
     return r
 
 
-def scores_dense(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, row_stride: int = 1,
-                 n_sample: int | None = None) -> torch.Tensor:
-    """Dense tensor-core score block (tests/diagnostics): [nq, n_sample] fp32."""
+def scan_tile_rows(nq: int, d: int) -> int:
+    r = _lib.load().rvo_scan_tile_rows(nq, d)
+    if r < 0:
+        check(r, "rvo_scan_tile_rows")
+    return r
+
+
+def scores_dense(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, tile_stride: int = 1) -> torch.Tensor:
+    """Dense tensor-core score block (tests/diagnostics): [nq, cols] fp32, column c = t*T + i is DB row
+    t*tile_stride*T + i with T = scan_tile_rows(nq, d); rows past n_rows hold -inf."""
     require_cuda(db, "db")
     nq = queries.shape[0]
-    if n_sample is None:
-        n_sample = (n_rows + row_stride - 1) // row_stride
+    T = scan_tile_rows(nq, d)
+    tiles = (n_rows + T - 1) // T
+    cols = (tiles + tile_stride - 1) // tile_stride * T
     nq_pad = padded_queries(nq, d)
-    out = torch.zeros((nq_pad, n_sample), dtype=torch.float32, device=db.device)
+    out = torch.zeros((nq_pad, cols), dtype=torch.float32, device=db.device)
     nbytes = nq_pad * d_pad_of(d) * 2 + 4096
     ws = workspace(db.device, nbytes)
     lib = _lib.load()
-    check(lib.rvo_scores_dense(_ptr(db), n_rows, d, db.stride(0), _ptr(queries), nq, row_stride, n_sample, _ptr(out),
+    check(lib.rvo_scores_dense(_ptr(db), n_rows, d, d_pad_of(d), _ptr(queries), nq, tile_stride, _ptr(out),
                                out.stride(0), _ptr(ws), nbytes, _stream(db.device)), "rvo_scores_dense")
     return out[:nq]
 

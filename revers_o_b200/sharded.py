@@ -18,11 +18,14 @@ from . import _lib, ops
 from ._lib import check
 
 
-def shard_bounds(n_rows: int, world: int, rank: int) -> tuple[int, int]:
-    """Contiguous row range of `rank`: first (n_rows % world) ranks get one extra row."""
-    base, extra = divmod(n_rows, world)
+def shard_bounds(n_rows: int, world: int, rank: int, align: int = 128) -> tuple[int, int]:
+    """Contiguous row range of `rank`.  Shards are whole 128-row blocks of the tiled DB storage (so that a shard
+    is a slice of it); the first (blocks % world) ranks get one extra block, the last shard ends at n_rows."""
+    blocks = (n_rows + align - 1) // align
+    base, extra = divmod(blocks, world)
     lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+    hi = lo + base + (1 if rank < extra else 0)
+    return min(lo * align, n_rows), min(hi * align, n_rows)
 
 
 def packed_bytes(nq: int, k: int) -> int:
@@ -59,6 +62,7 @@ class ShardedIndex:
     """The local shard of a row-sharded bf16 DB plus the exchange/merge step."""
 
     def __init__(self, local_db: torch.Tensor, n_local: int, d: int, id_offset: int, group=None):
+        """local_db: tiled bf16 storage (ops.db_alloc) of this rank's rows; id_offset: its first global row."""
         ops.require_cuda(local_db, "local_db")
         self.db, self.n_local, self.d, self.id_offset, self.group = local_db, int(n_local), int(d), int(id_offset), group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1

@@ -24,10 +24,15 @@ def make_queries(nq: int, d: int, seed: int = 7, device="cpu") -> torch.Tensor:
 
 def make_db(n: int, d: int, queries: torch.Tensor | None = None, n_plant: int = 128, seed: int = 1000,
             device="cpu", chunk: int = 1 << 18) -> torch.Tensor:
-    """bf16 [n, d_pad] (d_pad = d rounded up to 64, zero padded), generated on `device` chunk by chunk."""
+    """Tiled bf16 DB storage (ops.db_alloc layout) of n L2-normalised rows, generated on `device` chunk by chunk.
+    `ops.untile_rows(db, n, d)` gives the row-major view for checkers."""
+    from . import ops
     d_pad = (d + 63) // 64 * 64
     dev = torch.device(device)
-    db = torch.zeros((n, d_pad), dtype=torch.bfloat16, device=dev)
+    tiled = ops.db_alloc(n, d, dev)
+    nb, nk = tiled.shape[0], tiled.shape[1]
+    # row-major alias of the same values, written chunk by chunk and permuted into the tiled storage at the end
+    db = torch.zeros((nb * 128, d_pad), dtype=torch.bfloat16, device=dev)
     g = torch.Generator(device=dev).manual_seed(seed)
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)
@@ -50,7 +55,10 @@ def make_db(n: int, d: int, queries: torch.Tensor | None = None, n_plant: int = 
             v = alpha * qq + torch.sqrt(1 - alpha * alpha) * noise
             v = v / v.norm(dim=-1, keepdim=True)
             db[rows[lo:hi].reshape(-1), :d] = v.reshape(-1, d).to(torch.bfloat16)
-    return db
+    for b0 in range(0, nb, 1024):  # permute into [block][k-chunk][128][64], 1024 row blocks at a time
+        b1 = min(nb, b0 + 1024)
+        tiled[b0:b1].copy_(db[b0 * 128: b1 * 128].view(b1 - b0, 128, nk, 64).permute(0, 2, 1, 3))
+    return tiled
 
 
 def make_maskpool_inputs(B: int, M: int, grid: int, D: int, seed: int = 11, device="cpu", n_empty: int = 2):

@@ -8,12 +8,12 @@ It duck-types exactly the five qdrant-client methods core_system.py uses (SURVEY
   .search(collection_name, query_vector, limit, score_threshold) -> [obj(.score,.payload)]     :659-664
 plus the batched entry point `search_batch` (new; reduces to `search` row by row).
 
-Vectors live on the GPU as an L2-normalised bf16 matrix [capacity, d_pad] (the DB is DEFINED as its
-bf16 values); ids (uuid strings) and payload dicts stay in host lists indexed by row.  All arithmetic
+Vectors live on the GPU as L2-normalised bf16 rows in the TILED storage of include/revers_o_b200.h
+([row/128][col/64][128][64]: one contiguous 16 KiB TMA box per tile; the DB is DEFINED as its bf16 values); ids (uuid strings) and payload dicts stay in host lists indexed by row.  All arithmetic
 (normalise, scan, select, re-score) runs in the CUDA library; there is no CPU fallback.
 
-On-disk format: <path>/meta.json + <path>/<collection>.bf16 (raw row-major
-[n, d_pad] bf16, mmap-able, loadable shard-wise) + <path>/<collection>.payload.jsonl.
+On-disk format: <path>/meta.json + <path>/<collection>.bf16 (the tiled storage
+as is, mmap-able, loadable shard-wise by 128-row block) + <path>/<collection>.payload.jsonl.
 """
 from __future__ import annotations
 
@@ -68,18 +68,18 @@ class _Collection:
         self.name, self.dim, self.device = name, int(dim), device
         self.d_pad = ops.d_pad_of(self.dim)
         self.n = 0
-        self.vectors = torch.zeros((0, self.d_pad), dtype=torch.bfloat16, device=device)
+        self.vectors = ops.db_alloc(0, self.dim, device)  # tiled bf16 storage [blocks, d_pad/64, 128, 64]
         self.ids: list = []
         self.payloads: list = []
         self.row_of: dict = {}
 
     def reserve(self, rows: int) -> None:
-        if rows <= self.vectors.shape[0]:
+        have = ops.db_capacity(self.vectors)
+        if rows <= have:
             return
-        cap = max(rows, int(self.vectors.shape[0] * 1.5), 1024)
-        new = torch.zeros((cap, self.d_pad), dtype=torch.bfloat16, device=self.device)
-        if self.n:
-            new[: self.n].copy_(self.vectors[: self.n])  # device-to-device memcpy, no arithmetic
+        new = ops.db_alloc(max(rows, int(have * 1.5), 1024), self.dim, self.device)
+        if self.vectors.shape[0]:
+            new[: self.vectors.shape[0]].copy_(self.vectors)  # whole row blocks: device-to-device memcpy
         self.vectors = new
 
 
@@ -228,9 +228,11 @@ class B200VectorDB:
         with self._lock:
             meta = {"format": "revers_o_b200/1", "collections": {}}
             for name, c in self._collections.items():
-                meta["collections"][name] = {"dim": c.dim, "d_pad": c.d_pad, "n": c.n, "distance": "Cosine"}
-                raw = c.vectors[: c.n].contiguous().view(torch.int16).cpu().numpy()
-                raw.tofile(os.path.join(path, f"{name}.bf16"))
+                blocks = (c.n + ops.TILE_ROWS - 1) // ops.TILE_ROWS
+                meta["collections"][name] = {"dim": c.dim, "d_pad": c.d_pad, "n": c.n, "distance": "Cosine",
+                                             "layout": "tiled[block][d_pad/64][128][64] bf16", "blocks": blocks}
+                raw = c.vectors[:blocks].contiguous().view(torch.int16).cpu().numpy()
+                raw.tofile(os.path.join(path, f"{name}.bf16"))  # the tiled storage as is: loadable shard-wise by block
                 with open(os.path.join(path, f"{name}.payload.jsonl"), "w") as f:
                     for pid, pay in zip(c.ids, c.payloads):
                         f.write(json.dumps({"id": pid, "payload": pay}, default=str) + "\n")
@@ -244,9 +246,11 @@ class B200VectorDB:
             c = _Collection(name, m["dim"], self.device)
             n = int(m["n"])
             if n:
-                raw = np.fromfile(os.path.join(path, f"{name}.bf16"), dtype=np.int16).reshape(n, c.d_pad)
+                blocks = (n + ops.TILE_ROWS - 1) // ops.TILE_ROWS
+                raw = np.fromfile(os.path.join(path, f"{name}.bf16"), dtype=np.int16).reshape(
+                    blocks, c.d_pad // ops.TILE_COLS, ops.TILE_ROWS, ops.TILE_COLS)
                 c.reserve(n)
-                c.vectors[:n].copy_(torch.from_numpy(raw).view(torch.bfloat16))
+                c.vectors[:blocks].copy_(torch.from_numpy(raw).view(torch.bfloat16))
             with open(os.path.join(path, f"{name}.payload.jsonl")) as f:
                 for line in f:
                     rec = json.loads(line)
@@ -296,13 +300,13 @@ class B200VectorDB:
 
     def _write_rows(self, c: _Collection, rows: list, host_or_dev: torch.Tensor) -> None:
         src = self._to_device_f32(host_or_dev)
-        contiguous = rows == list(range(rows[0], rows[0] + len(rows)))
-        if contiguous:
-            ops.normalize_rows(src, c.vectors[rows[0]: rows[0] + len(rows)])
-        else:  # overwrites of existing ids: normalise into a staging block, then scatter rows (memcpy only)
-            stage, _ = ops.normalize_rows(src)
-            idx = torch.tensor(rows, dtype=torch.long, device=self.device)
-            c.vectors.index_copy_(0, idx, stage)
+        i = 0
+        while i < len(rows):  # one normalise-and-store launch per run of consecutive destination rows
+            j = i + 1
+            while j < len(rows) and rows[j] == rows[j - 1] + 1:
+                j += 1
+            ops.normalize_rows(src[i:j], db=c.vectors, row0=rows[i])
+            i = j
 
 
 def _get(p, name):

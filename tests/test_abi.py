@@ -58,7 +58,7 @@ def test_compute_fails_loudly_without_gpu():
         B200VectorDB()
     lib = _lib.load()
     buf = (ctypes.c_float * 64)()
-    rc = lib.rvo_normalize_rows(ctypes.addressof(buf), 1, 8, 8, ctypes.addressof(buf), 8, None, None)
+    rc = lib.rvo_normalize_rows(ctypes.addressof(buf), 1, 8, 8, ctypes.addressof(buf), 8, -1, None, None)
     assert rc < 0 and lib.rvo_last_error() != b""
 
 

@@ -59,7 +59,10 @@ class Det(NS):
 def make_image(seed, size=(96, 80)):
     from PIL import Image
     rs = np.random.RandomState(seed)
-    return Image.fromarray((rs.rand(size[1], size[0], 3) * 255).astype(np.uint8))
+    coarse = Image.fromarray((rs.rand(5, 6, 3) * 255).astype(np.uint8))       # low-frequency content: images differ globally
+    img = np.asarray(coarse.resize(size, Image.BILINEAR), dtype=np.float32)
+    img += rs.rand(size[1], size[0], 3) * 20
+    return Image.fromarray(np.clip(img, 0, 255).astype(np.uint8))
 
 
 @pytest.mark.parametrize("mode", ["reference", "pooled"])
@@ -102,7 +105,8 @@ def test_ui_call_pattern(dev, tmp_path, mode):
     oc = O.QdrantLocalOracle()
     c = r.vector_db._coll(r.current_database)
     oc.recreate_collection("x", size=c.dim)
-    vec = c.vectors[: c.n, : c.dim].float().cpu().numpy()
+    from revers_o_b200 import ops
+    vec = ops.untile_rows(c.vectors, c.n, c.dim).float().cpu().numpy()
     oc.upsert("x", [NS(id=i, vector=v, payload=p) for i, v, p in zip(c.ids, vec, c.payloads)])
     ref = oc.search("x", keep[0].numpy(), limit=5, score_threshold=0.5)
     got = r.vector_db.search(r.current_database, keep[0].numpy(), limit=5, score_threshold=0.5)
@@ -143,7 +147,9 @@ def test_vector_db_upsert_overwrite_and_batch(dev):
     hits = db.search("c", v[3].tolist(), limit=3, score_threshold=0.99)
     assert sorted(h.payload["i"] for h in hits) == [3, 7] and all(h.score > 0.999 for h in hits)
     ids, sc, cnt = db.search_batch("c", v[:40], 5)
-    ref = O.search_batch(db._coll("c").vectors[:250, :100].float().cpu().numpy(), v[:40], 5, None, db_is_normalized=True)
+    from revers_o_b200 import ops
+    ref = O.search_batch(ops.untile_rows(db._coll("c").vectors, 250, 100).float().cpu().numpy(), v[:40], 5, None,
+                         db_is_normalized=True)
     for i, (a, b) in enumerate(ref):
         assert np.allclose(sc[i], b, atol=1e-3)
     with pytest.raises(Exception):

@@ -23,7 +23,8 @@ def dev():
 
 
 def _oracle(db_bf16: torch.Tensor, n, d, queries: torch.Tensor, k, thr=None):
-    dbf = db_bf16[:n, :d].float().cpu().numpy()
+    from revers_o_b200 import ops
+    dbf = ops.untile_rows(db_bf16, n, d).float().cpu().numpy()
     return O.search_batch(dbf, queries.float().cpu().numpy(), k, thr, db_is_normalized=True)
 
 
@@ -36,18 +37,24 @@ def _run(db, n, d, q, k, thr=None, id_offset=0):
 
 # ---- the tcgen05 mainloop by itself ---------------------------------------------------------------
 @pytest.mark.parametrize("n,d,nq,stride", [(1000, 64, 5, 1), (4096, 1024, 16, 1), (5000, 1024, 37, 1),
-                                            (3000, 1280, 256, 1), (20000, 1024, 300, 7), (777, 96, 130, 1)])
+                                            (3000, 1280, 256, 1), (20000, 1024, 300, 7), (777, 96, 130, 1),
+                                            (9000, 1024, 200, 3)])
 def test_dense_scores_match_fp32_reference(dev, n, d, nq, stride):
     from revers_o_b200 import ops, synth
     q = synth.make_queries(nq, d, seed=3, device=dev)
     db = synth.make_db(n, d, q, n_plant=8, seed=5, device=dev)
-    ns = (n + stride - 1) // stride
-    got = ops.scores_dense(db, n, d, q, row_stride=stride, n_sample=ns)
+    got = ops.scores_dense(db, n, d, q, tile_stride=stride)
     torch.cuda.synchronize()
+    T = ops.scan_tile_rows(nq, d)
+    tiles = (n + T - 1) // T
+    rows = torch.cat([torch.arange(t * T, (t + 1) * T) for t in range(0, tiles, stride)]).to(dev)
     qn = (q / q.norm(dim=1, keepdim=True)).to(torch.bfloat16).float()          # tensor path rounds the query
-    ref = qn @ db[: n: stride, :d].float().T
+    ok = rows < n
+    ref = torch.full((nq, rows.numel()), -math.inf, device=dev)
+    ref[:, ok] = qn @ ops.untile_rows(db, n, d, rows[ok]).float().T
     assert got.shape == ref.shape
-    assert torch.max(torch.abs(got - ref)).item() < 2e-5
+    assert torch.equal(torch.isinf(got), torch.isinf(ref))
+    assert torch.max(torch.abs(got[:, ok] - ref[:, ok])).item() < 2e-5
 
 
 # ---- full search, both paths ------------------------------------------------------------------------
@@ -84,7 +91,7 @@ def test_scores_also_within_tolerance_of_unrounded_fp32_db(dev):
             v = a * qf[i] / np.linalg.norm(qf[i]) + math.sqrt(1 - a * a) * rs.randn(d).astype(np.float32) / math.sqrt(d)
             dbf[(i * 601 + j * 7) % n] = v / np.linalg.norm(v)
     src = torch.from_numpy(dbf).to(dev)
-    db, _ = ops.normalize_rows(src)
+    db, _ = ops.normalize_rows(src, db=ops.db_alloc(n, d, dev))
     ids, sc, cnt = _run(db, n, d, torch.from_numpy(qf).to(dev), k)
     ref = O.search_batch(dbf, qf, k, None, db_is_normalized=True)
     assert_topk_match(ids, sc, cnt, ref, k, TOL, "fp32db")
@@ -111,8 +118,8 @@ def test_known_answers_identity_duplicates_limit(dev, nq):
     d = 128
     eye = torch.eye(d, dtype=torch.float32, device=dev)
     src = torch.cat([eye, eye[5:6], eye[5:6]], 0)                 # rows 128,129 duplicate row 5
-    db, _ = ops.normalize_rows(src)
     n = src.shape[0]
+    db, _ = ops.normalize_rows(src, db=ops.db_alloc(n, d, dev))
     q = eye[[5] + list(range(1, nq))].contiguous() * 3.0
     ids, sc, cnt = _run(db, n, d, q, 3)
     assert ids[0].tolist() == [5, 128, 129] and np.allclose(sc[0], 1.0, atol=1e-6)   # ties -> lower id first
@@ -136,7 +143,7 @@ def test_id_offset_and_virtual_shards_merge(dev, golden):
     parts = []
     for r in range(G):
         lo, hi = shard_bounds(n, G, r)
-        parts.append(ops.search_topk(db[lo:hi], hi - lo, d, q, k, None, lo))
+        parts.append(ops.search_topk(db[lo // 128: (hi + 127) // 128], hi - lo, d, q, k, None, lo))
     ids = torch.stack([p[0] for p in parts]); sc = torch.stack([p[1] for p in parts]); cnt = torch.stack([p[2] for p in parts])
     mi, ms, mc = ops.merge_topk(ids.contiguous(), sc.contiguous(), cnt.contiguous(), k)
     torch.cuda.synchronize()
@@ -158,11 +165,10 @@ def test_id_offset_and_virtual_shards_merge(dev, golden):
 
 
 def test_golden_search_fixture(dev, golden):
+    from revers_o_b200 import ops
     db = torch.from_numpy(golden["search_db_bf16_bits"].astype(np.int16)).view(torch.bfloat16)
     n, d = db.shape
-    dbp = torch.zeros((n, 128), dtype=torch.bfloat16)
-    dbp[:, :d] = db
-    dbp = dbp.to(dev)
+    dbp = ops.tile_rows(db.to(dev))
     q = torch.from_numpy(golden["search_queries"]).to(dev)
     for tag, k, thr in (("k10", 10, None), ("k10_t07", 10, 0.7), ("k100", 100, None)):   # nq=9 -> tensor path
         ids, sc, cnt = _run(dbp, n, d, q, k, thr)
@@ -183,9 +189,9 @@ def test_overflow_flag_and_exact_fallback(dev):
     from revers_o_b200 import ops, synth
     n, d, nq, k = 40_000, 256, 8, 20
     q = synth.make_queries(nq, d, seed=31, device=dev)
-    db = synth.make_db(n, d, None, seed=32, device=dev)
-    qn = (q[0] / q[0].norm()).to(torch.bfloat16)
-    db[5000:30000, :d] = qn                                          # 25k identical rows, all score ~1.0 for query 0
+    rows = ops.untile_rows(synth.make_db(n, d, None, seed=32, device=dev), n, d).clone()
+    rows[5000:30000] = (q[0] / q[0].norm()).to(torch.bfloat16)        # 25k identical rows, all score ~1.0 for query 0
+    db = ops.tile_rows(rows)
     ids, sc, cnt = ops.search_topk(db, n, d, q, k)
     torch.cuda.synchronize()
     assert cnt[0].item() == -1 and torch.all(cnt[1:] == k)
@@ -201,14 +207,16 @@ def test_clustered_ingest_order_is_still_exact(dev):
     from revers_o_b200 import synth
     n, d, nq, k = 150_000, 1024, 32, 100
     q = synth.make_queries(nq, d, seed=41, device=dev)
-    db = synth.make_db(n, d, None, seed=42, device=dev)
+    from revers_o_b200 import ops
+    rows = ops.untile_rows(synth.make_db(n, d, None, seed=42, device=dev), n, d).clone()
     qn = q / q.norm(dim=1, keepdim=True)
     g = torch.Generator(device=dev).manual_seed(43)
     for i in range(nq):
         noise = torch.randn((300, d), generator=g, device=dev) / math.sqrt(d)
         a = torch.linspace(0.6, 0.99, 300, device=dev).view(-1, 1)
         v = a * qn[i] + torch.sqrt(1 - a * a) * noise
-        db[70_000 + i * 300: 70_000 + (i + 1) * 300, :d] = (v / v.norm(dim=1, keepdim=True)).to(torch.bfloat16)
+        rows[70_000 + i * 300: 70_000 + (i + 1) * 300] = (v / v.norm(dim=1, keepdim=True)).to(torch.bfloat16)
+    db = ops.tile_rows(rows)
     ids, sc, cnt = _run(db, n, d, q, k)
     assert_topk_match(ids, sc, cnt, _oracle(db, n, d, q, k), k, TOL, "clustered")
 
@@ -217,7 +225,7 @@ def test_config1_full_size_properties_and_sampled_parity(dev):
     """BASELINE config 1 at full size (1M x 1024, Q=256, k=100): size-independent properties on every query
     (descending, in-range unique ids, every returned score reproduced by an fp32 dot with the stored row, the
     planted >=0.99 neighbour found first) plus oracle parity on a sample of queries."""
-    from revers_o_b200 import synth
+    from revers_o_b200 import ops, synth
     n, d, nq, k = 1_000_000, 1024, 256, 100
     q = synth.make_queries(nq, d, seed=7, device=dev)
     db = synth.make_db(n, d, q, n_plant=128, seed=1000, device=dev)
@@ -226,11 +234,11 @@ def test_config1_full_size_properties_and_sampled_parity(dev):
     assert np.all(np.diff(sc, axis=1) <= 1e-7) and ids.min() >= 0 and ids.max() < n
     assert all(len(set(r.tolist())) == k for r in ids)
     qn = (q / q.norm(dim=1, keepdim=True))
-    rows = db[torch.from_numpy(ids).to(dev).view(-1), :d].float().view(nq, k, d)
+    rows = ops.untile_rows(db, n, d, torch.from_numpy(ids).to(dev).view(-1)).float().view(nq, k, d)
     redo = torch.einsum("qkd,qd->qk", rows, qn).cpu().numpy()
     assert np.max(np.abs(redo - sc)) < 1e-5
     assert np.all(sc[:, 0] > 0.98)
     sel = list(range(0, nq, 16))
-    dbf = db[:, :d].float().cpu().numpy()
+    dbf = ops.untile_rows(db, n, d).float().cpu().numpy()
     ref = O.search_batch(dbf, q[sel].cpu().numpy(), k, None, db_is_normalized=True)
     assert_topk_match(ids[sel], sc[sel], cnt[sel], ref, k, TOL, "cfg1")

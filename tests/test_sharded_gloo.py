@@ -27,7 +27,7 @@ def _worker(rank, world, port, ret):
     try:
         from revers_o_b200.sharded import allgather_packed, pack_results, shard_bounds, unpack_results
         rs = np.random.RandomState(0)                       # same DB / queries on every rank
-        n, d, nq, k = 5000, 64, 6, 20
+        n, d, nq, k = 5000, 64, 6, 20                      # 40 row blocks -> shards [0,2560) and [2560,5000)
         db = O.round_to_bf16(O._cosine_prepare(rs.randn(n, d).astype(np.float32)))
         db[4000] = db[17]                                  # cross-shard tie
         q = rs.randn(nq, d).astype(np.float32)
