@@ -194,6 +194,9 @@ def run_b200(args):
     db = synth.make_db(n_local, d, q_dev, n_plant=max(1, 128 // world), seed=1000 + rank, device=dev)
     index = ShardedIndex(db, n_local, d, lo)
     lib = _lib.load()
+    for kv in filter(None, os.environ.get("RVO_OPTS", "").split(",")):  # tuning sweeps only (scripts/gpu_sweep.sh)
+        name, val = kv.split("=")
+        _lib.set_option(name.strip(), int(val))
 
     def barrier():
         if world > 1:

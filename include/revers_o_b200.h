@@ -168,7 +168,7 @@ float rvo_last_scan_ms(void);
 
 /* Tuning knobs (benchmarks/tests only; defaults reproduce the documented behaviour).
  *   name: "force_path" (0 auto, 1 small-q scan, 2 tcgen05 scan), "m_sub" (0 auto,1,2),
- *         "cand_cap" (candidates per query, default 16384), "final_ratio" (default 48),
+ *         "cand_cap" (candidates per query, default 32768), "final_ratio" (default 48),
  *         "time_scan" (0/1, see rvo_last_scan_ms)                                                */
 int rvo_set_option(const char* name, int64_t value);
 

@@ -20,7 +20,7 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static std::atomic<long long> opt_force_path{0}, opt_m_sub{0}, opt_cand_cap{16384}, opt_final_ratio{48}, opt_time_scan{0};
+static std::atomic<long long> opt_force_path{0}, opt_m_sub{0}, opt_cand_cap{32768}, opt_final_ratio{48}, opt_time_scan{0};
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static bool g_ev_valid = false;
 
@@ -191,8 +191,8 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
         const long long supers = (n_rows + T - 1) / T;
         sp->K2 = next_pow2_host((2 * k > k + 64) ? 2 * k : k + 64);
         if (sp->K2 > 1024) sp->K2 = 1024;
-        long long cap = opt_cand_cap.load();
-        if (cap < 1024) cap = 1024;
+        long long cap = opt_cand_cap.load() / kCandSplit;  // per sub-list
+        if (cap < 64) cap = 64;
         sp->cap = (int)cap;
         // levels: DENSE seed over ~16k rows (every seed_stride-th super-tile), then geometric FILTER samples,
         // then the full scan.  Any sample gives a valid threshold (k-th best of a subset <= k-th best overall).
@@ -219,13 +219,13 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
         sp->seed_cols = scan_tc_sample_rows(n_rows, sp->tc, sp->seed_stride);
         sp->zero_off = ar.off;
         sp->qb = ar.take<uint16_t>((size_t)nq_pad * sp->d_pad, 1024);
-        sp->cnt = ar.take<int>((size_t)(sp->n_levels + 1) * nq_pad);
+        sp->cnt = ar.take<int>((size_t)(sp->n_levels + 1) * nq_pad * kCandSplit);
         sp->zero_bytes = ar.off - sp->zero_off;
         sp->qn = ar.take<float>((size_t)nq * sp->d_pad, 1024);
         sp->tau = ar.take<float>((size_t)(sp->n_levels + 1) * nq_pad);
         sp->dense_ld = (sp->seed_cols + 63) / 64 * 64;
         sp->dense = ar.take<float>((size_t)nq_pad * (size_t)sp->dense_ld);
-        if (sp->n_levels > 0) sp->cand = ar.take<unsigned long long>((size_t)nq_pad * (size_t)sp->cap);
+        if (sp->n_levels > 0) sp->cand = ar.take<unsigned long long>((size_t)nq_pad * kCandSplit * (size_t)sp->cap);
         sp->bufA = ar.take<unsigned long long>((size_t)nq * sp->K2);
         sp->bufB = nullptr;
     }
@@ -430,7 +430,7 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
     // FILTER levels: each tightens tau on a larger tile sample; the last one scans every row
     for (int L = 0; L < sp.n_levels; ++L) {
         const bool last = L == sp.n_levels - 1;
-        int* cnt = sp.cnt + (size_t)L * nq_pad;
+        int* cnt = sp.cnt + (size_t)L * nq_pad * kCandSplit;
         const float* tau_in = sp.tau + (size_t)L * nq_pad;
         if (last && (rc = scan_timer(true, stream))) return rc;
         rc = launch_scan_tc(kModeFilter, db, n_rows, sp.level_stride[L], sp.d_pad, sp.qb, sp.tc, tau_in, sp.cand, cnt, sp.cap,
@@ -440,8 +440,8 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
         memset(&sa, 0, sizeof(sa));
         sa.nq = nq;
         sa.keys = sp.cand;
-        sa.keys_ld = sp.cap;
         sa.cnt = cnt;
+        sa.nseg = kCandSplit;
         sa.cap = sp.cap;
         if (!last) {
             sa.K = k;
@@ -463,6 +463,7 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
             fa.rescore = 1;
             fa.margin = margin;
             fa.cnt = cnt;
+            fa.nseg = kCandSplit;
             fa.cap = sp.cap;
             rc = launch_final(fa, nq, stream);
             if (rc) return rc;

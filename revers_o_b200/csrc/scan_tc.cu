@@ -172,6 +172,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
         uint32_t acc = 0;
         uint32_t wcount = 0;
         int cur_qb = -1;
+        // candidate appends in flight from the previous TMEM slot (FILTER mode)
+        const int seg = (int)(blockIdx.x % kCandSplit);  // this CTA's sub-list of every query
+        int pend_n = 0, pend_q0 = 0;
+        uint32_t pend_row = 0;
+        int pend_pos[4] = {0, 0, 0, 0};
+        unsigned long long pend_ent[4] = {0ull, 0ull, 0ull, 0ull};
 
         for (long long w = blockIdx.x; w < total_work; w += gridDim.x, ++wcount) {
             const long long st = w / p.num_qblk;
@@ -220,61 +226,99 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                 } else {
                     int n = 0;
                     const uint32_t key_row_bits = 0xFFFFFFFFu - (uint32_t)row;
-                    // Append queued survivors (score, query column) of this row to the candidate lists.
-                    auto flush = [&](int cnt) {
-                        for (int e = 0; e < cnt; e += 4) {
+                    // Synchronous append of queue entries [from, cnt) (rare paths only: queue overflow, >4 survivors).
+                    auto flush_sync = [&](int from, int cnt) {
+                        for (int e = from; e < cnt; e += 4) {
                             int slot_pos[4];
                             unsigned long long ent[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
                                 if (e + u < cnt) {
                                     ent[u] = s_queue[(e + u) * kEpiThreads + qt];
-                                    slot_pos[u] = atomicAdd(p.cand_cnt + q0 + (int)(ent[u] & 0xFFFFu), 1);
+                                    slot_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(ent[u] & 0xFFFFu)) * kCandSplit + seg, 1);
                                 }
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
                                 if (e + u < cnt && slot_pos[u] < p.cap) {
                                     const int q = q0 + (int)(ent[u] & 0xFFFFu);
                                     const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(ent[u] >> 32)));
-                                    p.cand[(size_t)q * (size_t)p.cap + (size_t)slot_pos[u]] =
+                                    p.cand[((size_t)q * kCandSplit + seg) * (size_t)p.cap + (size_t)slot_pos[u]] =
                                         ((unsigned long long)ob << 32) | (unsigned long long)key_row_bits;
                                 }
                         }
                     };
-                    for (int c = half; c < nchunks; c += 2) {
-                        uint32_t v[16];
-                        tmem_ld_x16(taddr + (uint32_t)c * 16u, v);
+                    for (int c = half; c < nchunks; c += 4) {
+                        // two 16-column chunks per TMEM wait
+                        uint32_t v[2][16];
+                        const bool two = c + 2 < nchunks;
+                        tmem_ld_x16(taddr + (uint32_t)c * 16u, v[0]);
+                        if (two) tmem_ld_x16(taddr + (uint32_t)(c + 2) * 16u, v[1]);
                         tmem_ld_wait();
                         if (valid) {
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                if (n > kQueueCap - 8) {  // rare: keep room for 8 more
-                                    flush(n);
-                                    n = 0;
-                                }
-                                const float4 t0 = *(const float4*)(tau_s + c * 16 + h * 8);
-                                const float4 t1 = *(const float4*)(tau_s + c * 16 + h * 8 + 4);
-                                const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                            for (int g = 0; g < 2; ++g) {
+                                if (g == 1 && !two) break;
+                                const int cc = c + 2 * g;
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    if (__uint_as_float(v[h * 8 + i]) >= tt[i]) {
-                                        s_queue[n * kEpiThreads + qt] =
-                                            ((unsigned long long)v[h * 8 + i] << 32) | (unsigned)(c * 16 + h * 8 + i);
-                                        ++n;
+                                for (int h = 0; h < 2; ++h) {
+                                    if (n > kQueueCap - 8) {  // rare: keep room for 8 more
+                                        flush_sync(0, n);
+                                        n = 0;
+                                    }
+                                    const float4 t0 = *(const float4*)(tau_s + cc * 16 + h * 8);
+                                    const float4 t1 = *(const float4*)(tau_s + cc * 16 + h * 8 + 4);
+                                    const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        if (__uint_as_float(v[g][h * 8 + i]) >= tt[i]) {
+                                            s_queue[n * kEpiThreads + qt] = ((unsigned long long)v[g][h * 8 + i] << 32) |
+                                                                            (unsigned)(cc * 16 + h * 8 + i);
+                                            ++n;
+                                        }
                                     }
                                 }
                             }
                         }
                         __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next one
                     }
-                    // TMEM slot is drained: hand it back before paying the atomics' latency.
+                    // TMEM slot is drained: hand it back to the MMA warp.
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar_tempty[slot]);
-                    if (n > 0) flush(n);
+                    // Software-pipelined append: the atomics issued for the PREVIOUS slot have had a whole slot of
+                    // time to return; finish its stores now, then issue this slot's atomics and move on without
+                    // waiting for them (their ~3 us round trip is hidden behind the next slot's scan).
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (u < pend_n && pend_pos[u] < p.cap) {
+                            const int q = pend_q0 + (int)(pend_ent[u] & 0xFFFFu);
+                            const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(pend_ent[u] >> 32)));
+                            p.cand[((size_t)q * kCandSplit + seg) * (size_t)p.cap + (size_t)pend_pos[u]] =
+                                ((unsigned long long)ob << 32) | (unsigned long long)pend_row;
+                        }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (u < n) {
+                            pend_ent[u] = s_queue[u * kEpiThreads + qt];
+                            pend_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(pend_ent[u] & 0xFFFFu)) * kCandSplit + seg, 1);
+                        }
+                    pend_n = n < 4 ? n : 4;
+                    pend_q0 = q0;
+                    pend_row = key_row_bits;
+                    if (n > 4) flush_sync(4, n);
                 }
             }
             acc += (uint32_t)m_valid;
+        }
+        if (MODE == kModeFilter) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < pend_n && pend_pos[u] < p.cap) {
+                    const int q = pend_q0 + (int)(pend_ent[u] & 0xFFFFu);
+                    const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(pend_ent[u] >> 32)));
+                    p.cand[((size_t)q * kCandSplit + seg) * (size_t)p.cap + (size_t)pend_pos[u]] =
+                        ((unsigned long long)ob << 32) | (unsigned long long)pend_row;
+                }
         }
     }
 
@@ -355,7 +399,8 @@ int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl) {
     pl->m_sub = 1;
     if (pl->num_qblk == 1 && res_bytes + 3 * (size_t)kSubTileBytes <= budget && force_m_sub <= 0) pl->resident = 1;
     if (!pl->resident) {
-        pl->m_sub = 2;
+        // one query block: TMEM double-buffering (m_sub = 1) beats sharing the query chunk (measured)
+        pl->m_sub = pl->num_qblk == 1 ? 1 : 2;
         if (force_m_sub == 1 || force_m_sub == 2 || force_m_sub == 4) pl->m_sub = force_m_sub;
         while (pl->m_sub > pl->num_slots) pl->m_sub >>= 1;
     }

@@ -16,6 +16,8 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kScanThreads = 64 + kEpiThreads;            // TMA warp + MMA warp + epilogue warps
 constexpr int kQueueCap = 12;                             // smem survivor queue entries per epilogue thread
 constexpr int kSmemLimit = 232448;                        // 227 KiB opt-in dynamic smem per CTA
+constexpr int kCandSplit = 16;                            // sub-lists per query: spreads the append atomics over
+                                                          // 16x more L2 addresses (same-address atomics serialise)
 constexpr int kModeDense = 0;
 constexpr int kModeFilter = 1;
 
@@ -27,9 +29,9 @@ struct ScanParams {
     uint32_t stage_bytes, off_stages, off_queue, off_tau, off_bars;
     // FILTER
     const float* tau;              // [nq_pad] per-query admission thresholds
-    unsigned long long* cand;      // [nq_pad][cap] candidate ordering keys
-    int* cand_cnt;                 // [nq_pad]
-    int cap;
+    unsigned long long* cand;      // [nq_pad][kCandSplit][cap] candidate ordering keys
+    int* cand_cnt;                 // [nq_pad][kCandSplit]; CTA b appends to sub-list b % kCandSplit
+    int cap;                       // capacity of ONE sub-list
     // DENSE
     float* dense;                  // [nq_pad][dense_ld]
     long long dense_ld;

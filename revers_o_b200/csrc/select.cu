@@ -103,8 +103,15 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
     float* osc = a.out_scores + (size_t)q * (size_t)a.k;
 
     bool overflow = false;
-    const int raw = a.cnt ? a.cnt[q] : have;
-    if (a.cnt && raw > a.cap) overflow = true;
+    int raw = have;
+    if (a.cnt) {
+        raw = 0;
+        for (int sgm = 0; sgm < a.nseg; ++sgm) {
+            const int c = a.cnt[q * a.nseg + sgm];
+            raw += c;
+            if (c > a.cap) overflow = true;  // a sub-list dropped candidates
+        }
+    }
     float cut = -__int_as_float(0x7f800000);
     if (a.rescore && have >= a.k) {
         cut = key_score(s[a.k - 1]) - a.margin;
@@ -122,22 +129,25 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
     }
 
     if (a.rescore) {
-        // fp32 re-score of every kept candidate that can still reach the top-k: one warp per candidate,
-        // fp32 query (normalised) x bf16 DB row, fp32 FMA.
+        // fp32 re-score of every kept candidate that can still reach the top-k: 8 lanes per candidate (four
+        // candidates per warp in flight, 16 independent 16-byte loads per lane for d = 1024), fp32 query
+        // (normalised) x bf16 DB row, fp32 FMA, then a 3-step shuffle reduction inside the 8-lane group.
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        const int g = lane >> 3, l8 = lane & 7;
         const int nchunk = a.d_pad >> 3;
+        const int ntk = a.d_pad / kTileCols;
         const float* qv = a.qn + (size_t)q * (size_t)a.qn_ld;
-        for (int e = warp; e < have; e += nwarps) {
-            const unsigned long long key = s[e];
-            unsigned long long nk = 0ull;
-            if (key_score(key) >= cut) {
-                const uint32_t row = key_row(key);
-                // tiled DB storage: 16-byte chunk c of the row lives in tile (row/128, c/8)
-                const uint4* base = (const uint4*)a.db;
-                const int ntk = a.d_pad / kTileCols;
-                float acc = 0.f;
-                for (int c = lane; c < nchunk; c += 32) {
-                    const uint4 v = __ldg(base + (((size_t)(row >> 7) * ntk + (c >> 3)) * kTileRows + (row & 127)) * 8 + (c & 7));
+        const uint4* base = (const uint4*)a.db;  // tiled DB storage: 16-byte chunk c of a row lives in tile (row/128, c/8)
+        for (int e0 = 0; e0 < have; e0 += nwarps * 4) {
+            const int e = e0 + warp * 4 + g;
+            const unsigned long long key = e < have ? s[e] : 0ull;
+            const bool active = key != 0ull && key_score(key) >= cut;
+            const uint32_t row = key_row(key);
+            float acc = 0.f;
+            if (active) {
+                const uint4* r = base + ((size_t)(row >> 7) * ntk * kTileRows + (row & 127)) * 8;
+                for (int c = l8; c < nchunk; c += 8) {
+                    const uint4 v = __ldg(r + (size_t)(c >> 3) * kTileRows * 8 + (c & 7));
                     const float4 q0 = __ldg((const float4*)(qv + c * 8));
                     const float4 q1 = __ldg((const float4*)(qv + c * 8 + 4));
                     acc = fmaf(__uint_as_float(v.x << 16), q0.x, acc);
@@ -149,12 +159,11 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
                     acc = fmaf(__uint_as_float(v.w << 16), q1.z, acc);
                     acc = fmaf(__uint_as_float(v.w & 0xFFFF0000u), q1.w, acc);
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-                nk = make_key(acc, row);
             }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
             __syncwarp();
-            if (lane == 0) s[e] = nk;
+            if (l8 == 0 && e < have) s[e] = active ? make_key(acc, row) : 0ull;
         }
         __syncthreads();
         bitonic_desc_u64(s, K2);
@@ -177,22 +186,68 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
 // ---- exact top-K of one query's candidates by histogram refinement ---------------------------------
 // One CTA per query.  The 64-bit ordering keys are unique (score, row), so the K-th largest key is
 // found by narrowing a key range with 2048-bin histograms until at most kSelSort keys lie at or above
-// the range's lower bound; those are compacted into shared memory and sorted.  Work is O(n) per
-// round (1-2 rounds in practice) instead of the O(n log^2 n) of sorting every candidate.
-__device__ __forceinline__ unsigned long long select_load(const SelectArgs& a, int q, long long i) {
-    if (a.dense) {  // -inf marks rows past the end of the DB: empty key
-        const float v = a.dense[(size_t)q * (size_t)a.dense_ld + (size_t)i];
-        return v == -__int_as_float(0x7f800000) ? 0ull : make_key(v, (uint32_t)i);
+// the range's lower bound; those are compacted into shared memory and sorted.  A histogram over a small
+// SAMPLE first proposes the lower bound, so that the full-data histogram only sees the few keys near
+// the top (no shared-memory atomic contention, fine bins); if the proposal was too high the range is
+// widened to the true minimum, so the result is exact in every case.  Work is O(n) per round instead of
+// the O(n log^2 n) of sorting every candidate.
+template <class F>
+__device__ __forceinline__ void for_each_key(const SelectArgs& a, int q, const int* s_cnt, int sample_every, F f) {
+    if (a.dense) {
+        const float* src = a.dense + (size_t)q * (size_t)a.dense_ld;
+        const float NINF = -__int_as_float(0x7f800000);
+        for (long long i = (long long)threadIdx.x * sample_every; i < a.n_dense; i += (long long)blockDim.x * sample_every) {
+            const float v = src[i];
+            if (v != NINF) f(make_key(v, (uint32_t)i));  // -inf marks rows past the end of the DB
+        }
+    } else {
+        for (int sgm = 0; sgm < a.nseg; ++sgm) {
+            const unsigned long long* src = a.keys + ((size_t)q * a.nseg + sgm) * (size_t)a.cap;
+            const int c = s_cnt[sgm];
+            for (int i = threadIdx.x * sample_every; i < c; i += blockDim.x * sample_every) f(src[i]);
+        }
     }
-    return a.keys[(size_t)q * (size_t)a.keys_ld + (size_t)i];
 }
 
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a) {
+__device__ __forceinline__ int hist_shift(unsigned long long lo, unsigned long long hi) {
+    int shift = 0;
+    while (((hi - lo) >> shift) >= (unsigned long long)kSelBins) ++shift;
+    return shift;
+}
+
+// Warp 0: find the bin that holds the `need`-th largest key of the histogrammed range.
+// s_res = {bin, keys at/above the bin's lower bound (within the range), keys in the bin, found}.
+__device__ __forceinline__ void hist_find(const int* hist, int need, int lane, int* s_res) {
+    constexpr int per = kSelBins / 32;  // lane l owns bins [per*l, per*l + per)
+    int mine = 0;
+    for (int b = 0; b < per; ++b) mine += hist[lane * per + b];
+    int suffix = mine;  // inclusive suffix over lanes >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_down_sync(0xFFFFFFFFu, suffix, o);
+        if (lane + o < 32) suffix += t;
+    }
+    const int next = suffix - mine;
+    if (lane == 0 && suffix < need) s_res[3] = 0;
+    if (suffix >= need && next < need) {  // the crossing lane
+        int run = next, b = per - 1;
+        for (; b >= 0; --b) {
+            run += hist[lane * per + b];
+            if (run >= need) break;
+        }
+        s_res[0] = lane * per + b;
+        s_res[1] = run;
+        s_res[2] = hist[lane * per + b];
+        s_res[3] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs a) {
     __shared__ int hist[kSelBins];
     __shared__ unsigned long long sbuf[kSelSort];
     __shared__ unsigned long long s_red[2 * (kSelThreads / 32)];
-    __shared__ unsigned long long s_lo, s_hi;
-    __shared__ int s_above, s_count, s_done, s_shift;
+    __shared__ unsigned long long s_lo, s_hi, s_min;
+    __shared__ int s_above, s_count, s_done, s_cnt[32], s_res[4];
     const int q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float INF = __int_as_float(0x7f800000);
@@ -200,106 +255,112 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a)
         if (a.tau_out && tid == 0) a.tau_out[q] = INF;
         return;
     }
-    long long n = a.dense ? a.n_dense : (long long)(a.cnt[q] < a.cap ? a.cnt[q] : a.cap);
-    int C = 0;  // keys in sbuf
-    if (n <= kSelSort) {
-        const int ns = next_pow2((int)(n > 2 ? n : 2));
-        for (int i = tid; i < ns; i += blockDim.x) sbuf[i] = i < n ? select_load(a, q, i) : 0ull;
-        __syncthreads();
-        bitonic_desc_u64(sbuf, ns);
-        C = (int)n;
-    } else {
-        // round 0: key range
-        unsigned long long lmin = ~0ull, lmax = 0ull;
-        for (long long i = tid; i < n; i += blockDim.x) {
-            const unsigned long long k = select_load(a, q, i);
-            lmin = k < lmin ? k : lmin;
-            lmax = k > lmax ? k : lmax;
-        }
+    if (!a.dense && tid < a.nseg) {
+        const int c = a.cnt[q * a.nseg + tid];
+        s_cnt[tid] = c < a.cap ? c : a.cap;
+    }
+    __syncthreads();
+
+    // pass A: range and count of the keys
+    unsigned long long lmin = ~0ull, lmax = 0ull;
+    int lnz = 0;
+    for_each_key(a, q, s_cnt, 1, [&](unsigned long long k) {
+        lmin = k < lmin ? k : lmin;
+        lmax = k > lmax ? k : lmax;
+        ++lnz;
+    });
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long x = __shfl_xor_sync(0xFFFFFFFFu, lmin, o), y = __shfl_xor_sync(0xFFFFFFFFu, lmax, o);
-            lmin = x < lmin ? x : lmin;
-            lmax = y > lmax ? y : lmax;
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long x = __shfl_xor_sync(0xFFFFFFFFu, lmin, o), y = __shfl_xor_sync(0xFFFFFFFFu, lmax, o);
+        lmin = x < lmin ? x : lmin;
+        lmax = y > lmax ? y : lmax;
+        lnz += __shfl_xor_sync(0xFFFFFFFFu, lnz, o);
+    }
+    if (lane == 0) { s_red[warp] = lmin; s_red[kSelThreads / 32 + warp] = lmax; hist[warp] = lnz; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long mn = ~0ull, mx = 0ull;
+        int nnz = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) {
+            mn = s_red[w] < mn ? s_red[w] : mn;
+            mx = s_red[kSelThreads / 32 + w] > mx ? s_red[kSelThreads / 32 + w] : mx;
+            nnz += hist[w];
         }
-        if (lane == 0) { s_red[warp] = lmin; s_red[kSelThreads / 32 + warp] = lmax; }
+        s_min = mn; s_lo = mn; s_hi = mx; s_above = 0; s_count = nnz;
+        s_done = nnz <= kSelSort ? 1 : 0;  // few enough: keep every key
+    }
+    __syncthreads();
+    const int nnz = s_count;
+    const int want = a.K < nnz ? a.K : nnz;
+
+    if (!s_done) {
+        // round S: propose a lower bound from a sample (every `every`-th element of each sub-list / row)
+        const int every = nnz > 8 * kSelSort ? 8 : (nnz > 4 * kSelSort ? 4 : 2);
+        const unsigned long long lo0 = s_lo, hi0 = s_hi;
+        const int sh0 = hist_shift(lo0, hi0);
+        for (int i = tid; i < kSelBins; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        if (tid == 0) {
-            unsigned long long mn = ~0ull, mx = 0ull;
-            for (int w = 0; w < kSelThreads / 32; ++w) {
-                mn = s_red[w] < mn ? s_red[w] : mn;
-                mx = s_red[kSelThreads / 32 + w] > mx ? s_red[kSelThreads / 32 + w] : mx;
-            }
-            s_lo = mn; s_hi = mx; s_above = 0; s_done = 0;
+        for_each_key(a, q, s_cnt, every, [&](unsigned long long k) { atomicAdd(&hist[(int)((k - lo0) >> sh0)], 1); });
+        __syncthreads();
+        if (warp == 0) {
+            // aim at ~2x the wanted count above the bound (plus slack for sampling noise)
+            hist_find(hist, (2 * want) / every + 16, lane, s_res);
+            __syncwarp();
+            if (lane == 0 && s_res[3]) s_lo = lo0 + ((unsigned long long)s_res[0] << sh0);
         }
         __syncthreads();
-        const int want = (int)(a.K < n ? a.K : n);
-        for (int round = 0; round < 8; ++round) {
-            const unsigned long long lo = s_lo, hi = s_hi;
-            int shift = 0;
-            while (((hi - lo) >> shift) >= (unsigned long long)kSelBins) ++shift;
-            for (int i = tid; i < kSelBins; i += blockDim.x) hist[i] = 0;
-            __syncthreads();
-            for (long long i = tid; i < n; i += blockDim.x) {
-                const unsigned long long k = select_load(a, q, i);
-                if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
-            }
-            __syncthreads();
-            if (warp == 0) {
-                // suffix sums from the top bin: lane l owns bins [64 l, 64 l + 64)
-                constexpr int per = kSelBins / 32;
-                int mine = 0;
-                for (int b = 0; b < per; ++b) mine += hist[lane * per + b];
-                int suffix = mine;  // inclusive suffix over lanes >= lane
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_down_sync(0xFFFFFFFFu, suffix, o);
-                    if (lane + o < 32) suffix += t;
-                }
-                const int need = want - s_above;
-                // the crossing lane: suffix >= need while the suffix of the next lane is < need
-                const int next = suffix - mine;
-                const bool crossing = suffix >= need && next < need;
-                if (crossing) {
-                    int run = next, b = per - 1;
-                    for (; b >= 0; --b) {
-                        run += hist[lane * per + b];
-                        if (run >= need) break;
-                    }
-                    const int bstar = lane * per + b;
-                    const int cge = s_above + run;                       // keys >= lower bound of bin bstar
+    }
+
+    for (int round = 0; round < 10 && !s_done; ++round) {
+        const unsigned long long lo = s_lo, hi = s_hi;
+        const int shift = hist_shift(lo, hi);
+        __syncthreads();  // everyone has read s_lo/s_hi and finished with hist[] of the previous step
+        for (int i = tid; i < kSelBins; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for_each_key(a, q, s_cnt, 1, [&](unsigned long long k) {
+            if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+        });
+        __syncthreads();
+        if (warp == 0) {
+            const int need = want - s_above;
+            hist_find(hist, need, lane, s_res);
+            __syncwarp();
+            if (lane == 0) {
+                if (!s_res[3]) {
+                    s_lo = s_min;  // the proposed bound was too high: take the whole range (exactness first)
+                } else {
+                    const int cge = s_above + s_res[1];  // keys >= lower bound of the crossing bin
+                    s_lo = lo + ((unsigned long long)s_res[0] << shift);
                     if (cge <= kSelSort || shift == 0) {
-                        s_lo = lo + ((unsigned long long)bstar << shift);
                         s_done = 1;
                     } else {
-                        s_above = s_above + run - hist[bstar];          // keys strictly above the bin
-                        s_lo = lo + ((unsigned long long)bstar << shift);
+                        s_above = s_above + s_res[1] - s_res[2];  // keys strictly above the bin
                         s_hi = s_lo + ((1ull << shift) - 1ull);
                     }
-                    s_shift = shift;
                 }
             }
-            __syncthreads();
-            if (s_done) break;
-        }
-        // compaction of every key >= T, then a small sort
-        const unsigned long long T = s_lo;
-        if (tid == 0) s_count = 0;
-        __syncthreads();
-        for (long long i = tid; i < n; i += blockDim.x) {
-            const unsigned long long k = select_load(a, q, i);
-            if (k >= T) {
-                const int at = atomicAdd(&s_count, 1);
-                if (at < kSelSort) sbuf[at] = k;
-            }
         }
         __syncthreads();
-        C = s_count < kSelSort ? s_count : kSelSort;
-        const int ns = next_pow2(C > 2 ? C : 2);
-        for (int i = C + tid; i < ns; i += blockDim.x) sbuf[i] = 0ull;
-        __syncthreads();
-        bitonic_desc_u64(sbuf, ns);
     }
+
+    // compaction of every key >= T, then a small sort
+    const unsigned long long T = nnz <= kSelSort ? 0ull : s_lo;
+    __syncthreads();
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for_each_key(a, q, s_cnt, 1, [&](unsigned long long k) {
+        if (k >= T) {
+            const int at = atomicAdd(&s_count, 1);
+            if (at < kSelSort) sbuf[at] = k;
+        }
+    });
+    __syncthreads();
+    const int C = s_count < kSelSort ? s_count : kSelSort;
+    const int ns = next_pow2(C > 2 ? C : 2);
+    for (int i = C + tid; i < ns; i += blockDim.x) sbuf[i] = 0ull;
+    __syncthreads();
+    bitonic_desc_u64(sbuf, ns);
+
     if (a.out) {
         unsigned long long* out = a.out + (size_t)q * (size_t)a.out_ld;
         for (int i = tid; i < a.K; i += blockDim.x) out[i] = i < C ? sbuf[i] : 0ull;

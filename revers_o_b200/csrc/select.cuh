@@ -33,10 +33,9 @@ constexpr int kSelSort = 2048;    // keys compacted and sorted in shared memory
 struct SelectArgs {
     const float* dense;                 // dense mode: scores [nq][dense_ld], n_dense valid per query
     long long dense_ld, n_dense;
-    const unsigned long long* keys;     // list mode: keys [nq][keys_ld], min(cnt[q], cap) valid
-    long long keys_ld;
-    const int* cnt;
-    int cap;
+    const unsigned long long* keys;     // list mode: keys [nq][nseg][cap]; sub-list s of query q holds
+    const int* cnt;                     //   min(cnt[q*nseg + s], cap) valid keys
+    int nseg, cap;
     int K;                              // top keys wanted (<= 1024)
     unsigned long long* out;            // [nq][out_ld] top-K keys, sorted descending, zero padded (or nullptr)
     long long out_ld;
@@ -50,8 +49,8 @@ struct SelectArgs {
 struct FinalArgs {
     const unsigned long long* top;      // [nq][top_ld], first K2 sorted descending
     long long top_ld;
-    const int* cnt;                     // raw candidate counts (overflow detection) or nullptr
-    int cap, K2, k;
+    const int* cnt;                     // raw candidate counts [nq][nseg] (overflow detection) or nullptr
+    int nseg, cap, K2, k;
     float score_threshold, margin;
     int rescore;                        // 1: keys carry bf16-query tensor scores -> fp32 re-score
     const uint16_t* db;                 // tiled DB storage (common.cuh)

@@ -4,13 +4,14 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 TAG=${1:-prof}; shift
+KREGEX=${KREGEX:-scan_tc_kernel}; KSKIP=${KSKIP:-3}; KCOUNT=${KCOUNT:-3}
 ARGS="--steps 2 --warmup 1 --no-cpu-baseline $*"
 python bench.py $ARGS > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py $ARGS > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "launch list rc=$?"
 python bench.py $ARGS > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:scan_tc_kernel -s 3 -c 3 -o gpurun_out/${TAG}_scan \
+ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s $KSKIP -c $KCOUNT -o gpurun_out/${TAG}_scan \
     python bench.py $ARGS > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "full capture rc=$?"
 tail -n 3 gpurun_out/${TAG}_plain.log

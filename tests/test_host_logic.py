@@ -26,7 +26,7 @@ def test_shard_bounds_cover_exactly():
         for w in (1, 2, 3, 4, 8):
             b = [shard_bounds(n, w, r) for r in range(w)]
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
-            assert all(lo % 128 == 0 for lo, _ in b)                      # shards are whole blocks of the tiled storage
+            assert all(lo % 128 == 0 or lo == n for lo, _ in b)             # shards are whole blocks of the tiled storage
             if n >= 128 * w:
                 sizes = [hi - lo for lo, hi in b]
                 assert max(sizes) - min(sizes) <= 128
