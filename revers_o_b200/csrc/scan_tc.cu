@@ -173,8 +173,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
         uint32_t wcount = 0;
         int cur_qb = -1;
         // candidate appends in flight from the previous TMEM slot (FILTER mode)
-        const int seg = (int)(blockIdx.x % kCandSplit);  // this CTA's sub-list of every query
-        int pend_n = 0, pend_q0 = 0;
+        int pend_n = 0, pend_q0 = 0, pend_seg = 0;
         uint32_t pend_row = 0;
         int pend_pos[4] = {0, 0, 0, 0};
         unsigned long long pend_ent[4] = {0ull, 0ull, 0ull, 0ull};
@@ -186,6 +185,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
             long long left = (p.n_rows - row0 + kBlockM - 1) / kBlockM;
             const int m_valid = left < m_sub ? (int)left : m_sub;
             const int q0 = qb * nq_blk;
+            // sub-list of every query this super-tile appends to: a function of the ROW range only, so that the
+            // 16 sub-lists of a query fill evenly whatever the CTA <-> query-block assignment is
+            const int seg = (int)(st % kCandSplit);
             const uint32_t tbuf = p.num_qblk > 1 ? (wcount & 1u) : 0u;
             const float* tau_s = s_tau + tbuf * 256;
 
@@ -293,7 +295,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                         if (u < pend_n && pend_pos[u] < p.cap) {
                             const int q = pend_q0 + (int)(pend_ent[u] & 0xFFFFu);
                             const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(pend_ent[u] >> 32)));
-                            p.cand[((size_t)q * kCandSplit + seg) * (size_t)p.cap + (size_t)pend_pos[u]] =
+                            p.cand[((size_t)q * kCandSplit + pend_seg) * (size_t)p.cap + (size_t)pend_pos[u]] =
                                 ((unsigned long long)ob << 32) | (unsigned long long)pend_row;
                         }
 #pragma unroll
@@ -304,6 +306,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                         }
                     pend_n = n < 4 ? n : 4;
                     pend_q0 = q0;
+                    pend_seg = seg;
                     pend_row = key_row_bits;
                     if (n > 4) flush_sync(4, n);
                 }
@@ -316,7 +319,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                 if (u < pend_n && pend_pos[u] < p.cap) {
                     const int q = pend_q0 + (int)(pend_ent[u] & 0xFFFFu);
                     const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(pend_ent[u] >> 32)));
-                    p.cand[((size_t)q * kCandSplit + seg) * (size_t)p.cap + (size_t)pend_pos[u]] =
+                    p.cand[((size_t)q * kCandSplit + pend_seg) * (size_t)p.cap + (size_t)pend_pos[u]] =
                         ((unsigned long long)ob << 32) | (unsigned long long)pend_row;
                 }
         }

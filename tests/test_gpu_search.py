@@ -79,6 +79,21 @@ def test_search_matches_oracle(dev, n, d, nq, k):
     assert np.all(cnt == min(k, n))
 
 
+def test_many_query_blocks_and_intermediate_level(dev):
+    """3 query blocks (600 queries) over 1.7M rows: DENSE seed + one sampled FILTER level + the full scan.  Every
+    query must come back unflagged (candidate sub-lists must fill evenly across query blocks) and exact."""
+    from revers_o_b200 import ops, synth
+    n, d, nq, k = 1_700_000, 256, 600, 100
+    q = synth.make_queries(nq, d, seed=51, device=dev)
+    db = synth.make_db(n, d, q, n_plant=128, seed=52, device=dev)
+    ids, sc, cnt = _run(db, n, d, q, k)
+    assert np.all(cnt == k), f"{int(np.sum(cnt < 0))} queries overflowed"
+    sel = list(range(0, nq, 50))
+    dbf = ops.untile_rows(db, n, d).float().cpu().numpy()
+    ref = O.search_batch(dbf, q[sel].cpu().numpy(), k, None, db_is_normalized=True)
+    assert_topk_match(ids[sel], sc[sel], cnt[sel], ref, k, TOL, "multiblock")
+
+
 def test_scores_also_within_tolerance_of_unrounded_fp32_db(dev):
     """The GPU DB is bf16; the reference's is fp32.  North-star tolerance (1e-3) must hold against the fp32 DB too."""
     from revers_o_b200 import ops
