@@ -169,7 +169,8 @@ float rvo_last_scan_ms(void);
 /* Tuning knobs (benchmarks/tests only; defaults reproduce the documented behaviour).
  *   name: "force_path" (0 auto, 1 small-q scan, 2 tcgen05 scan), "m_sub" (0 auto,1,2),
  *         "cand_cap" (candidates per query, default 32768), "final_ratio" (default 48),
- *         "time_scan" (0/1, see rvo_last_scan_ms)                                                */
+ *         "time_scan" (0/1, see rvo_last_scan_ms), "pool_path" (0 auto: tensor-core mask pooling when the
+ *         shape fits TMEM, 1: CUDA-core kernels)                                                */
 int rvo_set_option(const char* name, int64_t value);
 
 #ifdef __cplusplus

@@ -10,6 +10,7 @@
 
 namespace rvo {
 
+extern bool g_force_cuda_core_pool;
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 
@@ -277,6 +278,7 @@ int rvo_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "cand_cap")) opt_cand_cap = value;
     else if (!strcmp(name, "final_ratio")) opt_final_ratio = value;
     else if (!strcmp(name, "time_scan")) opt_time_scan = value;
+    else if (!strcmp(name, "pool_path")) g_force_cuda_core_pool = value == 1;
     else {
         set_error("unknown option '%s'", name);
         return RVO_E_INVALID;

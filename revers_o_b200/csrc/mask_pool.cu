@@ -21,6 +21,7 @@ namespace rvo {
 constexpr int kPoolThreads = 512;
 constexpr int kPoolWarps = kPoolThreads / 32;
 constexpr int kSlab = 32;  // channels per CTA
+bool g_force_cuda_core_pool = false;  // option "pool_path" = 1: always use the CUDA-core kernels below
 
 __global__ void __launch_bounds__(256) mask_index_kernel(const uint8_t* __restrict__ masks, int BM, int M, int P, int lim,
                                                          uint16_t* __restrict__ idx, int* __restrict__ area) {
@@ -188,10 +189,15 @@ __global__ void __launch_bounds__(256) mask_scale_kernel(float* __restrict__ out
     }
 }
 
+int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int lim, float* out,
+                        int32_t* out_counts, int32_t* out_src, int32_t* out_total, int* img_base, unsigned int* ticket,
+                        int sm_count, cudaStream_t stream);
+
 size_t mask_pool_workspace_bytes(int B, int M, int P, int D) {
     (void)D;
     const size_t bm = (size_t)B * M;
     size_t n = 0;
+    n += align_up((size_t)B * sizeof(int), 256) + 256;  // img_base + ticket (tensor-core path)
     n += align_up(bm * P * sizeof(uint16_t), 256);  // patch lists
     n += align_up(bm * sizeof(int), 256) * 3;       // area, out_row, src_of_row
     n += align_up(bm * sizeof(float), 256);         // sumsq
@@ -201,7 +207,6 @@ size_t mask_pool_workspace_bytes(int B, int M, int P, int D) {
 int launch_mask_pool(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int max_regions, float* out,
                      int32_t* out_counts, int32_t* out_src, int32_t* out_total, void* workspace, size_t workspace_bytes,
                      int sm_count, cudaStream_t stream) {
-    (void)sm_count;
     if (D % kSlab != 0) {
         set_error("mask_pool: D=%d must be a multiple of %d", D, kSlab);
         return RVO_E_INVALID;
@@ -213,6 +218,8 @@ int launch_mask_pool(const uint16_t* feats, const uint8_t* masks, int B, int M, 
     const int lim = (max_regions <= 0 || max_regions > M) ? M : max_regions;
     const int bm = B * M;
     Arena ar(workspace, workspace_bytes);
+    int* img_base = ar.take<int>(B);
+    unsigned int* ticket = ar.take<unsigned int>(1);
     uint16_t* idx = ar.take<uint16_t>((size_t)bm * P);
     int* area = ar.take<int>(bm);
     int* out_row = ar.take<int>(bm);
@@ -221,6 +228,13 @@ int launch_mask_pool(const uint16_t* feats, const uint8_t* masks, int B, int M, 
     if (!ar.ok()) {
         set_error("mask_pool: workspace too small (%zu < %zu)", workspace_bytes, ar.off);
         return RVO_E_WORKSPACE;
+    }
+    if (!g_force_cuda_core_pool) {
+        // tensor-core path (mask_pool_tc.cu) whenever the image's whole output fits TMEM
+        RVO_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
+        const int rc = launch_mask_pool_tc(feats, masks, B, M, P, D, lim, out, out_counts, out_src, out_total, img_base,
+                                           ticket, sm_count, stream);
+        if (rc <= 0) return rc;
     }
     const int p_pad = (P + 7) & ~7;
     const size_t smem = (size_t)P * kSlab * 4 + (size_t)kPoolWarps * p_pad * 2;
