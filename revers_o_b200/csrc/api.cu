@@ -442,6 +442,7 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
         memset(&sa, 0, sizeof(sa));
         sa.nq = nq;
         sa.keys = sp.cand;
+        sa.range_lo = tau_in;
         sa.cnt = cnt;
         sa.nseg = kCandSplit;
         sa.cap = sp.cap;

@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(kSelThreads) chunk_topk_kernel(const ChunkTopk
     }
 }
 
-// grid (nq), 256 threads.  `top` holds the K2 best candidates of the query by tensor-core score.
-__global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
+// grid (nq), 512 threads.  `top` holds the K2 best candidates of the query by tensor-core score.
+__global__ void __launch_bounds__(512) final_kernel(const FinalArgs a) {
     __shared__ unsigned long long s[1024];
     __shared__ int s_flag;
     const int q = blockIdx.x;
@@ -261,100 +261,123 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
     }
     __syncthreads();
 
-    // pass A: range and count of the keys
-    unsigned long long lmin = ~0ull, lmax = 0ull;
-    int lnz = 0;
-    for_each_key(a, q, s_cnt, 1, [&](unsigned long long k) {
-        lmin = k < lmin ? k : lmin;
-        lmax = k > lmax ? k : lmax;
-        ++lnz;
-    });
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long x = __shfl_xor_sync(0xFFFFFFFFu, lmin, o), y = __shfl_xor_sync(0xFFFFFFFFu, lmax, o);
-        lmin = x < lmin ? x : lmin;
-        lmax = y > lmax ? y : lmax;
-        lnz += __shfl_xor_sync(0xFFFFFFFFu, lnz, o);
-    }
-    if (lane == 0) { s_red[warp] = lmin; s_red[kSelThreads / 32 + warp] = lmax; hist[warp] = lnz; }
-    __syncthreads();
+    // number of keys (dense: sample columns, the few -inf pads of the last tile included) and the key range
     if (tid == 0) {
-        unsigned long long mn = ~0ull, mx = 0ull;
         int nnz = 0;
-        for (int w = 0; w < kSelThreads / 32; ++w) {
-            mn = s_red[w] < mn ? s_red[w] : mn;
-            mx = s_red[kSelThreads / 32 + w] > mx ? s_red[kSelThreads / 32 + w] : mx;
-            nnz += hist[w];
-        }
-        s_min = mn; s_lo = mn; s_hi = mx; s_above = 0; s_count = nnz;
+        if (a.dense) nnz = (int)a.n_dense;
+        else for (int sgm = 0; sgm < a.nseg; ++sgm) nnz += s_cnt[sgm];
+        float lo_f = -2.0f;
+        if (a.range_lo) lo_f = fmaxf(a.range_lo[q], -2.0f);   // every list key scored >= its admission threshold
+        s_min = (unsigned long long)f32_orderable(lo_f) << 32;
+        s_lo = s_min;
+        s_hi = ((unsigned long long)f32_orderable(2.0f) << 32) | 0xFFFFFFFFull;
+        s_above = 0;
+        s_count = nnz;
         s_done = nnz <= kSelSort ? 1 : 0;  // few enough: keep every key
     }
     __syncthreads();
     const int nnz = s_count;
     const int want = a.K < nnz ? a.K : nnz;
+    auto compact = [&](unsigned long long T) {   // keys >= T -> sbuf (first kSelSort of them), count -> s_count
+        __syncthreads();
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        for_each_key(a, q, s_cnt, 1, [&](unsigned long long k) {
+            if (k >= T) {
+                const int at = atomicAdd(&s_count, 1);
+                if (at < kSelSort) sbuf[at] = k;
+            }
+        });
+        __syncthreads();
+    };
 
-    if (!s_done) {
-        // round S: propose a lower bound from a sample (every `every`-th element of each sub-list / row)
+    bool fast = false;
+    if (s_done) {
+        compact(0ull);
+        fast = true;
+    } else {
+        // round S: a histogram over a sample (every `every`-th element of each sub-list / row) proposes the bound
         const int every = nnz > 8 * kSelSort ? 8 : (nnz > 4 * kSelSort ? 4 : 2);
         const unsigned long long lo0 = s_lo, hi0 = s_hi;
         const int sh0 = hist_shift(lo0, hi0);
         for (int i = tid; i < kSelBins; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        for_each_key(a, q, s_cnt, every, [&](unsigned long long k) { atomicAdd(&hist[(int)((k - lo0) >> sh0)], 1); });
-        __syncthreads();
-        if (warp == 0) {
-            // aim at ~2x the wanted count above the bound (plus slack for sampling noise)
-            hist_find(hist, (2 * want) / every + 16, lane, s_res);
-            __syncwarp();
-            if (lane == 0 && s_res[3]) s_lo = lo0 + ((unsigned long long)s_res[0] << sh0);
-        }
-        __syncthreads();
-    }
-
-    for (int round = 0; round < 10 && !s_done; ++round) {
-        const unsigned long long lo = s_lo, hi = s_hi;
-        const int shift = hist_shift(lo, hi);
-        __syncthreads();  // everyone has read s_lo/s_hi and finished with hist[] of the previous step
-        for (int i = tid; i < kSelBins; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
-        for_each_key(a, q, s_cnt, 1, [&](unsigned long long k) {
-            if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+        for_each_key(a, q, s_cnt, every, [&](unsigned long long k) {
+            if (k >= lo0) atomicAdd(&hist[(int)((k - lo0) >> sh0)], 1);
         });
         __syncthreads();
         if (warp == 0) {
-            const int need = want - s_above;
-            hist_find(hist, need, lane, s_res);
+            // aim at ~1.5x the wanted count above the bound (plus slack for sampling noise)
+            hist_find(hist, (3 * want) / (2 * every) + 24, lane, s_res);
             __syncwarp();
-            if (lane == 0) {
-                if (!s_res[3]) {
-                    s_lo = s_min;  // the proposed bound was too high: take the whole range (exactness first)
-                } else {
-                    const int cge = s_above + s_res[1];  // keys >= lower bound of the crossing bin
-                    s_lo = lo + ((unsigned long long)s_res[0] << shift);
-                    if (cge <= kSelSort || shift == 0) {
+            if (lane == 0) s_lo = s_res[3] ? lo0 + ((unsigned long long)s_res[0] << sh0) : 0ull;
+        }
+        __syncthreads();
+        // one compaction pass with the proposed bound; exact whenever it kept between `want` and kSelSort keys
+        const unsigned long long T0 = s_lo;
+        compact(T0);
+        fast = s_count >= want && s_count <= kSelSort;
+    }
+
+    if (!fast) {
+        // rigorous path: true key range, then histogram refinement until <= kSelSort keys lie at/above the bound
+        unsigned long long lmin = ~0ull, lmax = 0ull;
+        for_each_key(a, q, s_cnt, 1, [&](unsigned long long k) {
+            lmin = k < lmin ? k : lmin;
+            lmax = k > lmax ? k : lmax;
+        });
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long x = __shfl_xor_sync(0xFFFFFFFFu, lmin, o), y = __shfl_xor_sync(0xFFFFFFFFu, lmax, o);
+            lmin = x < lmin ? x : lmin;
+            lmax = y > lmax ? y : lmax;
+        }
+        if (lane == 0) { s_red[warp] = lmin; s_red[kSelThreads / 32 + warp] = lmax; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long mn = ~0ull, mx = 0ull;
+            for (int w = 0; w < kSelThreads / 32; ++w) {
+                mn = s_red[w] < mn ? s_red[w] : mn;
+                mx = s_red[kSelThreads / 32 + w] > mx ? s_red[kSelThreads / 32 + w] : mx;
+            }
+            s_min = mn; s_lo = mn; s_hi = mx; s_above = 0; s_done = 0;
+        }
+        __syncthreads();
+        for (int round = 0; round < 12 && !s_done; ++round) {
+            const unsigned long long lo = s_lo, hi = s_hi;
+            const int shift = hist_shift(lo, hi);
+            __syncthreads();  // everyone has read s_lo/s_hi and finished with hist[] of the previous step
+            for (int i = tid; i < kSelBins; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            for_each_key(a, q, s_cnt, 1, [&](unsigned long long k) {
+                if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+            });
+            __syncthreads();
+            if (warp == 0) {
+                const int need = want - s_above;
+                hist_find(hist, need, lane, s_res);
+                __syncwarp();
+                if (lane == 0) {
+                    if (!s_res[3]) {
+                        s_lo = s_min;  // fewer than `want` keys exist (padded dense sample): take everything
                         s_done = 1;
                     } else {
-                        s_above = s_above + s_res[1] - s_res[2];  // keys strictly above the bin
-                        s_hi = s_lo + ((1ull << shift) - 1ull);
+                        const int cge = s_above + s_res[1];  // keys >= lower bound of the crossing bin
+                        s_lo = lo + ((unsigned long long)s_res[0] << shift);
+                        if (cge <= kSelSort || shift == 0) {
+                            s_done = 1;
+                        } else {
+                            s_above = s_above + s_res[1] - s_res[2];  // keys strictly above the bin
+                            s_hi = s_lo + ((1ull << shift) - 1ull);
+                        }
                     }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
+        const unsigned long long T1 = s_lo;
+        compact(T1);
     }
-
-    // compaction of every key >= T, then a small sort
-    const unsigned long long T = nnz <= kSelSort ? 0ull : s_lo;
-    __syncthreads();
-    if (tid == 0) s_count = 0;
-    __syncthreads();
-    for_each_key(a, q, s_cnt, 1, [&](unsigned long long k) {
-        if (k >= T) {
-            const int at = atomicAdd(&s_count, 1);
-            if (at < kSelSort) sbuf[at] = k;
-        }
-    });
-    __syncthreads();
     const int C = s_count < kSelSort ? s_count : kSelSort;
     const int ns = next_pow2(C > 2 ? C : 2);
     for (int i = C + tid; i < ns; i += blockDim.x) sbuf[i] = 0ull;
@@ -458,7 +481,7 @@ int launch_chunk_topk(const ChunkTopkArgs& a, int num_chunks, int nq, cudaStream
 }
 
 int launch_final(const FinalArgs& a, int nq, cudaStream_t stream) {
-    final_kernel<<<nq, 256, 0, stream>>>(a);
+    final_kernel<<<nq, 512, 0, stream>>>(a);
     RVO_LAUNCHED();
     return RVO_OK;
 }

@@ -44,6 +44,7 @@ struct SelectArgs {
     int tau_k;
     float tau_margin, tau_floor;
     int nq;                             // CTAs q >= nq only write tau_out[q] = +inf (padded query rows)
+    const float* range_lo;              // optional per-query lower bound of every key's score (finer first bins)
 };
 
 struct FinalArgs {
