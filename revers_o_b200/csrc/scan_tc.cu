@@ -375,6 +375,10 @@ static int make_tmap(CUtensorMap* m, const void* base, long long rows, int d_pad
     return RVO_OK;
 }
 
+int make_scan_tmap(CUtensorMap* m, const void* base, long long rows, int d_pad, long long pitch_elems, int box_rows) {
+    return make_tmap(m, base, rows, d_pad, pitch_elems, box_rows, false);
+}
+
 int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl) {
     if (nq < 1 || d_pad < kBlockK || d_pad % kBlockK != 0) {
         set_error("plan_scan_tc: bad nq=%d d_pad=%d", nq, d_pad);
@@ -421,6 +425,14 @@ int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl) {
     pl->off_tau = pl->off_queue + (size_t)kQueueCap * kEpiThreads * 8;
     pl->off_bars = pl->off_tau + 2 * 256 * 4;
     pl->smem_bytes = pl->off_bars + 512;
+    pl->pair = 0;
+    // query block too large to stay resident: CTA pairs halve the query operand's L2->SM traffic (scan_tc2.cu)
+    if (!pl->resident && force_m_sub <= 0 && pl->nq_blk >= 32) {
+        TcPlan p2;
+        plan_scan_tc2(*pl, d_pad, &p2);
+        p2.pair = 1;
+        *pl = p2;
+    }
     return RVO_OK;
 }
 
@@ -434,6 +446,9 @@ int launch_scan_tc(int mode, const uint16_t* db, long long n_rows, long long sup
                    const uint16_t* q_bf16, const TcPlan& pl, const float* tau, unsigned long long* cand,
                    int* cand_cnt, int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream) {
     if (n_rows <= 0) return RVO_OK;
+    if (pl.pair)
+        return launch_scan_tc2(mode, db, n_rows, super_stride, d_pad, q_bf16, pl, tau, cand, cand_cnt, cap, dense, dense_ld,
+                               sm_count, stream);
     if (n_rows >= (1ll << 31)) {
         set_error("launch_scan_tc: shard too large (%lld rows); shard the DB", n_rows);
         return RVO_E_INVALID;

@@ -39,10 +39,15 @@ struct ScanParams {
 
 struct TcPlan {
     int nq_blk, num_qblk, nq_pad, m_sub, num_stages, resident, slot_w, num_slots;
+    int pair;   // 1: CTA-pair kernel (cta_group::2, scan_tc2.cu)
     size_t stage_bytes, off_stages, off_queue, off_tau, off_bars, smem_bytes;
 };
 
-int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl);
+int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl);   // force_m_sub: 0 auto, 1/2 single-CTA kernel
+int plan_scan_tc2(const TcPlan& base, int d_pad, TcPlan* pl);
+int launch_scan_tc2(int mode, const uint16_t* db, long long n_rows, long long super_stride, int d_pad,
+                    const uint16_t* q_bf16, const TcPlan& pl, const float* tau, unsigned long long* cand, int* cand_cnt,
+                    int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream);
 // columns of the DENSE output / rows visited when only every super_stride-th super-tile is scanned
 long long scan_tc_sample_rows(long long n_rows, const TcPlan& pl, long long super_stride);
 int launch_scan_tc(int mode, const uint16_t* db, long long n_rows, long long super_stride, int d_pad,
