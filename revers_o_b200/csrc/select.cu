@@ -191,20 +191,44 @@ __global__ void __launch_bounds__(512) final_kernel(const FinalArgs a) {
 // the top (no shared-memory atomic contention, fine bins); if the proposal was too high the range is
 // widened to the true minimum, so the result is exact in every case.  Work is O(n) per round instead of
 // the O(n log^2 n) of sorting every candidate.
+// Visit every key of query q (or every `sample_every`-th).  Loads are issued four at a time before any of them is
+// consumed, so that a thread has four L2 round trips in flight instead of one (the loop body may contain atomics,
+// which keeps the compiler from hoisting the loads itself).
 template <class F>
 __device__ __forceinline__ void for_each_key(const SelectArgs& a, int q, const int* s_cnt, int sample_every, F f) {
     if (a.dense) {
         const float* src = a.dense + (size_t)q * (size_t)a.dense_ld;
         const float NINF = -__int_as_float(0x7f800000);
-        for (long long i = (long long)threadIdx.x * sample_every; i < a.n_dense; i += (long long)blockDim.x * sample_every) {
-            const float v = src[i];
-            if (v != NINF) f(make_key(v, (uint32_t)i));  // -inf marks rows past the end of the DB
+        const int n = (int)a.n_dense, step = (int)blockDim.x * sample_every;
+        for (int i0 = (int)threadIdx.x * sample_every; i0 < n; i0 += 4 * step) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (i0 + u * step) < n ? __ldg(src + i0 + u * step) : NINF;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (v[u] != NINF) f(make_key(v[u], (uint32_t)(i0 + u * step)));  // -inf: rows past the end of the DB
         }
     } else {
-        for (int sgm = 0; sgm < a.nseg; ++sgm) {
-            const unsigned long long* src = a.keys + ((size_t)q * a.nseg + sgm) * (size_t)a.cap;
-            const int c = s_cnt[sgm];
-            for (int i = threadIdx.x * sample_every; i < c; i += blockDim.x * sample_every) f(src[i]);
+        // all sub-lists of the query as one index space: thread t takes elements t, t + blockDim, ... of each
+        const int step = (int)blockDim.x * sample_every;
+        for (int sg0 = 0; sg0 < a.nseg; sg0 += 4) {
+            // four sub-lists side by side (their first blockDim elements cover most of a typical sub-list)
+            int cmax = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (sg0 + u < a.nseg) cmax = s_cnt[sg0 + u] > cmax ? s_cnt[sg0 + u] : cmax;
+            for (int i = (int)threadIdx.x * sample_every; i < cmax; i += step) {
+                unsigned long long k[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int sgm = sg0 + u;
+                    k[u] = (sgm < a.nseg && i < s_cnt[sgm])
+                               ? a.keys[((size_t)q * a.nseg + sgm) * (size_t)a.cap + (size_t)i] : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k[u]) f(k[u]);
+            }
         }
     }
 }

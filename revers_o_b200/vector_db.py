@@ -177,15 +177,20 @@ class B200VectorDB:
         nq = qd.shape[0]
         if as_device:
             return ops.search_topk_exact(vectors, n, c.dim, qd, k, score_threshold)
-        ids, scores, counts = ops.search_topk(vectors, n, c.dim, qd, k, score_threshold)
-        hi = self._pinned("ids", nq * k * 8).view(torch.int64)[: nq * k].view(nq, k)
-        hs = self._pinned("sc", nq * k * 4).view(torch.float32)[: nq * k].view(nq, k)
-        hc = self._pinned("cnt", nq * 4).view(torch.int32)[:nq]
-        hi.copy_(ids, non_blocking=True)
-        hs.copy_(scores, non_blocking=True)
-        hc.copy_(counts, non_blocking=True)
+        # results land in ONE device blob [ids int64 | scores f32 | counts i32] -> one D2H copy
+        nb_i, nb_s, nb_c = nq * k * 8, nq * k * 4, nq * 4
+        blob = self._device_buf("res", nb_i + nb_s + nb_c)
+        ids = blob[:nb_i].view(torch.int64).view(nq, k)
+        scores = blob[nb_i: nb_i + nb_s].view(torch.float32).view(nq, k)
+        counts = blob[nb_i + nb_s: nb_i + nb_s + nb_c].view(torch.int32)
+        ops.search_topk(vectors, n, c.dim, qd, k, score_threshold, out=(ids, scores, counts))
+        hb = self._pinned("res", nb_i + nb_s + nb_c)
+        hb.copy_(blob[: hb.numel()], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        out_i, out_s, out_c = hi.numpy().copy(), hs.numpy().copy(), hc.numpy().copy()
+        host = hb.numpy()
+        out_i = host[:nb_i].view(np.int64).reshape(nq, k).copy()
+        out_s = host[nb_i: nb_i + nb_s].view(np.float32).reshape(nq, k).copy()
+        out_c = host[nb_i + nb_s: nb_i + nb_s + nb_c].view(np.int32).copy()
         bad = np.nonzero(out_c < 0)[0]
         if len(bad):  # overflow protocol of rvo_search_topk: exact fp32 scan in batches of <= RVO_SMALL_Q
             a, b, cc = ops.search_topk_exact(vectors, n, c.dim, qd[torch.from_numpy(bad).to(self.device)].contiguous(), k,
