@@ -39,6 +39,9 @@ WORKLOADS = {
     "cfg1": (1_000_000, 1024, 256, 100, "configs[1]: 1M x 1024 bf16 DB, 256-query batch, top-100, fp32 rescore"),
     "cfg3shard": (12_500_000, 1280, 4096, 100, "configs[3] per-GPU shard: 12.5M x 1280 bf16, 4096-query batch, top-100"),
     "cfg3small": (12_500_000, 1280, 16, 100, "configs[3] per-GPU shard, bandwidth regime: 12.5M x 1280, 16 queries"),
+    "cfg3q64": (12_500_000, 1280, 64, 100, "configs[3] per-GPU shard, bandwidth regime: 12.5M x 1280, 64 queries"),
+    "cfg3q1": (12_500_000, 1280, 1, 100, "configs[3] per-GPU shard, the reference's operating point: 12.5M x 1280, 1 query"),
+    "cfg1q1": (1_000_000, 1024, 1, 10, "configs[1] DB, the reference's operating point: 1M x 1024, 1 query, top-10"),
 }
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 

@@ -327,7 +327,10 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
         for (int i = tid; i < kSelBins; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         for_each_key(a, q, s_cnt, every, [&](unsigned long long k) {
-            if (k >= lo0) atomicAdd(&hist[(int)((k - lo0) >> sh0)], 1);
+            if (k >= lo0) {
+                const unsigned long long b = (k - lo0) >> sh0;   // NaN scores order above +2.0: clamp into the top bin
+                atomicAdd(&hist[b < (unsigned long long)kSelBins ? (int)b : kSelBins - 1], 1);
+            }
         });
         __syncthreads();
         if (warp == 0) {

@@ -4,7 +4,7 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 TAG=${1:-prof}; shift
-KREGEX=${KREGEX:-scan_tc_kernel}; KSKIP=${KSKIP:-3}; KCOUNT=${KCOUNT:-3}
+KREGEX=${KREGEX:-scan_tc}; KSKIP=${KSKIP:-3}; KCOUNT=${KCOUNT:-3}
 ARGS="--steps 2 --warmup 1 --no-cpu-baseline $*"
 python bench.py $ARGS > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
