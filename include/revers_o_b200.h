@@ -155,6 +155,24 @@ int rvo_merge_topk_packed(const void* gathered, int64_t rank_stride_bytes, int32
                           int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Near-duplicate self-join (BASELINE.json config 4): all pairs (i, j), row_lo <= i < row_hi, i < j < n_rows,
+ * with cos(db[i], db[j]) >= threshold — the reference's `score_threshold` rule (core_system.py:663) with every
+ * stored row as a query.  The reference has no such feature (video_processing.py only writes frames).
+ * Built on K2: blocks of 4096 query rows, FILTER scan of the upper triangle, exact fp32 re-score of candidates.
+ *   out_pairs  [dev] int64 [out_cap][2] (i, j) + id_offset, in no particular order
+ *   out_scores [dev] float32 [out_cap]  fp32 dot of the two stored bf16 rows
+ *   out_count  [dev] uint64 [1]  pairs found (only the first out_cap are stored)
+ *   out_overflowed [dev] int32 [1]  candidate sub-lists that overflowed (> 0: result incomplete; raise "cand_cap")
+ *   workspace  [dev] rvo_selfjoin_workspace_bytes(d) bytes, 1024-B aligned
+ * Multi-GPU: DB replicated, ranks take disjoint [row_lo, row_hi) ranges; no collective on the data path.
+ * ---------------------------------------------------------------------------------------------- */
+size_t rvo_selfjoin_workspace_bytes(int32_t d);
+int rvo_selfjoin_threshold(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad, int64_t row_lo, int64_t row_hi,
+                           float threshold, int64_t id_offset, int64_t* out_pairs, float* out_scores, int64_t out_cap,
+                           uint64_t* out_count, int32_t* out_overflowed, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Counters for bench.py's `gpu_launches` claim: number of kernels THIS library has launched on the
  * calling process since load (monotonic).
  * ---------------------------------------------------------------------------------------------- */

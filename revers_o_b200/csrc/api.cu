@@ -11,6 +11,11 @@
 namespace rvo {
 
 extern bool g_force_cuda_core_pool;
+size_t selfjoin_workspace_bytes(int d, long long cand_cap);
+int launch_selfjoin(const uint16_t* db, long long n_rows, int d, long long row_lo, long long row_hi, float threshold,
+                    long long id_offset, long long cand_cap, long long* out_pairs, float* out_scores, long long out_cap,
+                    unsigned long long* out_count, int* out_overflowed, void* ws, size_t ws_bytes, int sm_count,
+                    cudaStream_t stream);
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 
@@ -517,6 +522,29 @@ int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pa
     if (rc) return rc;
     return launch_scan_tc(kModeDense, db, n_rows, tile_stride, d_pad, qb, tc, nullptr, nullptr, nullptr, 0, out, out_ld, sm,
                           stream);
+}
+
+size_t rvo_selfjoin_workspace_bytes(int32_t d) {
+    if (d <= 0) return 0;
+    return selfjoin_workspace_bytes(d, opt_cand_cap.load());
+}
+
+int rvo_selfjoin_threshold(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad_in, int64_t row_lo, int64_t row_hi,
+                           float threshold, int64_t id_offset, int64_t* out_pairs, float* out_scores, int64_t out_cap,
+                           uint64_t* out_count, int32_t* out_overflowed, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    RVO_REQUIRE(db && out_pairs && out_scores && out_count && workspace, "selfjoin: null pointer");
+    RVO_REQUIRE(n_rows > 0 && d > 0 && row_lo >= 0 && row_lo <= row_hi && row_hi <= n_rows && out_cap >= 0,
+                "selfjoin: bad shape n_rows=%lld rows [%lld,%lld)", (long long)n_rows, (long long)row_lo, (long long)row_hi);
+    RVO_REQUIRE(d_pad_in == (d + kBlockK - 1) / kBlockK * kBlockK, "selfjoin: d_pad must be d rounded up to 64");
+    RVO_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)db & 15) == 0, "selfjoin: alignment");
+    RVO_REQUIRE(n_rows < (1ll << 31), "selfjoin: too many rows");
+    int sm = 0;
+    int rc = select_device_of(db, &sm);
+    if (rc) return rc;
+    return launch_selfjoin(db, n_rows, d, row_lo, row_hi, threshold, id_offset, opt_cand_cap.load(), (long long*)out_pairs,
+                           out_scores, out_cap, (unsigned long long*)out_count, out_overflowed, workspace, workspace_bytes, sm,
+                           (cudaStream_t)stream);
 }
 
 int rvo_merge_topk(const int64_t* ids, const float* scores, const int32_t* counts, int32_t G, int32_t nq, int32_t k,

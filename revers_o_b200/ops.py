@@ -204,6 +204,27 @@ def scores_dense(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, t
     return out[:nq]
 
 
+def selfjoin_threshold(db: torch.Tensor, n_rows: int, d: int, threshold: float, row_lo: int = 0, row_hi: int | None = None,
+                       out_cap: int = 1 << 22, id_offset: int = 0):
+    """Near-duplicate self-join: pairs (i, j), row_lo <= i < row_hi, i < j, cos >= threshold.  Returns device tensors
+    (pairs int64 [out_cap, 2], scores f32 [out_cap], count int64 [1], overflowed int32 [1]); async."""
+    require_cuda(db, "db")
+    assert db.dtype == torch.bfloat16 and db.dim() == 4 and db.is_contiguous()
+    row_hi = n_rows if row_hi is None else row_hi
+    dev = db.device
+    pairs = torch.empty((out_cap, 2), dtype=torch.int64, device=dev)
+    scores = torch.empty((out_cap,), dtype=torch.float32, device=dev)
+    count = torch.zeros((1,), dtype=torch.int64, device=dev)
+    over = torch.zeros((1,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    nbytes = lib.rvo_selfjoin_workspace_bytes(d)
+    ws = workspace(dev, nbytes)
+    check(lib.rvo_selfjoin_threshold(_ptr(db), n_rows, d, d_pad_of(d), int(row_lo), int(row_hi), float(threshold),
+                                     int(id_offset), _ptr(pairs), _ptr(scores), out_cap, _ptr(count), _ptr(over), _ptr(ws),
+                                     nbytes, _stream(dev)), "rvo_selfjoin_threshold")
+    return pairs, scores, count, over
+
+
 def merge_topk(ids: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor, k: int):
     """K3.  ids int64 [G,nq,k], scores f32 [G,nq,k], counts int32 [G,nq] -> merged (ids, scores, counts)."""
     require_cuda(ids, "ids")

@@ -221,6 +221,21 @@ class B200VectorDB:
             self._write_rows(c, rows, v)
             c.n = len(c.ids)
 
+    def find_near_duplicates(self, collection_name: str, threshold: float = 0.95, max_pairs: int = 1 << 22):
+        """All pairs of stored points with cosine >= threshold (BASELINE config 4: keyframe near-duplicate self-join;
+        generalises `score_threshold`, core_system.py:663).  Returns (list of (id_a, id_b), scores float32 [n])."""
+        with self._lock:
+            c = self._coll(collection_name)
+            n, vectors = c.n, c.vectors
+        if n < 2:
+            return [], np.zeros(0, np.float32)
+        pairs, scores, count, over = ops.selfjoin_threshold(vectors, n, c.dim, threshold, out_cap=max_pairs)
+        m = int(count.item())
+        if int(over.item()) > 0 or m > max_pairs:
+            raise RvoError(f"near-duplicate join overflowed ({m} pairs, {int(over.item())} candidate lists): raise max_pairs / cand_cap")
+        p = pairs[:m].cpu().numpy()
+        return [(c.ids[int(a)], c.ids[int(b)]) for a, b in p], scores[:m].cpu().numpy()
+
     def count(self, collection_name: str) -> int:
         return self._coll(collection_name).n
 

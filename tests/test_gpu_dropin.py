@@ -152,5 +152,7 @@ def test_vector_db_upsert_overwrite_and_batch(dev):
                          db_is_normalized=True)
     for i, (a, b) in enumerate(ref):
         assert np.allclose(sc[i], b, atol=1e-3)
+    dup, dsc = db.find_near_duplicates("c", 0.999)
+    assert sorted(map(sorted, dup)) == [["p3", "p7"]] and dsc[0] > 0.999
     with pytest.raises(Exception):
         db.upsert("c", [models.PointStruct(id="bad", vector=[1.0, 2.0], payload=None)])

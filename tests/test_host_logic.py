@@ -5,7 +5,7 @@ import torch
 
 from oracle import reverso_oracle as O
 from revers_o_b200.core_system import SimpleReverso, binarize_mask, mask_to_patch_grid
-from revers_o_b200.sharded import pack_results, packed_bytes, shard_bounds, unpack_results
+from revers_o_b200.sharded import pack_results, packed_bytes, selfjoin_blocks, shard_bounds, unpack_results
 
 
 def test_patch_grid_matches_oracle_rule():
@@ -31,6 +31,16 @@ def test_shard_bounds_cover_exactly():
                 sizes = [hi - lo for lo, hi in b]
                 assert max(sizes) - min(sizes) <= 128
     assert shard_bounds(100_000_000, 8, 3) == (37_500_160, 50_000_128)
+
+
+def test_selfjoin_blocks_partition_rows_and_balance_triangle():
+    n = 2_000_000
+    for w in (1, 2, 8):
+        parts = [selfjoin_blocks(n, w, r) for r in range(w)]
+        rows = sorted(x for p in parts for x in p)
+        assert rows[0][0] == 0 and rows[-1][1] == n and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        work = [sum((hi - lo) * (n - lo) for lo, hi in p) for p in parts]     # rows scanned per query block
+        assert max(work) / min(work) < 1.02
 
 
 def test_pack_unpack_roundtrip():
