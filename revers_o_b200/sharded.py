@@ -59,11 +59,15 @@ def allgather_packed(blob: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def selfjoin_blocks(n_rows: int, world: int, rank: int, block: int = 4096) -> list[tuple[int, int]]:
-    """Query-row ranges of `rank` for the self-join (DB replicated): 4096-row blocks dealt round-robin, so that the
-    triangular work (block b scans rows >= b) is balanced across ranks.  Adjacent blocks are merged."""
+    """Query-row ranges of `rank` for the self-join (DB replicated): 4096-row blocks dealt in snake order
+    (0..w-1, w-1..0, ...), so that the triangular work (block b scans rows >= b) is balanced across ranks.
+    Adjacent blocks are merged."""
     out: list[tuple[int, int]] = []
     nblk = (n_rows + block - 1) // block
-    for b in range(rank, nblk, world):
+    for b in range(nblk):
+        rnd, pos = divmod(b, world)
+        if (pos if rnd % 2 == 0 else world - 1 - pos) != rank:
+            continue
         lo, hi = b * block, min(n_rows, (b + 1) * block)
         if out and out[-1][1] == lo:
             out[-1] = (out[-1][0], hi)
