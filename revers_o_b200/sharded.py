@@ -84,22 +84,34 @@ class ShardedIndex:
         ops.require_cuda(local_db, "local_db")
         self.db, self.n_local, self.d, self.id_offset, self.group = local_db, int(n_local), int(d), int(id_offset), group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self._bufs: dict = {}
 
     def search_local(self, queries: torch.Tensor, k: int, score_threshold=None):
         return ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset)
 
     def search(self, queries: torch.Tensor, k: int, score_threshold=None):
         """queries: f32 [Q, d] on this rank's GPU (replicated).  Returns merged (ids, scores, counts)."""
-        ids, scores, counts = self.search_local(queries, k, score_threshold)
         if self.world == 1:
-            return ids, scores, counts
+            return self.search_local(queries, k, score_threshold)
         nq = queries.shape[0]
-        gathered = allgather_packed(pack_results(ids, scores, counts), self.group)
-        oi = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
-        os_ = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
-        oc = torch.empty((nq,), dtype=torch.int32, device=queries.device)
-        check(_lib.load().rvo_merge_topk_packed(gathered.data_ptr(), gathered.stride(0), self.world, nq, k, oi.data_ptr(),
-                                                os_.data_ptr(), oc.data_ptr(),
-                                                torch.cuda.current_stream(queries.device).cuda_stream),
-              "rvo_merge_topk_packed")
-        return oi, os_, oc
+        dev = queries.device
+        # K2 writes straight into the packed [ids | scores | counts] blob that the all-gather ships (no pack kernels)
+        key = (nq, k)
+        if self._bufs.get("key") != key:
+            nb = packed_bytes(nq, k)
+            self._bufs = {"key": key, "blob": torch.zeros(nb, dtype=torch.uint8, device=dev),
+                          "gathered": torch.empty((self.world, nb), dtype=torch.uint8, device=dev),
+                          "oi": torch.empty((nq, k), dtype=torch.int64, device=dev),
+                          "os": torch.empty((nq, k), dtype=torch.float32, device=dev),
+                          "oc": torch.empty((nq,), dtype=torch.int32, device=dev)}
+        b = self._bufs
+        blob = b["blob"]
+        ids = blob[: nq * k * 8].view(torch.int64).view(nq, k)
+        scores = blob[nq * k * 8: nq * k * 12].view(torch.float32).view(nq, k)
+        counts = blob[nq * k * 12: nq * k * 12 + nq * 4].view(torch.int32)
+        ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset, out=(ids, scores, counts))
+        dist.all_gather_into_tensor(b["gathered"].view(-1), blob, group=self.group)   # the ONE collective of the path
+        check(_lib.load().rvo_merge_topk_packed(b["gathered"].data_ptr(), b["gathered"].stride(0), self.world, nq, k,
+                                                b["oi"].data_ptr(), b["os"].data_ptr(), b["oc"].data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream), "rvo_merge_topk_packed")
+        return b["oi"], b["os"], b["oc"]
