@@ -69,6 +69,9 @@ def test_dense_scores_match_fp32_reference(dev, n, d, nq, stride):
     (120_000, 1024, 256, 100),  # config 1 shape at reduced N
     (70_000, 1280, 300, 50),    # two query blocks
     (33_333, 2048, 40, 7),
+    (50_000, 64, 40, 512),      # maximum k, one k-chunk
+    (300_000, 128, 1000, 10),   # four query blocks on CTA pairs
+    (20_000, 1280, 130, 100),   # PE-Core-G14 width, odd query count
 ])
 def test_search_matches_oracle(dev, n, d, nq, k):
     from revers_o_b200 import synth
