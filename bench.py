@@ -37,10 +37,13 @@ WORKLOADS = {
     # name: (rows, dim, queries, k, description)
     "cfg0": (10_000, 1024, 1, 10, "configs[0]: 10k x 1024, single query, top-10"),
     "cfg1": (1_000_000, 1024, 256, 100, "configs[1]: 1M x 1024 bf16 DB, 256-query batch, top-100, fp32 rescore"),
+    "cfg3": (100_000_000, 1280, 4096, 100, "configs[3]: 100M x 1280 bf16 DB row-sharded over the ranks, 4096-query batch, top-100, NCCL top-k merge"),
+    "cfg3q64": (100_000_000, 1280, 64, 100, "configs[3] DB, bandwidth regime: 100M x 1280 row-sharded, 64 queries"),
+    "cfg3q16": (100_000_000, 1280, 16, 100, "configs[3] DB, bandwidth regime: 100M x 1280 row-sharded, 16 queries"),
     "cfg3shard": (12_500_000, 1280, 4096, 100, "configs[3] per-GPU shard: 12.5M x 1280 bf16, 4096-query batch, top-100"),
-    "cfg3small": (12_500_000, 1280, 16, 100, "configs[3] per-GPU shard, bandwidth regime: 12.5M x 1280, 16 queries"),
-    "cfg3q64": (12_500_000, 1280, 64, 100, "configs[3] per-GPU shard, bandwidth regime: 12.5M x 1280, 64 queries"),
-    "cfg3q1": (12_500_000, 1280, 1, 100, "configs[3] per-GPU shard, the reference's operating point: 12.5M x 1280, 1 query"),
+    "cfg3shardq16": (12_500_000, 1280, 16, 100, "configs[3] per-GPU shard, bandwidth regime: 12.5M x 1280, 16 queries"),
+    "cfg3shardq64": (12_500_000, 1280, 64, 100, "configs[3] per-GPU shard, bandwidth regime: 12.5M x 1280, 64 queries"),
+    "cfg3shardq1": (12_500_000, 1280, 1, 100, "configs[3] per-GPU shard, the reference's operating point: 12.5M x 1280, 1 query"),
     "cfg1q1": (1_000_000, 1024, 1, 10, "configs[1] DB, the reference's operating point: 1M x 1024, 1 query, top-10"),
 }
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
@@ -193,6 +196,9 @@ def run_b200(args):
     n, d, nq, k, desc = WORKLOADS[args.workload]
     lo, hi = shard_bounds(n, world, rank)
     n_local = hi - lo
+    if n_local * d * 2 > 150e9:
+        raise SystemExit(f"bench.py: workload {args.workload} needs {n_local * d * 2 / 1e9:.0f} GB per GPU at {world} GPU(s); "
+                         "launch it on more ranks")
     q_dev = synth.make_queries(nq, d, seed=7, device=dev)
     db = synth.make_db(n_local, d, q_dev, n_plant=max(1, 128 // world), seed=1000 + rank, device=dev)
     index = ShardedIndex(db, n_local, d, lo)
@@ -200,69 +206,85 @@ def run_b200(args):
     for kv in filter(None, os.environ.get("RVO_OPTS", "").split(",")):  # tuning sweeps only (scripts/gpu_sweep.sh)
         name, val = kv.split("=")
         _lib.set_option(name.strip(), int(val))
+    peaks, peaks_kind = load_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        return index.search(q_dev, k)
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step_fn, steps, warm):
+        """`warm` untimed + exactly `steps` timed calls, CUDA events on the launching stream, barrier + synchronize
+        on both sides, max over ranks.  Returns (ms per step, library kernel launches, last result)."""
+        for _ in range(warm):
+            out = step_fn()
+        barrier()
+        l0 = _lib.kernel_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            out = step_fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, _lib.kernel_launch_count() - l0, out
+
+    def scan_rooflines(idx, q, kk, ms_step, reps):
+        """The dominant kernel (full-shard scan) timed alone with CUDA events recorded by the library around that one
+        launch on its stream; algorithmic bytes = n_local*d*2 (DB read once), flops = 2*Q*n_local*d."""
+        _lib.set_option("time_scan", 1)
+        scan_ms = []
+        for _ in range(reps):
+            idx.search_local(q, kk)
+            scan_ms.append(float(lib.rvo_last_scan_ms()))
+        _lib.set_option("time_scan", 0)
+        torch.cuda.synchronize()
+        scan_avg = max_over_ranks(statistics.mean(scan_ms))
+        nq_ = q.shape[0]
+        alg_bytes = idx.n_local * idx.d * 2
+        alg_flops = 2.0 * nq_ * idx.n_local * idx.d
+        hbm_ach = alg_bytes / (scan_avg * 1e-3) / 1e9
+        tf_ach = alg_flops / (scan_avg * 1e-3) / 1e12
+        small_ = nq_ <= _lib.RVO_SMALL_Q
+        hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+               "frac": hbm_ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peaks_kind,
+               "kernel": "scan_small_kernel" if small_ else "scan_tc_kernel<FILTER> (full-DB level)",
+               "kernel_ms": scan_avg, "algorithmic_bytes": alg_bytes, "share_of_step": scan_avg / ms_step}
+        tensor = None if small_ else {
+            "bound": "tensor", "achieved": tf_ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": tf_ach / peaks["bf16_tflops"], "peak_kind": peaks_kind + " burst (kernel timed alone)",
+            "kernel": "scan_tc_kernel<FILTER> (full-DB level)", "kernel_ms": scan_avg,
+            "algorithmic_flops": alg_flops, "share_of_step": scan_avg / ms_step}
+        return hbm, tensor
 
     # ---- value: inputs resident in HBM --------------------------------------------------------------
     sampler = ClockSampler(local)
-    for _ in range(max(3, args.warmup)):
-        out = step_resident()
-    barrier()
     sampler.start()
-    l0 = _lib.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = step_resident()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = _lib.kernel_launch_count() - l0
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step, launches, out = timed(lambda: index.search(q_dev, k), args.steps, max(3, args.warmup))
     value = nq / (ms_step / 1e3)
     counts_ok = bool((out[2] == k).all().item())
 
-    # ---- roofline: the dominant kernel (full-shard scan), CUDA events around that one launch ---------
-    _lib.set_option("time_scan", 1)
-    scan_ms = []
-    for _ in range(max(5, min(args.steps, 30))):
-        index.search_local(q_dev, k)
-        scan_ms.append(float(lib.rvo_last_scan_ms()))
-    _lib.set_option("time_scan", 0)
-    torch.cuda.synchronize()
-    scan_avg = statistics.mean(scan_ms)
-    peaks, peaks_kind = load_peaks()
-    alg_bytes = n_local * d * 2
-    alg_flops = 2.0 * nq * n_local * d
-    hbm_ach = alg_bytes / (scan_avg * 1e-3) / 1e9
-    tf_ach = alg_flops / (scan_avg * 1e-3) / 1e12
+    # ---- roofline: the dominant kernel (full-shard scan) ------------------------------------------------
+    roofline, roofline_tensor = scan_rooflines(index, q_dev, k, ms_step, max(5, min(args.steps, 30)))
     small = nq <= _lib.RVO_SMALL_Q
-    traffic = None
+    alg_bytes = n_local * d * 2
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            roofline["traffic"] = json.load(open(tp)).get(args.workload)
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": hbm_ach / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peaks_kind,
-                "kernel": "scan_small_kernel" if small else "scan_tc_kernel<FILTER> (full-DB level)",
-                "kernel_ms": scan_avg, "algorithmic_bytes": alg_bytes,
-                "share_of_step": scan_avg / ms_step}
-    roofline_tensor = None if small else {
-        "bound": "tensor", "achieved": tf_ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": tf_ach / peaks["bf16_tflops"], "peak_kind": peaks_kind + " burst (kernel timed alone)",
-        "algorithmic_flops": alg_flops}
+            pass
+    if roofline_tensor is not None and nq >= 1024:     # tensor-bound regime: the tensor roofline is the binding one
+        roofline_tensor["traffic"] = roofline["traffic"]
+        roofline, roofline_hbm = roofline_tensor, roofline
+    else:
+        roofline_hbm = None
 
     # ---- e2e: public API with HOST buffers (N=1: B200VectorDB.search_batch; N>1: H2D + sharded search + D2H) --
     q_host = q_dev.cpu().numpy()
@@ -289,19 +311,35 @@ def run_b200(args):
             pi.copy_(a, non_blocking=True); ps.copy_(b, non_blocking=True); pc.copy_(c_, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return pi, ps, pc
-    for _ in range(max(3, args.warmup)):
-        step_e2e()
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        r = step_e2e()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / args.steps
+    e2e_ms, _, _ = timed(step_e2e, args.steps, max(3, args.warmup))
     clocks = sampler.stop()
+
+    # ---- north star series (BASELINE.json metric: 100M x 1280 at 1/2/4/8 GPUs): the 100M x 1280 DB does not fit
+    # one GPU, so every rank holds ITS 12.5M-row shard of the 8-GPU layout (weak scaling: N = 8 IS configs[3]) ----
+    north = None
+    if args.workload == "cfg1" and not args.no_north_star:
+        del index, db
+        if world == 1:
+            del vdb, c
+        torch.cuda.empty_cache()
+        north = {"workload": f"configs[3] shard layout: 12.5M x 1280 bf16 rows per GPU x {world} GPU(s) = "
+                             f"{12.5 * world:.1f}M rows total, top-100, all-gather + K3 merge when N > 1",
+                 "scaling": "weak", "rows_per_gpu": 12_500_000, "rows_total": 12_500_000 * world, "dim": 1280, "points": []}
+        ns_n, ns_d = 12_500_000, 1280
+        q_all = synth.make_queries(4096, ns_d, seed=7, device=dev)
+        ns_db = synth.make_db(ns_n, ns_d, q_all, n_plant=16, seed=2000 + rank, device=dev)
+        ns_index = ShardedIndex(ns_db, ns_n, ns_d, rank * ns_n)
+        for ns_q in (4096, 64, 16):
+            qd_ = q_all[:ns_q].contiguous()
+            ns_steps = 5 if ns_q >= 1024 else 10
+            ns_ms, _, ns_out = timed(lambda: ns_index.search(qd_, 100), ns_steps, 3)
+            r_h, r_t = scan_rooflines(ns_index, qd_, 100, ns_ms, 3)
+            north["points"].append({
+                "queries": ns_q, "value": ns_q / (ns_ms / 1e3), "unit": "queries/s", "ms_per_step": ns_ms, "steps": ns_steps,
+                "results_ok": bool((ns_out[2] == 100).all().item()),
+                "roofline": r_t if ns_q >= 1024 else r_h})
+        del ns_db, ns_index
+        torch.cuda.empty_cache()
 
     # ---- cpu baseline (rank 0, N=1): the oracle port in a numpy-only subprocess, bounded sample ----------
     cpu = None
@@ -327,7 +365,8 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "api": "B200VectorDB.search_batch(host numpy)" if world == 1 else "pinned H2D + ShardedIndex.search + D2H"},
             "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_tensor": roofline_tensor, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_hbm": roofline_hbm,
+            "north_star": north, "cpu_baseline": cpu, "clocks": clocks,
             "results_ok": counts_ok,
         }
         print(json.dumps(line), flush=True)
@@ -346,6 +385,7 @@ def main():
     ap.add_argument("--sample-queries", type=int, default=8, help="queries per CPU step (bounded sample)")
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the 12.5M x 1280 rows/GPU north-star series")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -159,6 +159,7 @@ struct SearchPlan {
     float* qn;
     uint16_t* qb;
     float* tau;       // [n_levels+1][nq_pad]
+    float* margin;    // [nq_pad] per-query admission margin (common.cuh query_margin)
     int* cnt;         // [n_levels+1][nq_pad]
     unsigned long long* cand;
     float* dense;
@@ -229,6 +230,7 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
         sp->zero_bytes = ar.off - sp->zero_off;
         sp->qn = ar.take<float>((size_t)nq * sp->d_pad, 1024);
         sp->tau = ar.take<float>((size_t)(sp->n_levels + 1) * nq_pad);
+        sp->margin = ar.take<float>((size_t)nq_pad);
         sp->dense_ld = (sp->seed_cols + 63) / 64 * 64;
         sp->dense = ar.take<float>((size_t)nq_pad * (size_t)sp->dense_ld);
         if (sp->n_levels > 0) sp->cand = ar.take<unsigned long long>((size_t)nq_pad * kCandSplit * (size_t)sp->cap);
@@ -245,7 +247,8 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
 
 static int prep_queries(const SearchPlan& sp, const float* queries, int nq, int d, void* ws, cudaStream_t stream) {
     RVO_CUDA(cudaMemsetAsync((char*)ws + sp.zero_off, 0, sp.zero_bytes, stream));
-    return launch_normalize_rows(queries, nq, d, d, sp.small ? nullptr : sp.qb, sp.d_pad, -1, sp.qn, sp.d_pad, stream);
+    return launch_normalize_rows(queries, nq, d, d, sp.small ? nullptr : sp.qb, sp.d_pad, -1, sp.qn, sp.d_pad, stream,
+                                 sp.small ? nullptr : sp.margin);
 }
 
 }  // namespace rvo
@@ -393,19 +396,19 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
         fa.top = top;
         fa.top_ld = top_ld;
         fa.rescore = 0;
-        fa.margin = 0.f;
+        fa.margin = nullptr;
         return launch_final(fa, nq, stream);
     }
 
     const int nq_pad = sp.tc.nq_pad;
-    const float margin = kBf16QueryMargin;
-    const float floor_t = score_threshold - margin;  // -inf stays -inf
+    fa.rescore = 1;
+    fa.margin = sp.margin;
 
     SelectArgs sa;
     memset(&sa, 0, sizeof(sa));
     sa.nq = nq;
-    sa.tau_margin = margin;
-    sa.tau_floor = floor_t;
+    sa.margin = sp.margin;
+    sa.score_floor = score_threshold;   // nothing below score_threshold - margin is ever queued (-inf stays -inf)
     sa.tau_k = k;
 
     // level 0: DENSE pass over the seed sample (or the whole shard when it is small)
@@ -416,18 +419,9 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
     sa.dense_ld = sp.dense_ld;
     sa.n_dense = sp.seed_cols;
     if (sp.n_levels == 0) {
-        // the sample IS the shard (dense column == row): exact top-K2 by tensor score, then fp32 re-score
+        // the sample IS the shard (dense column == row): exact candidates by tensor score, fp32 re-score, final order
         sa.K = sp.K2;
-        sa.out = sp.bufA;
-        sa.out_ld = sp.K2;
-        rc = launch_select(sa, nq, stream);
-        if (rc) return rc;
-        fa.top = sp.bufA;
-        fa.top_ld = sp.K2;
-        fa.rescore = 1;
-        fa.margin = margin;
-        fa.cnt = nullptr;
-        return launch_final(fa, nq, stream);
+        return launch_select_final(sa, fa, nq, stream);
     }
     sa.K = k;
     sa.tau_out = sp.tau;
@@ -451,29 +445,19 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
         sa.cnt = cnt;
         sa.nseg = kCandSplit;
         sa.cap = sp.cap;
+        sa.margin = sp.margin;
+        sa.score_floor = score_threshold;
         if (!last) {
             sa.K = k;
             sa.tau_out = sp.tau + (size_t)(L + 1) * nq_pad;
             sa.tau_prev = tau_in;
             sa.tau_k = k;
-            sa.tau_margin = margin;
-            sa.tau_floor = floor_t;
             rc = launch_select(sa, nq_pad, stream);
             if (rc) return rc;
         } else {
+            // last level: exact candidate selection fused with the fp32 re-score and the final ordering
             sa.K = sp.K2;
-            sa.out = sp.bufA;
-            sa.out_ld = sp.K2;
-            rc = launch_select(sa, nq, stream);
-            if (rc) return rc;
-            fa.top = sp.bufA;
-            fa.top_ld = sp.K2;
-            fa.rescore = 1;
-            fa.margin = margin;
-            fa.cnt = cnt;
-            fa.nseg = kCandSplit;
-            fa.cap = sp.cap;
-            rc = launch_final(fa, nq, stream);
+            rc = launch_select_final(sa, fa, nq, stream);
             if (rc) return rc;
         }
     }

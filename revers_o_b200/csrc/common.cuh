@@ -98,11 +98,18 @@ __host__ __device__ __forceinline__ size_t tiled_offset(long long row, int col, 
            (size_t)(row & 127) * kTileCols + (size_t)(col & 63);
 }
 
-// eps = 2^-8 bounds |<bf16(q),d> - <q,d>| for unit q, |d| <= 1 (||q - bf16(q)|| <= 2^-8 ||q||).
-// If t(k) is the k-th best TENSOR score of any subset, every item of the true top-k (ranked by the
-// fp32 re-score f) has f >= t(k) - eps, hence tensor score >= t(k) - 2 eps.  Thresholds taken from
-// tensor-core scores are therefore lowered by 2 eps (+ fp32 accumulation slack) so that no true
-// top-k item can be filtered out.
-constexpr float kBf16QueryMargin = 0.008f;
+// Admission margin of a query whose MMA operand is bf16(q_hat) while the final ranking uses the fp32 re-score
+// f = <q_hat, d>.  DB rows are L2-normalised bf16 values (||d|| <= 1 + 2^-8), so
+//     |<bf16(q_hat), d> - <q_hat, d>|  <=  ||bf16(q_hat) - q_hat|| * ||d||  =: eps_q      (Cauchy-Schwarz),
+// with ||bf16(q_hat) - q_hat|| MEASURED per query by the normalise kernel (about 1.7e-3 for random directions, 2.3x
+// below the worst case 2^-8).  If t(k) is the k-th best TENSOR score of any subset of the DB, k rows have tensor score >= t(k),
+// hence f >= t(k) - eps_q; so the k-th best f is >= t(k) - eps_q, and every row of the true top-k has tensor score
+// >= t(k) - 2 eps_q.  Thresholds taken from tensor-core scores are therefore lowered by margin = 2 eps_q, where eps_q
+// also carries 2^-13 of slack for fp32 accumulation-order differences between tile shapes and the fp32 FMA re-score.
+__host__ __device__ __forceinline__ float query_margin(float bf16_err_norm) {
+    return 2.0f * (bf16_err_norm * (1.0f + 0.00390625f) + 0.0001220703125f);
+}
+// worst case of query_margin (||bf16(q)-q|| <= 2^-8 ||q||): used where no per-query value exists
+constexpr float kBf16QueryMargin = 0.0082f;
 
 }  // namespace rvo

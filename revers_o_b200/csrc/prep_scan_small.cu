@@ -13,7 +13,8 @@ namespace rvo {
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ src, long long n, int d,
                                                              long long src_ld, uint16_t* __restrict__ dst_bf16,
                                                              long long dst_ld, long long tiled_row0,
-                                                             float* __restrict__ dst_f32, long long f32_ld) {
+                                                             float* __restrict__ dst_f32, long long f32_ld,
+                                                             float* __restrict__ margin_out) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -30,9 +31,18 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
     if (dst_bf16) {
         if (tiled_row0 < 0) {
             uint16_t* o = dst_bf16 + (size_t)row * (size_t)dst_ld;
+            float e2 = 0.f;  // ||bf16(q_hat) - q_hat||^2: the exact rounding error of THIS query operand
             for (long long i = lane; i < dst_ld; i += 32) {
                 const float v = i < d ? s[i] * inv : 0.f;
-                o[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+                const __nv_bfloat16 b = __float2bfloat16_rn(v);
+                const float e = __bfloat162float(b) - v;
+                e2 = fmaf(e, e, e2);
+                o[i] = __bfloat16_as_ushort(b);
+            }
+            if (margin_out) {
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) e2 += __shfl_xor_sync(0xFFFFFFFFu, e2, o2);
+                if (lane == 0) margin_out[row] = query_margin(sqrtf(e2));
             }
         } else {
             const int nk = (int)(dst_ld / kTileCols);
@@ -49,11 +59,12 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
 }
 
 int launch_normalize_rows(const float* src, long long n, int d, long long src_ld, uint16_t* dst_bf16, long long dst_ld,
-                          long long tiled_row0, float* dst_f32, long long f32_ld, cudaStream_t stream) {
+                          long long tiled_row0, float* dst_f32, long long f32_ld, cudaStream_t stream,
+                          float* margin_out) {
     if (n <= 0) return RVO_OK;
     const long long blocks = (n + 7) / 8;
     normalize_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, n, d, src_ld, dst_bf16, dst_ld, tiled_row0, dst_f32,
-                                                                f32_ld);
+                                                                f32_ld, margin_out);
     RVO_LAUNCHED();
     return RVO_OK;
 }

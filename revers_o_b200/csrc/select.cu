@@ -75,7 +75,76 @@ __global__ void __launch_bounds__(kSelThreads) chunk_topk_kernel(const ChunkTopk
     }
 }
 
-// grid (nq), 512 threads.  `top` holds the K2 best candidates of the query by tensor-core score.
+// fp32 re-score of the candidates s[0..have) whose tensor score can still reach the top-k (score >= cut): 8 lanes
+// per candidate (four candidates per warp in flight, 16 independent 16-byte loads per lane for d = 1024), fp32
+// query (normalised) x bf16 DB row, fp32 FMA, then a 3-step shuffle reduction inside the 8-lane group.  Candidates
+// below the cut become empty keys.  Whole block; the caller synchronises afterwards.
+__device__ __forceinline__ void rescore_candidates(unsigned long long* s, int have, float cut, const uint16_t* db, int d_pad,
+                                                   const float* qv) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int g = lane >> 3, l8 = lane & 7;
+    const int nchunk = d_pad >> 3;
+    const int ntk = d_pad / kTileCols;
+    const uint4* base = (const uint4*)db;  // tiled DB storage: 16-byte chunk c of a row lives in tile (row/128, c/8)
+    for (int e0 = 0; e0 < have; e0 += nwarps * 4) {
+        const int e = e0 + warp * 4 + g;
+        const unsigned long long key = e < have ? s[e] : 0ull;
+        const bool active = key != 0ull && key_score(key) >= cut;
+        const uint32_t row = key_row(key);
+        float acc = 0.f;
+        if (active) {
+            const uint4* r = base + ((size_t)(row >> 7) * ntk * kTileRows + (row & 127)) * 8;
+            for (int c = l8; c < nchunk; c += 8) {
+                const uint4 v = __ldg(r + (size_t)(c >> 3) * kTileRows * 8 + (c & 7));
+                const float4 q0 = __ldg((const float4*)(qv + c * 8));
+                const float4 q1 = __ldg((const float4*)(qv + c * 8 + 4));
+                acc = fmaf(__uint_as_float(v.x << 16), q0.x, acc);
+                acc = fmaf(__uint_as_float(v.x & 0xFFFF0000u), q0.y, acc);
+                acc = fmaf(__uint_as_float(v.y << 16), q0.z, acc);
+                acc = fmaf(__uint_as_float(v.y & 0xFFFF0000u), q0.w, acc);
+                acc = fmaf(__uint_as_float(v.z << 16), q1.x, acc);
+                acc = fmaf(__uint_as_float(v.z & 0xFFFF0000u), q1.y, acc);
+                acc = fmaf(__uint_as_float(v.w << 16), q1.z, acc);
+                acc = fmaf(__uint_as_float(v.w & 0xFFFF0000u), q1.w, acc);
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        __syncwarp();
+        if (l8 == 0 && e < have) s[e] = active ? make_key(acc, row) : 0ull;
+    }
+}
+
+// emit: first k keys of the sorted list with score >= score_threshold (the reference's walk stops at the first score
+// below it; `score == threshold` is kept).  s_n must be 0 on entry; whole block.
+__device__ __forceinline__ void emit_topk(const unsigned long long* s, int n_sorted, const FinalArgs& a, int q, int* s_n) {
+    int64_t* oid = a.out_ids + (size_t)q * (size_t)a.k;
+    float* osc = a.out_scores + (size_t)q * (size_t)a.k;
+    int n_out_local = 0;
+    for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
+        const unsigned long long key = i < n_sorted ? s[i] : 0ull;
+        const bool ok = key != 0ull && key_score(key) >= a.score_threshold;
+        oid[i] = ok ? (int64_t)key_row(key) + a.id_offset : -1;
+        osc[i] = ok ? key_score(key) : -__int_as_float(0x7f800000);
+        n_out_local += ok;
+    }
+    if (n_out_local) atomicAdd(s_n, n_out_local);
+    __syncthreads();
+    if (threadIdx.x == 0) a.out_counts[q] = *s_n;
+}
+
+__device__ __forceinline__ void emit_overflow(const FinalArgs& a, int q) {
+    int64_t* oid = a.out_ids + (size_t)q * (size_t)a.k;
+    float* osc = a.out_scores + (size_t)q * (size_t)a.k;
+    for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
+        oid[i] = -1;
+        osc[i] = -__int_as_float(0x7f800000);
+    }
+    if (threadIdx.x == 0) a.out_counts[q] = -1;
+}
+
+// grid (nq), 512 threads.  `top` holds the K2 best candidates of the query, sorted descending (small-Q path: exact fp32
+// scores, rescore == 0; kept general for lists of tensor scores).
 __global__ void __launch_bounds__(512) final_kernel(const FinalArgs a) {
     __shared__ unsigned long long s[1024];
     __shared__ int s_flag;
@@ -99,9 +168,6 @@ __global__ void __launch_bounds__(512) final_kernel(const FinalArgs a) {
     __syncthreads();
     const int have = s_have;
 
-    int64_t* oid = a.out_ids + (size_t)q * (size_t)a.k;
-    float* osc = a.out_scores + (size_t)q * (size_t)a.k;
-
     bool overflow = false;
     int raw = have;
     if (a.cnt) {
@@ -114,73 +180,21 @@ __global__ void __launch_bounds__(512) final_kernel(const FinalArgs a) {
     }
     float cut = -__int_as_float(0x7f800000);
     if (a.rescore && have >= a.k) {
-        cut = key_score(s[a.k - 1]) - a.margin;
+        cut = key_score(s[a.k - 1]) - (a.margin ? a.margin[q] : 0.f);
         // K2 list is full, more survivors exist, and the worst kept one is still inside the margin:
         // a survivor we did not keep could out-rank a kept one after the fp32 re-score.
         if (have == K2 && raw > K2 && key_score(s[K2 - 1]) >= cut) overflow = true;
     }
     if (overflow) {
-        for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
-            oid[i] = -1;
-            osc[i] = -__int_as_float(0x7f800000);
-        }
-        if (threadIdx.x == 0) a.out_counts[q] = -1;
+        emit_overflow(a, q);
         return;
     }
-
     if (a.rescore) {
-        // fp32 re-score of every kept candidate that can still reach the top-k: 8 lanes per candidate (four
-        // candidates per warp in flight, 16 independent 16-byte loads per lane for d = 1024), fp32 query
-        // (normalised) x bf16 DB row, fp32 FMA, then a 3-step shuffle reduction inside the 8-lane group.
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-        const int g = lane >> 3, l8 = lane & 7;
-        const int nchunk = a.d_pad >> 3;
-        const int ntk = a.d_pad / kTileCols;
-        const float* qv = a.qn + (size_t)q * (size_t)a.qn_ld;
-        const uint4* base = (const uint4*)a.db;  // tiled DB storage: 16-byte chunk c of a row lives in tile (row/128, c/8)
-        for (int e0 = 0; e0 < have; e0 += nwarps * 4) {
-            const int e = e0 + warp * 4 + g;
-            const unsigned long long key = e < have ? s[e] : 0ull;
-            const bool active = key != 0ull && key_score(key) >= cut;
-            const uint32_t row = key_row(key);
-            float acc = 0.f;
-            if (active) {
-                const uint4* r = base + ((size_t)(row >> 7) * ntk * kTileRows + (row & 127)) * 8;
-                for (int c = l8; c < nchunk; c += 8) {
-                    const uint4 v = __ldg(r + (size_t)(c >> 3) * kTileRows * 8 + (c & 7));
-                    const float4 q0 = __ldg((const float4*)(qv + c * 8));
-                    const float4 q1 = __ldg((const float4*)(qv + c * 8 + 4));
-                    acc = fmaf(__uint_as_float(v.x << 16), q0.x, acc);
-                    acc = fmaf(__uint_as_float(v.x & 0xFFFF0000u), q0.y, acc);
-                    acc = fmaf(__uint_as_float(v.y << 16), q0.z, acc);
-                    acc = fmaf(__uint_as_float(v.y & 0xFFFF0000u), q0.w, acc);
-                    acc = fmaf(__uint_as_float(v.z << 16), q1.x, acc);
-                    acc = fmaf(__uint_as_float(v.z & 0xFFFF0000u), q1.y, acc);
-                    acc = fmaf(__uint_as_float(v.w << 16), q1.z, acc);
-                    acc = fmaf(__uint_as_float(v.w & 0xFFFF0000u), q1.w, acc);
-                }
-            }
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-            __syncwarp();
-            if (l8 == 0 && e < have) s[e] = active ? make_key(acc, row) : 0ull;
-        }
+        rescore_candidates(s, have, cut, a.db, a.d_pad, a.qn + (size_t)q * (size_t)a.qn_ld);
         __syncthreads();
         bitonic_desc_u64(s, K2);
     }
-
-    // emit: first k keys with score >= score_threshold (the walk stops at the first score below it)
-    int n_out_local = 0;
-    for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
-        const unsigned long long key = i < K2 ? s[i] : 0ull;
-        const bool ok = key != 0ull && key_score(key) >= a.score_threshold;
-        oid[i] = ok ? (int64_t)key_row(key) + a.id_offset : -1;
-        osc[i] = ok ? key_score(key) : -__int_as_float(0x7f800000);
-        n_out_local += ok;
-    }
-    if (n_out_local) atomicAdd(&s_flag, n_out_local);
-    __syncthreads();
-    if (threadIdx.x == 0) a.out_counts[q] = s_flag;
+    emit_topk(s, K2, a, q, &s_flag);
 }
 
 // ---- exact top-K of one query's candidates by histogram refinement ---------------------------------
@@ -266,12 +280,13 @@ __device__ __forceinline__ void hist_find(const int* hist, int need, int lane, i
     }
 }
 
-__global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs a) {
+template <bool FINAL>
+__global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs a, const FinalArgs f) {
     __shared__ int hist[kSelBins];
     __shared__ unsigned long long sbuf[kSelSort];
     __shared__ unsigned long long s_red[2 * (kSelThreads / 32)];
     __shared__ unsigned long long s_lo, s_hi, s_min;
-    __shared__ int s_above, s_count, s_done, s_cnt[32], s_res[4];
+    __shared__ int s_above, s_count, s_done, s_cnt[32], s_res[4], s_over;
     const int q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float INF = __int_as_float(0x7f800000);
@@ -279,11 +294,18 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
         if (a.tau_out && tid == 0) a.tau_out[q] = INF;
         return;
     }
+    if (tid == 0) s_over = 0;
+    __syncthreads();
     if (!a.dense && tid < a.nseg) {
         const int c = a.cnt[q * a.nseg + tid];
         s_cnt[tid] = c < a.cap ? c : a.cap;
+        if (c > a.cap) s_over = 1;   // a sub-list dropped candidates
     }
     __syncthreads();
+    if (FINAL && s_over) {
+        emit_overflow(f, q);
+        return;
+    }
 
     // number of keys (dense: sample columns, the few -inf pads of the last tile included) and the key range
     if (tid == 0) {
@@ -316,6 +338,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
     };
 
     bool fast = false;
+    unsigned long long T_used = 0ull;   // sbuf holds every key >= T_used (unless s_count > kSelSort)
     if (s_done) {
         compact(0ull);
         fast = true;
@@ -343,6 +366,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
         // one compaction pass with the proposed bound; exact whenever it kept between `want` and kSelSort keys
         const unsigned long long T0 = s_lo;
         compact(T0);
+        T_used = T0;
         fast = s_count >= want && s_count <= kSelSort;
     }
 
@@ -404,12 +428,53 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
         }
         const unsigned long long T1 = s_lo;
         compact(T1);
+        T_used = T1;
     }
-    const int C = s_count < kSelSort ? s_count : kSelSort;
-    const int ns = next_pow2(C > 2 ? C : 2);
+    int C = s_count < kSelSort ? s_count : kSelSort;
+    int ns = next_pow2(C > 2 ? C : 2);
     for (int i = C + tid; i < ns; i += blockDim.x) sbuf[i] = 0ull;
     __syncthreads();
     bitonic_desc_u64(sbuf, ns);
+
+    if constexpr (FINAL) {
+        // ---- fused last level: every candidate that can still reach the top-k after the fp32 re-score is one whose
+        // tensor score lies within the query's margin of the k-th best tensor score (common.cuh) ----
+        const float NINF = -INF;
+        const float m = f.margin ? f.margin[q] : 0.f;
+        const float cut = C >= f.k ? key_score(sbuf[f.k - 1]) - m : NINF;
+        // sbuf holds every key >= T (none was dropped if s_count <= kSelSort); keys with score >= cut are >= Kc
+        const unsigned long long T = T_used;
+        const unsigned long long Kc = cut == NINF ? 0ull : (unsigned long long)f32_orderable(cut) << 32;
+        const bool covered = s_count <= kSelSort && (T <= Kc || C == nnz);
+        if (!covered) {
+            compact(Kc);                                  // a superset of the k best: the cut stays valid
+            if (s_count > kSelSort) {                     // more than kSelSort candidates inside the margin
+                emit_overflow(f, q);
+                return;
+            }
+            C = s_count;
+            ns = next_pow2(C > 2 ? C : 2);
+            for (int i = C + tid; i < ns; i += blockDim.x) sbuf[i] = 0ull;
+            __syncthreads();
+            bitonic_desc_u64(sbuf, ns);
+        }
+        // the candidates at or above the cut are a prefix of the sorted list
+        if (tid == 0) s_above = 0;
+        __syncthreads();
+        int mine = 0;
+        for (int i = tid; i < C; i += blockDim.x) mine += key_score(sbuf[i]) >= cut;
+        if (mine) atomicAdd(&s_above, mine);
+        __syncthreads();
+        const int n_act = s_above;
+        rescore_candidates(sbuf, n_act, cut, f.db, f.d_pad, f.qn + (size_t)q * (size_t)f.qn_ld);
+        const int ns2 = next_pow2(n_act > 2 ? n_act : 2);
+        for (int i = n_act + tid; i < ns2; i += blockDim.x) sbuf[i] = 0ull;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        bitonic_desc_u64(sbuf, ns2);
+        emit_topk(sbuf, ns2, f, q, &s_count);
+        return;
+    }
 
     if (a.out) {
         unsigned long long* out = a.out + (size_t)q * (size_t)a.out_ld;
@@ -418,11 +483,12 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
     // The k-th best of ANY subset of the DB is a lower bound of the k-th best of the whole DB, so
     // admitting `score >= tau` in the next scan level never drops a true top-k item.
     if (a.tau_out && tid == 0) {
-        float t = a.tau_floor;
+        const float m = a.margin ? a.margin[q] : kBf16QueryMargin;
+        float t = a.score_floor - m;
         if (a.tau_prev && a.tau_prev[q] > t) t = a.tau_prev[q];
         const unsigned long long key = (a.tau_k - 1) < C ? sbuf[a.tau_k - 1] : 0ull;
         if (key) {
-            const float c = key_score(key) - a.tau_margin;
+            const float c = key_score(key) - m;
             if (c > t) t = c;
         }
         a.tau_out[q] = t;
@@ -431,7 +497,16 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
 
 int launch_select(const SelectArgs& a, int grid_q, cudaStream_t stream) {
     if (grid_q <= 0) return RVO_OK;
-    select_kernel<<<grid_q, kSelThreads, 0, stream>>>(a);
+    FinalArgs f;
+    memset(&f, 0, sizeof(f));
+    select_kernel<false><<<grid_q, kSelThreads, 0, stream>>>(a, f);
+    RVO_LAUNCHED();
+    return RVO_OK;
+}
+
+int launch_select_final(const SelectArgs& a, const FinalArgs& f, int nq, cudaStream_t stream) {
+    if (nq <= 0) return RVO_OK;
+    select_kernel<true><<<nq, kSelThreads, 0, stream>>>(a, f);
     RVO_LAUNCHED();
     return RVO_OK;
 }

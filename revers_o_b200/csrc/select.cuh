@@ -39,10 +39,11 @@ struct SelectArgs {
     int K;                              // top keys wanted (<= 1024)
     unsigned long long* out;            // [nq][out_ld] top-K keys, sorted descending, zero padded (or nullptr)
     long long out_ld;
-    float* tau_out;                     // optional: tau_out[q] = max(tau_prev[q], score(key[tau_k-1]) - margin, floor)
-    const float* tau_prev;
+    float* tau_out;                     // optional: tau_out[q] = max(tau_prev[q], score(key[tau_k-1]), score_floor) - margin[q]
+    const float* tau_prev;              //   (tau_prev is already lowered by the margin)
     int tau_k;
-    float tau_margin, tau_floor;
+    const float* margin;                // per-query admission margin (common.cuh query_margin), [nq]
+    float score_floor;                  // the caller's score_threshold (-inf when there is none)
     int nq;                             // CTAs q >= nq only write tau_out[q] = +inf (padded query rows)
     const float* range_lo;              // optional per-query lower bound of every key's score (finer first bins)
 };
@@ -52,7 +53,8 @@ struct FinalArgs {
     long long top_ld;
     const int* cnt;                     // raw candidate counts [nq][nseg] (overflow detection) or nullptr
     int nseg, cap, K2, k;
-    float score_threshold, margin;
+    float score_threshold;
+    const float* margin;                // per-query admission margin (nullptr: 0)
     int rescore;                        // 1: keys carry bf16-query tensor scores -> fp32 re-score
     const uint16_t* db;                 // tiled DB storage (common.cuh)
     int d_pad;
@@ -66,6 +68,9 @@ struct FinalArgs {
 
 int launch_chunk_topk(const ChunkTopkArgs& a, int num_chunks, int nq, cudaStream_t stream);
 int launch_select(const SelectArgs& a, int grid_q, cudaStream_t stream);
+// last level fused with the fp32 re-score and the final ordering: `a` selects (a.K = candidates aimed at, a.out unused),
+// `f` supplies k, score_threshold, margin, db/qn and the outputs (f.top / f.cnt / f.K2 unused)
+int launch_select_final(const SelectArgs& a, const FinalArgs& f, int nq, cudaStream_t stream);
 int launch_final(const FinalArgs& a, int nq, cudaStream_t stream);
 int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts, long long ids_gs, long long scores_gs,
                  long long counts_gs, int G, int nq, int k, int64_t* out_ids, float* out_scores, int32_t* out_counts,

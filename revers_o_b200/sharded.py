@@ -115,3 +115,23 @@ class ShardedIndex:
                                                 b["oi"].data_ptr(), b["os"].data_ptr(), b["oc"].data_ptr(),
                                                 torch.cuda.current_stream(dev).cuda_stream), "rvo_merge_topk_packed")
         return b["oi"], b["os"], b["oc"]
+
+    def search_exact(self, queries: torch.Tensor, k: int, score_threshold=None):
+        """`search` plus the overflow protocol of rvo_search_topk: queries whose merged count is -1 (more than 2048
+        candidates inside the bf16 admission margin on some shard) are re-run on every rank through the exact fp32 scan
+        (`ops.search_topk_exact`) and merged again.  Every rank computes the same merged counts, so all ranks take the
+        same branch without an extra collective; reading the counts is one host sync."""
+        ids, scores, counts = self.search(queries, k, score_threshold)
+        bad = (counts < 0).nonzero().flatten()
+        if bad.numel() == 0:
+            return ids, scores, counts
+        ids, scores, counts = ids.clone(), scores.clone(), counts.clone()
+        sub = queries[bad].contiguous()
+        a, b_, c = ops.search_topk_exact(self.db, self.n_local, self.d, sub, k, score_threshold, self.id_offset)
+        if self.world > 1:
+            blob = pack_results(a, b_, c)
+            g = allgather_packed(blob, self.group)
+            gi, gs, gc = unpack_results(g, sub.shape[0], k)
+            a, b_, c = ops.merge_topk(gi, gs, gc, k)
+        ids[bad], scores[bad], counts[bad] = a, b_, c
+        return ids, scores, counts

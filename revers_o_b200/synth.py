@@ -27,24 +27,35 @@ def make_db(n: int, d: int, queries: torch.Tensor | None = None, n_plant: int = 
     """Tiled bf16 DB storage (ops.db_alloc layout) of n L2-normalised rows, generated on `device` chunk by chunk.
     `ops.untile_rows(db, n, d)` gives the row-major view for checkers."""
     from . import ops
-    d_pad = (d + 63) // 64 * 64
     dev = torch.device(device)
     tiled = ops.db_alloc(n, d, dev)
-    nb, nk = tiled.shape[0], tiled.shape[1]
-    # row-major alias of the same values, written chunk by chunk and permuted into the tiled storage at the end
-    db = torch.zeros((nb * 128, d_pad), dtype=torch.bfloat16, device=dev)
+    nk = tiled.shape[1]
+    d_pad = nk * 64
+    chunk = max(128, chunk // 128 * 128)
     g = torch.Generator(device=dev).manual_seed(seed)
+    # chunk by chunk straight into the tiled storage [block][k-chunk][128][64]: peak extra memory is one chunk
+    # (a 128 GB shard of the 100M x 1280 DB at 2 GPUs leaves no room for a row-major alias)
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)
         x = torch.randn((hi - lo, d), generator=g, dtype=torch.float32, device=dev)
         x = x / x.norm(dim=1, keepdim=True)
-        db[lo:hi, :d] = x.to(torch.bfloat16)
+        nb_c = (hi - lo + 127) // 128
+        pad = torch.zeros((nb_c * 128, d_pad), dtype=torch.bfloat16, device=dev)
+        pad[: hi - lo, :d] = x.to(torch.bfloat16)
+        del x
+        tiled[lo // 128: lo // 128 + nb_c].copy_(pad.view(nb_c, 128, nk, 64).permute(0, 2, 1, 3))
+        del pad
     if queries is not None and n_plant > 0 and n > 0:
         nq = queries.shape[0]
         qn = (queries.float() / queries.float().norm(dim=1, keepdim=True)).to(dev)
         gp = torch.Generator(device="cpu").manual_seed(seed + 1)
         per = min(n_plant, max(1, n // max(nq, 1)))
-        rows = torch.randperm(n, generator=gp)[: nq * per].view(nq, per).to(dev)
+        if n <= (1 << 24):
+            rows = torch.randperm(n, generator=gp)[: nq * per]
+        else:  # big shards: distinct rows without materialising a permutation of n
+            rows = torch.randint(0, n, (2 * nq * per,), generator=gp).unique()
+            rows = rows[torch.randperm(rows.numel(), generator=gp)][: nq * per]
+        rows = rows.view(nq, per).to(dev)
         alpha = torch.linspace(0.5, 0.99, per, device=dev).view(1, per, 1)
         for lo in range(0, nq, 64):
             hi = min(nq, lo + 64)
@@ -54,10 +65,10 @@ def make_db(n: int, d: int, queries: torch.Tensor | None = None, n_plant: int = 
             noise = noise / noise.norm(dim=-1, keepdim=True)
             v = alpha * qq + torch.sqrt(1 - alpha * alpha) * noise
             v = v / v.norm(dim=-1, keepdim=True)
-            db[rows[lo:hi].reshape(-1), :d] = v.reshape(-1, d).to(torch.bfloat16)
-    for b0 in range(0, nb, 1024):  # permute into [block][k-chunk][128][64], 1024 row blocks at a time
-        b1 = min(nb, b0 + 1024)
-        tiled[b0:b1].copy_(db[b0 * 128: b1 * 128].view(b1 - b0, 128, nk, 64).permute(0, 2, 1, 3))
+            vb = torch.zeros(((hi - lo) * per, d_pad), dtype=torch.bfloat16, device=dev)
+            vb[:, :d] = v.reshape(-1, d).to(torch.bfloat16)
+            r = rows[lo:hi].reshape(-1)
+            tiled[r // 128, :, r % 128, :] = vb.view(-1, nk, 64)
     return tiled
 
 

@@ -260,3 +260,69 @@ def test_config1_full_size_properties_and_sampled_parity(dev):
     dbf = ops.untile_rows(db, n, d).float().cpu().numpy()
     ref = O.search_batch(dbf, q[sel].cpu().numpy(), k, None, db_is_normalized=True)
     assert_topk_match(ids[sel], sc[sel], cnt[sel], ref, k, TOL, "cfg1")
+
+
+# ---- tightly packed top-k (what an unstructured DB looks like: many rows within the bf16 margin of the k-th) ----
+def _cluster_db(dev, n, d, q, lo, hi, m, seed):
+    """Background rows plus, for EVERY query, `m` rows whose cosine to it is spread over [lo, hi]."""
+    from revers_o_b200 import ops, synth
+    db = synth.make_db(n, d, None, seed=seed, device=dev)
+    g = torch.Generator(device=dev).manual_seed(seed + 7)
+    nq = q.shape[0]
+    qn = (q / q.norm(dim=1, keepdim=True)).to(dev)
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(seed + 9))[: nq * m].view(nq, m).to(dev)
+    alpha = torch.linspace(lo, hi, m, device=dev).view(1, m, 1)
+    for i in range(nq):
+        noise = torch.randn((1, m, d), generator=g, device=dev)
+        qq = qn[i].view(1, 1, d)
+        noise = noise - (noise * qq).sum(-1, keepdim=True) * qq
+        noise = noise / noise.norm(dim=-1, keepdim=True)
+        v = alpha * qq + torch.sqrt(1 - alpha * alpha) * noise
+        vb = torch.zeros((m, db.shape[1] * 64), dtype=torch.bfloat16, device=dev)
+        vb[:, :d] = (v / v.norm(dim=-1, keepdim=True)).view(m, d).to(torch.bfloat16)
+        r = rows[i]
+        db[r // 128, :, r % 128, :] = vb.view(m, db.shape[1], 64)
+    return db
+
+
+@pytest.mark.parametrize("m,nq", [(600, 12), (1500, 40)])
+def test_many_candidates_inside_the_margin(dev, m, nq):
+    """m rows per query within 0.002 of each other at the top: far more than k candidates lie inside the bf16 admission
+    margin of the k-th score.  The fused select/re-score keeps up to 2048 of them, so the result stays exact and no
+    query is flagged."""
+    from revers_o_b200 import synth
+    n, d, k = 200_000, 1024, 100
+    q = synth.make_queries(nq, d, seed=61, device=dev)
+    db = _cluster_db(dev, n, d, q, 0.900, 0.902, m, seed=62)
+    ids, sc, cnt = _run(db, n, d, q, k)
+    assert np.all(cnt == k), f"{int(np.sum(cnt < 0))} queries flagged"
+    assert_topk_match(ids, sc, cnt, _oracle(db, n, d, q, k), k, TOL, f"cluster{m}")
+
+
+def test_unplanted_background_top_k(dev):
+    """No planted neighbours at all: the top-100 of 3M random rows sit ~0.004 apart in total (the densest score
+    distribution a DB can have at this size).  Every query must come back exact and unflagged."""
+    from revers_o_b200 import ops, synth
+    n, d, nq, k = 3_000_000, 256, 48, 100
+    q = synth.make_queries(nq, d, seed=71, device=dev)
+    db = synth.make_db(n, d, None, seed=72, device=dev)
+    ids, sc, cnt = _run(db, n, d, q, k)
+    assert np.all(cnt == k), f"{int(np.sum(cnt < 0))} queries flagged"
+    sel = list(range(0, nq, 6))
+    dbf = ops.untile_rows(db, n, d).float().cpu().numpy()
+    ref = O.search_batch(dbf, q[sel].cpu().numpy(), k, None, db_is_normalized=True)
+    assert_topk_match(ids[sel], sc[sel], cnt[sel], ref, k, TOL, "background")
+
+
+def test_overflow_beyond_capacity_falls_back_exactly(dev):
+    """3000 near-identical rows per query exceed the 2048-candidate capacity: rvo_search_topk flags the query
+    (count -1) and the public API re-runs it through the exact fp32 scan — still the right answer, never a wrong one."""
+    from revers_o_b200 import ops, synth
+    n, d, nq, k = 100_000, 512, 6, 50
+    q = synth.make_queries(nq, d, seed=81, device=dev)
+    db = _cluster_db(dev, n, d, q, 0.9500, 0.9503, 3000, seed=82)
+    ids, sc, cnt = _run(db, n, d, q, k)
+    assert np.all((cnt == k) | (cnt == -1))
+    ids2, sc2, cnt2 = ops.search_topk_exact(db, n, d, q, k)
+    torch.cuda.synchronize()
+    assert_topk_match(ids2.cpu().numpy(), sc2.cpu().numpy(), cnt2.cpu().numpy(), _oracle(db, n, d, q, k), k, TOL, "fallback")
