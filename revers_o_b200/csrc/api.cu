@@ -11,6 +11,7 @@
 namespace rvo {
 
 extern bool g_force_cuda_core_pool;
+extern void* g_pool_trace;
 size_t selfjoin_workspace_bytes(int d, long long cand_cap);
 int launch_selfjoin(const uint16_t* db, long long n_rows, int d, long long row_lo, long long row_hi, float threshold,
                     long long id_offset, long long cand_cap, long long* out_pairs, float* out_scores, long long out_cap,
@@ -287,6 +288,7 @@ int rvo_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "final_ratio")) opt_final_ratio = value;
     else if (!strcmp(name, "time_scan")) opt_time_scan = value;
     else if (!strcmp(name, "pool_path")) g_force_cuda_core_pool = value == 1;
+    else if (!strcmp(name, "pool_trace")) g_pool_trace = (void*)(uintptr_t)value;
     else {
         set_error("unknown option '%s'", name);
         return RVO_E_INVALID;

@@ -21,6 +21,7 @@ namespace rvo {
 constexpr int kPoolThreads = 512;
 constexpr int kPoolWarps = kPoolThreads / 32;
 constexpr int kSlab = 32;  // channels per CTA
+void* g_pool_trace = nullptr;          // option "pool_trace": device buffer [B][8] u64 for per-image pipeline time stamps (debug)
 bool g_force_cuda_core_pool = false;  // option "pool_path" = 1: always use the CUDA-core kernels below
 
 __global__ void __launch_bounds__(256) mask_index_kernel(const uint8_t* __restrict__ masks, int BM, int M, int P, int lim,
@@ -190,8 +191,8 @@ __global__ void __launch_bounds__(256) mask_scale_kernel(float* __restrict__ out
 }
 
 int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int lim, float* out,
-                        int32_t* out_counts, int32_t* out_src, int32_t* out_total, int* img_base, unsigned int* ticket,
-                        int sm_count, cudaStream_t stream);
+                        int32_t* out_counts, int32_t* out_src, int32_t* out_total, int* img_base, int* area,
+                        unsigned int* ticket, int sm_count, cudaStream_t stream);
 
 size_t mask_pool_workspace_bytes(int B, int M, int P, int D) {
     (void)D;
@@ -231,9 +232,8 @@ int launch_mask_pool(const uint16_t* feats, const uint8_t* masks, int B, int M, 
     }
     if (!g_force_cuda_core_pool) {
         // tensor-core path (mask_pool_tc.cu) whenever the image's whole output fits TMEM
-        RVO_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
         const int rc = launch_mask_pool_tc(feats, masks, B, M, P, D, lim, out, out_counts, out_src, out_total, img_base,
-                                           ticket, sm_count, stream);
+                                           area, ticket, sm_count, stream);
         if (rc <= 0) return rc;
     }
     const int p_pad = (P + 7) & ~7;

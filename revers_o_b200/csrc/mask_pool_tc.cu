@@ -7,12 +7,18 @@
 //   A operand  = features, M = 128 channels of a slab, K = patches: F is [p][d] with d contiguous, i.e. an
 //                MN-major A; TMA boxes {64 d, 64 p} (128-byte swizzle) land as 8-row x 128-byte atoms;
 //                descriptor: LBO = 8 KiB (next 64 channels), SBO = 1 KiB (next 8 patches).
-//   B operand  = masks, N = regions (padded to 16), K = patches: converted u8 -> bf16 0/1 by four warps
-//                straight into the K-major 128B-swizzled smem tiles (double-buffered per image).
-//   D (TMEM)   = [128 channels][slab * N + m] fp32: all D/128 slabs of an image at once (D/128 * N <= 512),
-//                so the epilogue sees the complete un-normalised embedding of every region of the image:
-//                pass 1 reduces ||e_m||^2 over channels (shuffle + smem), pass 2 writes e_m / ||e_m||.
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2-9 epilogue (two per TMEM lane quarter), 10-13 mask conversion.
+//   B operand  = masks, N = regions (padded to 16), K = patches: u8 -> bf16 0/1, converted by four warps into
+//                K-major 128B-swizzled smem tiles, ONE 64-patch tile at a time: tile pc of the next image is
+//                converted as soon as the current image's last MMA on tile pc has retired (per-tile
+//                mbarriers), with the tile's mask bytes prefetched into registers before that wait.  The first
+//                version converted a whole image between two images' MMAs (8-12 us of bubble per image).
+//   D (TMEM)   = [128 channels][slab * N + m] fp32: all D/128 slabs of an image (D/128 * N <= 512), in TWO
+//                halves with their own full/empty barriers.  MMA order is half -> patch tile -> slab, so the
+//                epilogue's sum-of-squares pass over half 0 runs under the MMAs of half 1, and half 0 is handed
+//                back (after its normalise + store pass) while half 1 is still being stored.
+// Epilogue: pass 1 reduces ||e_m||^2 over channels (shuffle + smem), pass 2 writes e_m / ||e_m|| (TMEM loads
+// software-pipelined against the stores).
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2-9 epilogue (two per TMEM lane quarter), 10-11 mask conversion.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "prep_scan_small.cuh"
@@ -21,17 +27,24 @@ namespace rvo {
 
 using namespace ptx;
 
-constexpr int kPtThreads = 448;
+constexpr int kPtThreads = 384;       // 12 warps = 3 per SM sub-partition -> up to 168 registers per thread
+constexpr int kPtCvtThreads = 64;     // mask-conversion warps 10..11
 constexpr int kPtMaxStages = 12;
+constexpr int kPtMaxPc = 16;          // patch tiles per image (P <= 1024)
 constexpr int kPtStageBytes = 16384;  // 64 patches x 128 channels bf16
+constexpr int kPtBars = 2 * kPtMaxStages + 2 * kPtMaxPc + 8;
 
 struct PoolTcParams {
     const uint8_t* masks;
-    const int* img_base;   // exclusive scan of kept regions per image
+    int* counts;           // [B] kept (non-empty, below the cap) regions per image — the caller's out_counts
+    int* area;             // [B*M] set patches per region, 0 for regions at or beyond the cap
+    int* out_total;        // sum of counts
+    unsigned int* arrived; // grid-wide arrival counter (zeroed by the launcher): CTAs that have published their counts
     float* out;
     int* out_src;
     int B, M, P, D, lim, n_pad, num_pc, num_slab, num_stages;
     uint32_t off_b, b_buf_bytes, off_misc;
+    unsigned long long* trace;     // option "pool_trace": [B][8] globaltimer stamps of the per-image pipeline events (or null)
 };
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
@@ -56,8 +69,31 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
     return d;
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned int* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void trace_stamp(const PoolTcParams& p, int b, int slot) {
+    if (p.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.trace[(size_t)b * 8 + slot] = t;
+    }
+}
+
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// four mask bytes (any non-zero value = set) -> four bf16 0/1 in two words.  Non-zero bytes are flagged 0x80
+// (SWAR), spread into 16-bit lanes and multiplied by 127: 0x80 * 127 = 0x3F80 = bf16(1.0).
+__device__ __forceinline__ void mask4_to_bf16(uint32_t x, uint32_t& w0, uint32_t& w1, int& cnt) {
+    const uint32_t f = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+    cnt += __popc(f);
+    w0 = __byte_perm(f, 0u, 0x4140) * 127u;   // bytes {f0, 0, f1, 0}
+    w1 = __byte_perm(f, 0u, 0x4342) * 127u;   // bytes {f2, 0, f3, 0}
 }
 
 __global__ void __launch_bounds__(kPtThreads, 1)
@@ -65,33 +101,37 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_a = smem;                                  // [num_stages][16 KiB] feature tiles
     uint8_t* s_b = smem + p.off_b;                        // [num_pc][n_pad x 128 B] mask tiles (single buffer)
-    int* s_area = (int*)(smem + p.off_misc);              // [2][64]
-    int* s_outrow = s_area + 128;                         // [2][64]
+    int* s_outrow = (int*)(smem + p.off_misc);            // [2][64]
     float* s_invarea = (float*)(s_outrow + 128);          // [2][64]
     float* s_ss = s_invarea + 128;                        // [64] + [4][64] per-quarter partials
     uint64_t* bars = (uint64_t*)(s_ss + 64 + 256);
     uint64_t* bar_full = bars;                            // [kPtMaxStages]
     uint64_t* bar_empty = bars + kPtMaxStages;            // [kPtMaxStages]
-    uint64_t* bar_bfull = bars + 2 * kPtMaxStages;        // masks of the next image converted
-    uint64_t* bar_bfree = bars + 2 * kPtMaxStages + 1;    // MMAs of an image retired: mask tiles may be overwritten
-    uint64_t* bar_tfull = bars + 2 * kPtMaxStages + 2;    // accumulators of an image complete
-    uint64_t* bar_tempty = bars + 2 * kPtMaxStages + 3;   // TMEM drained
-    uint64_t* bar_mfree = bars + 2 * kPtMaxStages + 4;    // [2] epilogue done with s_outrow/s_invarea[buf]
-    uint32_t* s_tmem = (uint32_t*)(bars + 2 * kPtMaxStages + 6);
+    uint64_t* bar_bfull = bars + 2 * kPtMaxStages;        // [kPtMaxPc] mask tile pc of the next image converted
+    uint64_t* bar_bfree = bar_bfull + kPtMaxPc;           // [kPtMaxPc] this image's MMAs on tile pc retired
+    uint64_t* bar_tfull = bar_bfree + kPtMaxPc;           // [2] accumulators of a half complete
+    uint64_t* bar_tempty = bar_tfull + 2;                 // [2] half drained
+    uint64_t* bar_mfree = bar_tempty + 2;                 // [2] epilogue done with s_outrow/s_invarea[buf]
+    uint64_t* bar_mready = bar_mfree + 2;                 // [2] s_outrow/s_invarea[buf] of an image written
+    uint32_t* s_tmem = (uint32_t*)(bars + kPtBars);
     const uint32_t kPtStages = (uint32_t)p.num_stages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pad = p.n_pad, num_pc = p.num_pc, num_slab = p.num_slab;
+    const int half_split = (num_slab + 1) >> 1;           // slabs [0, half_split) form half 0, the rest half 1
+    const int last_half = num_slab > half_split ? 1 : 0;
     const uint32_t b_tile_bytes = (uint32_t)n_pad * 128u;
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
         for (int i = 0; i < kPtMaxStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-        mbar_init(bar_bfull, 1);
-        mbar_init(bar_bfree, 1);
-        for (int i = 0; i < 2; ++i) mbar_init(&bar_mfree[i], 8);
-        mbar_init(bar_tfull, 1);
-        mbar_init(bar_tempty, 8);
+        for (int i = 0; i < kPtMaxPc; ++i) { mbar_init(&bar_bfull[i], 1); mbar_init(&bar_bfree[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], 8);
+            mbar_init(&bar_mfree[i], 8);
+            mbar_init(&bar_mready[i], 1);
+        }
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -107,15 +147,18 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             for (int b = blockIdx.x; b < p.B; b += gridDim.x)
-                for (int s = 0; s < num_slab; ++s)
-                    for (int pc = 0; pc < num_pc; ++pc) {
-                        mbar_wait(&bar_empty[stage], phase ^ 1);
-                        mbar_expect_tx(&bar_full[stage], kPtStageBytes);
-                        uint8_t* dst = s_a + (size_t)stage * kPtStageBytes;
-                        tma_load_3d(&tmap_f, &bar_full[stage], dst, s * 128, pc * 64, b, kEvictFirst);
-                        tma_load_3d(&tmap_f, &bar_full[stage], dst + 8192, s * 128 + 64, pc * 64, b, kEvictFirst);
-                        if (++stage == kPtStages) { stage = 0; phase ^= 1; }
-                    }
+                for (int h = 0; h <= last_half; ++h) {
+                    const int s0 = h ? half_split : 0, s1 = h ? num_slab : half_split;
+                    for (int pc = 0; pc < num_pc; ++pc)
+                        for (int s = s0; s < s1; ++s) {
+                            mbar_wait(&bar_empty[stage], phase ^ 1);
+                            mbar_expect_tx(&bar_full[stage], kPtStageBytes);
+                            uint8_t* dst = s_a + (size_t)stage * kPtStageBytes;
+                            tma_load_3d(&tmap_f, &bar_full[stage], dst, s * 128, pc * 64, b, kEvictFirst);
+                            tma_load_3d(&tmap_f, &bar_full[stage], dst + 8192, s * 128 + 64, pc * 64, b, kEvictFirst);
+                            if (++stage == kPtStages) { stage = 0; phase ^= 1; }
+                        }
+                }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -123,175 +166,309 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
             // A: MN-major (bit 15), B: K-major, bf16 x bf16 -> fp32, M = 128, N = n_pad
             const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_pad) | (1u << 15);
             uint32_t stage = 0, phase = 0, it = 0;
+            const uint32_t sB0 = smem_u32(s_b);
             for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
-                mbar_wait(bar_bfull, it & 1u);                    // masks of this image are in smem
-                mbar_wait(bar_tempty, (it & 1u) ^ 1u);            // previous image drained from TMEM
-                tc_fence_after();
-                const uint32_t sB0 = smem_u32(s_b);
-                for (int s = 0; s < num_slab; ++s) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(s * n_pad);
+                for (int h = 0; h <= last_half; ++h) {
+                    const int s0 = h ? half_split : 0, s1 = h ? num_slab : half_split;
+                    mbar_wait(&bar_tempty[h], (it & 1u) ^ 1u);        // this half of the previous image drained from TMEM
+                    if (h == 0) trace_stamp(p, b, 1);
+                    tc_fence_after();
                     for (int pc = 0; pc < num_pc; ++pc) {
-                        mbar_wait(&bar_full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sA = smem_u32(s_a + (size_t)stage * kPtStageBytes);
+                        if (h == 0) {
+                            mbar_wait(&bar_bfull[pc], it & 1u);       // mask tile pc of this image is in smem
+                            if (pc == 0) trace_stamp(p, b, 0);
+                            tc_fence_after();
+                        }
                         const uint32_t sB = sB0 + (uint32_t)pc * b_tile_bytes;
+                        for (int s = s0; s < s1; ++s) {
+                            mbar_wait(&bar_full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t sA = smem_u32(s_a + (size_t)stage * kPtStageBytes);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(s * n_pad);
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4)
-                            umma_bf16(d_tmem, make_mnmajor_sw128_desc(sA + k4 * 2048, 8192, 1024),
-                                      make_kmajor_sw128_desc(sB + k4 * 32), idesc, (uint32_t)((pc | k4) != 0));
-                        umma_commit(&bar_empty[stage]);
-                        if (++stage == kPtStages) { stage = 0; phase ^= 1; }
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma_bf16(d_tmem, make_mnmajor_sw128_desc(sA + k4 * 2048, 8192, 1024),
+                                          make_kmajor_sw128_desc(sB + k4 * 32), idesc, (uint32_t)((pc | k4) != 0));
+                            umma_commit(&bar_empty[stage]);
+                            if (++stage == kPtStages) { stage = 0; phase ^= 1; }
+                        }
+                        if (h == last_half) umma_commit(&bar_bfree[pc]);   // tile pc may be overwritten with the next image's
                     }
+                    umma_commit(&bar_tfull[h]);
                 }
-                umma_commit(bar_tfull);
-                umma_commit(bar_bfree);
+                trace_stamp(p, b, 2);
             }
         }
     } else if (warp < 10) {
         // ===================== epilogue (warps 2..9): mean, ||.||, normalise, compacted store =====================
-        // two warps per TMEM lane quarter; warp `half` owns the 16-region groups half, half+2, ...
-        const int ew = warp - 2, half = ew >> 2;
+        // two warps per TMEM lane quarter; warp `half_w` owns the 16-region groups half_w, half_w + 2
+        const int ew = warp - 2, half_w = ew >> 2;
         const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
         const int ch = (int)lane_base + lane;  // channel inside a slab
         const int ngroups = n_pad / 16;
         float* s_part = s_ss + 64;             // [4 quarters][64] per-warp partial sums of squares
+        // ---- prologue (these warps idle until the first accumulators are complete): areas and kept-region counts of
+        // ALL images of this CTA, published grid-wide; the compaction offsets are a prefix sum over every image's count
+        {
+            int* s_area = (int*)s_part;        // [64] set patches per region of the image being counted
+            const int tid = threadIdx.x - 64;  // 0..255
+            const bool vec16 = (p.P & 15) == 0 && (((uintptr_t)p.masks) & 15) == 0;
+            const int cpr = p.P >> 4;          // 16-byte chunks per mask row
+            for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+                if (tid < 64) s_area[tid] = 0;
+                named_bar(2, 256);
+                const uint8_t* img = p.masks + (size_t)b * p.M * p.P;
+                const int lim_m = p.M < p.lim ? p.M : p.lim;
+                if (vec16) {
+                    // flat (row, chunk) slots, four independent 16-byte loads in flight per thread
+                    const int slots = lim_m * cpr;
+                    for (int f0 = tid; f0 < slots; f0 += 4 * 256) {
+                        uint4 v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int f = f0 + u * 256;
+                            v[u] = make_uint4(0, 0, 0, 0);
+                            if (f < slots) v[u] = __ldg((const uint4*)(img + (size_t)(f / cpr) * p.P) + (f % cpr));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                            int n = 0;
+#pragma unroll
+                            for (int hh = 0; hh < 4; ++hh)
+                                n += __popc((((w[hh] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w[hh]) & 0x80808080u);
+                            if (n) atomicAdd(&s_area[(f0 + u * 256) / cpr], n);
+                        }
+                    }
+                } else {
+                    for (int m = ew; m < lim_m; m += 8) {
+                        const uint8_t* row = img + (size_t)m * p.P;
+                        int n = 0;
+                        for (int i = lane; i < p.P; i += 32) n += __ldg(row + i) != 0;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
+                        if (lane == 0) s_area[m] = n;
+                    }
+                }
+                named_bar(2, 256);
+                if (tid < 64) {   // warps 2 and 3
+                    const int a = tid < p.M ? s_area[tid] : 0;
+                    if (tid < p.M) p.area[(size_t)b * p.M + tid] = a;
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, a > 0);
+                    if (lane == 0) s_area[64 + (tid >> 5)] = __popc(bal);
+                }
+                named_bar(2, 256);
+                if (tid == 0) p.counts[b] = s_area[64] + s_area[65];
+            }
+            named_bar(2, 256);
+            if (tid == 0) {
+                __threadfence();               // areas and counts (ordered by the barrier) before the arrival
+                atomicAdd(p.arrived, 1u);
+            }
+        }
         uint32_t it = 0;
         for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
             const uint32_t buf = it & 1u;
             const float* invarea = s_invarea + buf * 64;
             const int* outrow = s_outrow + buf * 64;
-            mbar_wait(bar_tfull, it & 1u);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + (lane_base << 16);
-            // pass 1: ||mean_m||^2 over all channels
-            for (int g = half; g < ngroups; g += 2) {
-                const int m0 = g * 16;
-                float ss[16];
+            // pass 1: ||mean_m||^2 over all channels; half 0 is reduced while the MMAs of half 1 run
+            float ss[2][16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) ss[i] = 0.f;
-                for (int s = 0; s < num_slab; s += 2) {
-                    uint32_t v[2][16];
-                    tmem_ld_x16(taddr + (uint32_t)(s * n_pad + m0), v[0]);
-                    if (s + 1 < num_slab) tmem_ld_x16(taddr + (uint32_t)((s + 1) * n_pad + m0), v[1]);
-                    tmem_ld_wait();
+            for (int gi = 0; gi < 2; ++gi)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float e = __uint_as_float(v[0][i]) * invarea[m0 + i];
-                        ss[i] = fmaf(e, e, ss[i]);
-                    }
-                    if (s + 1 < num_slab) {
+                for (int i = 0; i < 16; ++i) ss[gi][i] = 0.f;
+            for (int h = 0; h <= last_half; ++h) {
+                const int s0 = h ? half_split : 0, s1 = h ? num_slab : half_split;
+                mbar_wait(&bar_tfull[h], it & 1u);
+                tc_fence_after();
+                if (threadIdx.x == 64) trace_stamp(p, b, 3 + h);
+#pragma unroll
+                for (int gi = 0; gi < 2; ++gi) {
+                    const int g = half_w + 2 * gi;
+                    if (g >= ngroups) break;
+                    const int m0 = g * 16;
+                    for (int s = s0; s < s1; s += 2) {
+                        uint32_t v[2][16];
+                        tmem_ld_x16(taddr + (uint32_t)(s * n_pad + m0), v[0]);
+                        if (s + 1 < s1) tmem_ld_x16(taddr + (uint32_t)((s + 1) * n_pad + m0), v[1]);
+                        tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float e = __uint_as_float(v[1][i]) * invarea[m0 + i];
-                            ss[i] = fmaf(e, e, ss[i]);
+                            const float e = __uint_as_float(v[0][i]);
+                            ss[gi][i] = fmaf(e, e, ss[gi][i]);
+                        }
+                        if (s + 1 < s1) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float e = __uint_as_float(v[1][i]);
+                                ss[gi][i] = fmaf(e, e, ss[gi][i]);
+                            }
                         }
                     }
                 }
+            }
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const int g = half_w + 2 * gi;
+                if (g >= ngroups) break;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    float x = ss[i];
+                    float x = ss[gi][i];
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
-                    if (lane == 0) s_part[(warp & 3) * 64 + m0 + i] = x;
+                    if (lane == 0) s_part[(warp & 3) * 64 + g * 16 + i] = x;
                 }
             }
+            // the image's output rows / 1/area (written by the conversion warp after the grid-wide count rendezvous) are
+            // first needed here: sum_d (acc_d / area)^2 = (sum_d acc_d^2) / area^2
+            mbar_wait(&bar_mready[buf], (it >> 1) & 1u);
             named_bar(2, 256);
             if (ew * 32 + lane < 64) {
                 const int m = ew * 32 + lane;
-                s_ss[m] = s_part[m] + s_part[64 + m] + s_part[128 + m] + s_part[192 + m];
+                s_ss[m] = (s_part[m] + s_part[64 + m] + s_part[128 + m] + s_part[192 + m]) * invarea[m] * invarea[m];
             }
             named_bar(2, 256);
-            // pass 2: e / ||e|| -> compacted rows (no epsilon, core_system.py:407)
-            for (int g = half; g < ngroups; g += 2) {
-                const int m0 = g * 16;
-                float sc[16];
-                float* optr[16];
+            if (threadIdx.x == 64) trace_stamp(p, b, 5);
+            // pass 2: e / ||e|| -> compacted rows (no epsilon, core_system.py:407); one half at a time so that half 0
+            // goes back to the MMA issuer early.  The TMEM load of step j+1 is in flight while step j is stored; the
+            // slab loop is unrolled over its maximum (4 slabs per half at D = 1024) so that the store addresses are
+            // immediates off one 64-bit base per region.
+            float* __restrict__ gout = p.out + ch;
+            for (int h = 0; h <= last_half; ++h) {
+                const int s0 = h ? half_split : 0, s1 = h ? num_slab : half_split;
+                const int ns = s1 - s0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    sc[i] = invarea[m0 + i] / sqrtf(s_ss[m0 + i]);
-                    const int r = outrow[m0 + i];
-                    optr[i] = r >= 0 ? p.out + (size_t)r * p.D + ch : nullptr;
-                }
-                for (int s = 0; s < num_slab; ++s) {
-                    uint32_t v[16];
-                    tmem_ld_x16(taddr + (uint32_t)(s * n_pad + m0), v);
-                    tmem_ld_wait();
+                for (int gi = 0; gi < 2; ++gi) {
+                    const int g = half_w + 2 * gi;
+                    if (g >= ngroups) break;
+                    const int m0 = g * 16;
+                    float sc[16];
+                    int rr[16];                     // output row of the region, < 0: empty region (dropped)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (optr[i]) optr[i][s * 128] = __uint_as_float(v[i]) * sc[i];
+                    for (int i = 0; i < 16; ++i) {
+                        sc[i] = invarea[m0 + i] * rsqrtf(s_ss[m0 + i]);
+                        rr[i] = outrow[m0 + i];
+                    }
+                    for (int j0 = 0; j0 < ns; j0 += 4) {
+                        uint32_t v[2][16];
+                        tmem_ld_x16(taddr + (uint32_t)((s0 + j0) * n_pad + m0), v[0]);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = j0 + jj;
+                            if (j < ns) {
+                                tmem_ld_wait();
+                                if (jj < 3 && j + 1 < ns) tmem_ld_x16(taddr + (uint32_t)((s0 + j + 1) * n_pad + m0), v[(jj + 1) & 1]);
+                                float* __restrict__ o = gout + (size_t)(s0 + j0) * 128 + jj * 128;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (rr[i] >= 0) __stcs(o + (size_t)rr[i] * (size_t)p.D, __uint_as_float(v[jj & 1][i]) * sc[i]);
+                            }
+                        }
+                    }
                 }
+                tc_fence_before();
+                named_bar(2, 256);
+                if (lane == 0) mbar_arrive(&bar_tempty[h]);
             }
             if (p.out_src && warp == 2)
                 for (int m = lane; m < n_pad; m += 32)
                     if (outrow[m] >= 0) p.out_src[outrow[m]] = b * p.M + m;
-            tc_fence_before();
-            named_bar(2, 256);
-            if (lane == 0) {
-                mbar_arrive(bar_tempty);
-                mbar_arrive(&bar_mfree[buf]);
-            }
+            if (threadIdx.x == 64) trace_stamp(p, b, 6);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_mfree[buf]);
         }
     } else {
-        // ===================== mask conversion (warps 10..13): u8 [M][P] -> bf16 K-major swizzled tiles =====================
-        const int t = threadIdx.x - 320;  // 0..127
+        // ===================== mask conversion (warps 10..11): u8 [M][P] -> bf16 K-major swizzled tiles =====================
+        const int t = threadIdx.x - 320;  // 0..63
+        const size_t img_bytes = (size_t)p.M * p.P;
+        const bool vec = (p.P & 7) == 0 && (((uintptr_t)p.masks) & 7) == 0;   // one 8-byte load per 8-patch chunk
+        // the 8-patch chunks of one 64-patch tile: n_pad rows x 8 chunks, thread t takes chunks t, t + 64, ...
+        auto load_tile = [&](int b, int pc, unsigned long long (&r)[8]) {
+            const uint8_t* src = p.masks + (size_t)b * img_bytes;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int idx = t + kPtCvtThreads * j, m = idx >> 3, p0 = pc * 64 + (idx & 7) * 8;
+                unsigned long long bytes = 0ull;
+                if (m < p.M && m < p.lim && p0 < p.P) {
+                    const uint8_t* row = src + (size_t)m * p.P;
+                    if (vec) {
+                        bytes = __ldg((const unsigned long long*)(row + p0));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (p0 + i < p.P) bytes |= (unsigned long long)__ldg(row + p0 + i) << (8 * i);
+                    }
+                }
+                r[j] = bytes;
+            }
+        };
+        unsigned long long cur[8], nxt[8];
+        if ((int)blockIdx.x < p.B) load_tile(blockIdx.x, 0, cur);
+        int img_base = 0, prefix_from = 0;   // warp 10: kept regions of the images before `prefix_from`
         uint32_t it = 0;
         for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
             const uint32_t buf = it & 1u;
-            mbar_wait(bar_bfree, (it & 1u) ^ 1u);                   // previous image's MMAs no longer read the tiles
-            mbar_wait(&bar_mfree[buf], ((it >> 1) & 1u) ^ 1u);      // epilogue of image it-2 released the small arrays
-            int* area = s_area + buf * 64;
-            uint8_t* dstb = s_b;
-            const int chunks_per_row = num_pc * 8;  // 16-byte smem chunks (8 patches) per mask row
-            const uint8_t* src = p.masks + (size_t)b * p.M * p.P;
-            const bool vec = (p.P & 7) == 0 && (((uintptr_t)src) & 7) == 0;   // one 8-byte load per chunk
-            for (int m = warp - 10; m < n_pad; m += 4) {                       // warp per mask row, lane per chunk
-                const bool live = m < p.M && m < p.lim;
-                const uint8_t* row = src + (size_t)m * p.P;
-                int cnt = 0;
-                for (int ck = lane; ck < chunks_per_row; ck += 32) {
-                    const int p0 = ck * 8;
-                    unsigned long long bytes = 0ull;
-                    if (live) {
-                        if (vec) {
-                            if (p0 < p.P) bytes = __ldg((const unsigned long long*)(row + p0));
-                        } else {
+            for (int pc = 0; pc < num_pc; ++pc) {
+                // prefetch the next tile's mask bytes, then wait for this tile's smem to be released
+                const bool more = pc + 1 < num_pc;
+                const int nb = more ? b : b + (int)gridDim.x;
+                if (nb < p.B) load_tile(nb, more ? pc + 1 : 0, nxt);
+                mbar_wait(&bar_bfree[pc], (it & 1u) ^ 1u);          // previous image's MMAs no longer read tile pc
+                if (t == 0 && pc == 0) trace_stamp(p, b, 7);
+                uint8_t* tile = s_b + (size_t)pc * b_tile_bytes;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (p0 + i < p.P) bytes |= (unsigned long long)row[p0 + i] << (8 * i);
+                for (int j = 0; j < 8; ++j) {
+                    const int idx = t + kPtCvtThreads * j, m = idx >> 3, cin = idx & 7;
+                    if (m < n_pad) {
+                        uint32_t w0, w1, w2, w3;
+                        int unused = 0;
+                        mask4_to_bf16((uint32_t)cur[j], w0, w1, unused);
+                        mask4_to_bf16((uint32_t)(cur[j] >> 32), w2, w3, unused);
+                        *(uint4*)(tile + (size_t)m * 128 + (size_t)((cin ^ (m & 7)) << 4)) = make_uint4(w0, w1, w2, w3);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+                fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async proxy
+                named_bar(3, kPtCvtThreads);
+                if (t == 0) mbar_arrive(&bar_bfull[pc]);
+                if (warp == 10 && pc == num_pc - 1) {  // needed by the epilogue only (bar_mready): after the last tile is handed over
+                    // compacted output rows of this image: img_base[b] + number of non-empty regions before m
+                    mbar_wait(&bar_mfree[buf], ((it >> 1) & 1u) ^ 1u);  // epilogue of image it-2 released the small arrays
+                    if (it == 0) {
+                        // every CTA of the (co-resident, <= one per SM) grid has published the counts of its images
+                        uint32_t spins = 0;
+                        while (ld_acquire_u32(p.arrived) < gridDim.x) {
+                            __nanosleep(64);
+                            if (++spins == (1u << 24)) {
+                                if (lane == 0) printf("rvo: mask_pool grid rendezvous timed out (block %d)\n", blockIdx.x);
+                                __trap();
+                            }
                         }
                     }
-                    uint32_t w[4];
+                    // exclusive prefix of the kept counts, carried from this CTA's previous image (<= gridDim.x new terms)
+                    int add = 0;
+                    for (int i = prefix_from + lane; i < b; i += 32) add += __ldcg(p.counts + i);
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const uint32_t lo = (uint32_t)(bytes >> (16 * h)) & 0xFFu, hi = (uint32_t)(bytes >> (16 * h + 8)) & 0xFFu;
-                        w[h] = (lo ? 0x00003F80u : 0u) | (hi ? 0x3F800000u : 0u);   // bf16 1.0 per set patch
-                        cnt += (lo != 0) + (hi != 0);
+                    for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xFFFFFFFFu, add, o);
+                    img_base += add;
+                    prefix_from = b;
+                    const int base = img_base;
+                    if (b == p.B - 1 && lane == 0) *p.out_total = img_base + __ldcg(p.counts + b);
+                    int run = 0;
+                    for (int m0 = 0; m0 < 64; m0 += 32) {
+                        const int m = m0 + lane;
+                        const int a = (m < p.M && m < p.lim) ? __ldcg(p.area + (size_t)b * p.M + m) : 0;
+                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, a > 0);
+                        s_outrow[buf * 64 + m] = a > 0 ? base + run + __popc(bal & ((1u << lane) - 1u)) : -1;
+                        s_invarea[buf * 64 + m] = a > 0 ? 1.0f / (float)a : 0.f;
+                        run += __popc(bal);
                     }
-                    const int pc = ck >> 3, cin = ck & 7;
-                    uint4* d4 = (uint4*)(dstb + (size_t)pc * b_tile_bytes + (size_t)m * 128 + (size_t)((cin ^ (m & 7)) << 4));
-                    *d4 = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-                if (lane == 0 && m < 64) area[m] = cnt;
-            }
-            named_bar(3, 128);
-            if (warp == 10) {
-                // compacted output rows of this image: img_base[b] + number of non-empty regions before m
-                const int base = p.img_base[b];
-                int run = 0;
-                for (int m0 = 0; m0 < 64; m0 += 32) {
-                    const int m = m0 + lane;
-                    const int a = m < n_pad ? area[m] : 0;
-                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, a > 0);
-                    s_outrow[buf * 64 + m] = a > 0 ? base + run + __popc(bal & ((1u << lane) - 1u)) : -1;
-                    s_invarea[buf * 64 + m] = a > 0 ? 1.0f / (float)a : 0.f;
-                    run += __popc(bal);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_mready[buf]);
                 }
             }
-            fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async proxy
-            named_bar(3, 128);
-            if (t == 0) mbar_arrive(bar_bfull);
         }
     }
 
@@ -300,64 +477,7 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// per-image count of kept (non-empty, < lim) regions, then an exclusive scan by the last block to finish
-__global__ void __launch_bounds__(256) mask_count_kernel(const uint8_t* __restrict__ masks, int B, int M, int P, int lim,
-                                                         int* __restrict__ counts, int* __restrict__ img_base,
-                                                         int* __restrict__ out_total, unsigned int* __restrict__ ticket) {
-    __shared__ int s_cnt;
-    __shared__ bool s_last;
-    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    const bool vec = (P & 15) == 0 && (((uintptr_t)masks) & 15) == 0;
-    for (int m = warp; m < M && m < lim; m += 8) {
-        const uint8_t* row = masks + ((size_t)b * M + m) * P;
-        bool any = false;
-        if (vec) {
-            for (int i = lane; i < (P >> 4); i += 32) {
-                const uint4 v = __ldg((const uint4*)row + i);
-                any |= (v.x | v.y | v.z | v.w) != 0u;
-            }
-        } else {
-            for (int i = lane; i < P; i += 32) any |= row[i] != 0;
-        }
-        if (__any_sync(0xFFFFFFFFu, any) && lane == 0) atomicAdd(&s_cnt, 1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        counts[b] = s_cnt;
-        __threadfence();
-        s_last = atomicAdd(ticket, 1u) == (unsigned)(B - 1);
-    }
-    __syncthreads();
-    if (s_last) {  // block-wide exclusive scan over the B per-image counts, 256 at a time
-        __shared__ int s_scan[256];
-        __shared__ int s_carry;
-        if (threadIdx.x == 0) s_carry = 0;
-        __threadfence();
-        __syncthreads();
-        for (int c0 = 0; c0 < B; c0 += 256) {
-            const int i = c0 + threadIdx.x;
-            const int v = i < B ? ((volatile int*)counts)[i] : 0;
-            s_scan[threadIdx.x] = v;
-            __syncthreads();
-            for (int o = 1; o < 256; o <<= 1) {
-                const int t = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
-                __syncthreads();
-                s_scan[threadIdx.x] += t;
-                __syncthreads();
-            }
-            if (i < B) img_base[i] = s_carry + s_scan[threadIdx.x] - v;
-            __syncthreads();
-            if (threadIdx.x == 255) s_carry += s_scan[255];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            *out_total = s_carry;
-            *ticket = 0u;
-        }
-    }
-}
+extern void* g_pool_trace;
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -366,13 +486,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 // returns RVO_OK when the tensor-core path ran, 1 when the shape is not supported by it (caller falls back to the
 // CUDA-core kernel — same results), <0 on error.
 int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int lim, float* out,
-                        int32_t* out_counts, int32_t* out_src, int32_t* out_total, int* img_base, unsigned int* ticket,
-                        int sm_count, cudaStream_t stream) {
+                        int32_t* out_counts, int32_t* out_src, int32_t* out_total, int* img_base, int* area,
+                        unsigned int* ticket, int sm_count, cudaStream_t stream) {
     const int n_pad = (M + 15) / 16 * 16;
     const int num_pc = (P + 63) / 64, num_slab = D / 128;
     if (D % 128 != 0 || n_pad > 64 || num_slab * n_pad > 512) return 1;
+    if (num_pc > kPtMaxPc) return 1;
     const size_t b_buf = (size_t)num_pc * n_pad * 128;
-    const size_t tail = (128 * 3 + 64 + 256) * 4 + (2 * kPtMaxStages + 8) * 8;
+    const size_t tail = (128 * 2 + 64 + 256) * 4 + (kPtBars + 1) * 8;
     if (b_buf + tail + 2 * kPtStageBytes > 227 * 1024) return 1;
     int stages = (int)((227 * 1024 - b_buf - tail) / kPtStageBytes);   // as many 16 KiB feature tiles in flight as fit
     if (stages > kPtMaxStages) stages = kPtMaxStages;
@@ -403,12 +524,12 @@ int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int 
         set_error("mask_pool: cuTensorMapEncodeTiled failed (%d)", (int)r);
         return RVO_E_CUDA;
     }
-    mask_count_kernel<<<B, 256, 0, stream>>>(masks, B, M, P, lim, out_counts, img_base, out_total, ticket);
-    RVO_LAUNCHED();
-
     PoolTcParams p;
     p.masks = masks;
-    p.img_base = img_base;
+    p.counts = out_counts;
+    p.area = area;
+    p.out_total = out_total;
+    p.arrived = ticket;
     p.out = out;
     p.out_src = out_src;
     p.B = B; p.M = M; p.P = P; p.D = D; p.lim = lim;
@@ -416,8 +537,12 @@ int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int 
     p.off_b = (uint32_t)off_b;
     p.b_buf_bytes = (uint32_t)b_buf;
     p.off_misc = (uint32_t)off_misc;
+    p.trace = (unsigned long long*)g_pool_trace;
     RVO_CUDA(cudaFuncSetAttribute(mask_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = B < sm_count ? B : sm_count;
+    // ONE launch: the grid is persistent with at most one CTA per SM (all co-resident), which the in-kernel rendezvous
+    // on `arrived` relies on; the launcher zeroes the counter on the same stream
+    RVO_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
     mask_pool_tc_kernel<<<grid, kPtThreads, smem, stream>>>(tm, p);
     RVO_LAUNCHED();
     return RVO_OK;

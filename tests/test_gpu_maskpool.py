@@ -43,7 +43,9 @@ def test_golden_fixture(dev, golden):
     assert np.allclose(out[: int(total.item())].cpu().numpy(), golden["pool_emb_cap4"], atol=1e-5)
 
 
-@pytest.mark.parametrize("B,M,grid,D", [(2, 8, 24, 1024), (5, 64, 24, 1024), (3, 50, 16, 1280), (1, 1, 7, 32), (4, 33, 23, 96)])
+@pytest.mark.parametrize("B,M,grid,D", [(2, 8, 24, 1024), (5, 64, 24, 1024), (3, 50, 16, 1280), (1, 1, 7, 32), (4, 33, 23, 96),
+                                        (300, 3, 7, 128),     # > 148 images, masks converted from global memory (M*P % 16 != 0)
+                                        (331, 16, 24, 256)])  # > 2 images per CTA on the bulk-prefetched raw-mask path
 def test_random_rectangles(dev, B, M, grid, D):
     from revers_o_b200 import synth
     feats, masks = synth.make_maskpool_inputs(B, M, grid, D, seed=11 + B, device=dev, n_empty=min(2, M - 1))
