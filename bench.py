@@ -343,6 +343,25 @@ def run_b200(args):
         del ns_db, ns_index
         torch.cuda.empty_cache()
 
+    # ---- K1 (the other half of the path): mask pooling on BASELINE configs[2], rank 0 at N = 1 only ---------------
+    pool = None
+    if world == 1 and args.workload == "cfg1" and not args.no_north_star:
+        pB, pM, pG, pD = 256, 64, 24, 1024
+        feats, masks = synth.make_maskpool_inputs(pB, pM, pG, pD, seed=11, device=dev)
+        p_ms, p_launches, p_out = timed(lambda: ops.mask_pool(feats, masks), 20, 5)   # 311 MB of inputs > L2: streams HBM
+        regions = int(p_out[3].item())
+        alg = pB * pG * pG * pD * 2 + pB * pM * pG * pG + regions * pD * 4
+        pool = {"workload": "configs[2]: 256 images x 64 masks x 24x24 patches x 1024-d bf16 features (random-init stand-in), "
+                            "fp32 L2-normalised region embeddings out",
+                "value": pB / (p_ms / 1e3), "unit": "images/s", "ms_per_batch": p_ms, "regions": regions,
+                "gpu_launches_per_batch": p_launches / 20,
+                "roofline": {"bound": "hbm", "achieved": alg / (p_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": alg / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg,
+                             "kernel": "mask_pool_tc_kernel (whole rvo_mask_pool call: memset + one launch)",
+                             "peak_kind": peaks_kind}}
+        del feats, masks, p_out
+        torch.cuda.empty_cache()
+
     # ---- cpu baseline (rank 0, N=1): the oracle port in a numpy-only subprocess, bounded sample ----------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,7 +387,7 @@ def run_b200(args):
                     "api": "B200VectorDB.search_batch(host numpy)" if world == 1 else "pinned H2D + ShardedIndex.search + D2H"},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_hbm": roofline_hbm,
-            "north_star": north, "cpu_baseline": cpu, "clocks": clocks,
+            "north_star": north, "mask_pool": pool, "cpu_baseline": cpu, "clocks": clocks,
             "results_ok": counts_ok,
         }
         print(json.dumps(line), flush=True)
