@@ -76,8 +76,13 @@ def check(rc: int, what: str) -> None:
         raise RvoError(f"{what} failed (code {rc}): {msg}")
 
 
+option_epoch = 0   # bumped by set_option: cached plans (workspace sizes) depend on the tuning options
+
+
 def set_option(name: str, value: int) -> None:
+    global option_epoch
     check(load().rvo_set_option(name.encode(), int(value)), f"rvo_set_option({name})")
+    option_epoch += 1
 
 
 def kernel_launch_count() -> int:

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
                                                              float* __restrict__ margin_out) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the seed scan may pre-launch (it waits for this grid)
     if (row >= n) return;
     const float* s = src + (size_t)row * (size_t)src_ld;
     float ss = 0.f;

@@ -19,6 +19,14 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its
+// predecessor in the stream still runs; `grid_dependency_wait` blocks until the predecessor has completed and its
+// writes are visible (a no-op for a normal launch).  Every kernel of the search chain waits BEFORE it touches any
+// global memory, so the only thing that overlaps is the launch latency and the barrier/TMEM/tensor-map prologue.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -85,6 +85,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    grid_dependency_wait();      // thresholds / queries / counters come from the previous kernels of the chain
+    grid_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -498,11 +500,11 @@ int launch_scan_tc(int mode, const uint16_t* db, long long n_rows, long long sup
     if (mode == kModeDense) {
         RVO_CUDA(cudaFuncSetAttribute(scan_tc_kernel<kModeDense>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));
-        scan_tc_kernel<kModeDense><<<grid, kScanThreads, pl.smem_bytes, stream>>>(tm_db, tm_q, p);
+        RVO_CUDA(launch_pdl(scan_tc_kernel<kModeDense>, dim3(grid), dim3(kScanThreads), pl.smem_bytes, stream, tm_db, tm_q, p));
     } else {
         RVO_CUDA(cudaFuncSetAttribute(scan_tc_kernel<kModeFilter>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));
-        scan_tc_kernel<kModeFilter><<<grid, kScanThreads, pl.smem_bytes, stream>>>(tm_db, tm_q, p);
+        RVO_CUDA(launch_pdl(scan_tc_kernel<kModeFilter>, dim3(grid), dim3(kScanThreads), pl.smem_bytes, stream, tm_db, tm_q, p));
     }
     RVO_LAUNCHED();
     return RVO_OK;

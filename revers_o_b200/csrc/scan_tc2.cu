@@ -74,6 +74,8 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
     cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    grid_dependency_wait();      // thresholds / queries / counters come from the previous kernels of the chain
+    grid_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -347,13 +349,15 @@ int launch_scan_tc2(int mode, const uint16_t* db, long long n_rows, long long su
     cfg.blockDim = dim3(kScanThreads);
     cfg.dynamicSmemBytes = pl.smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see ptx.cuh grid_dependency_wait
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     if (mode == kModeDense) {
         RVO_CUDA(cudaFuncSetAttribute(scan_tc2_kernel<kModeDense>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));

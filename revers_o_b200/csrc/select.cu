@@ -4,8 +4,12 @@
 // qdrant-local search behind core_system.py:659-664.
 #include "common.cuh"
 #include "select.cuh"
+#include "ptx.cuh"
 
 namespace rvo {
+
+using ptx::grid_dependency_wait;
+using ptx::grid_launch_dependents;
 
 // Bitonic sort, descending, n a power of two, keys in shared memory, whole block cooperates.
 __device__ __forceinline__ void bitonic_desc_u64(unsigned long long* s, int n) {
@@ -290,6 +294,8 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
     const int q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float INF = __int_as_float(0x7f800000);
+    grid_dependency_wait();      // candidates / scores come from the scan that precedes this kernel in the stream
+    grid_launch_dependents();
     if (q >= a.nq) {  // padded query rows of the tensor path never admit anything
         if (a.tau_out && tid == 0) a.tau_out[q] = INF;
         return;
@@ -499,14 +505,14 @@ int launch_select(const SelectArgs& a, int grid_q, cudaStream_t stream) {
     if (grid_q <= 0) return RVO_OK;
     FinalArgs f;
     memset(&f, 0, sizeof(f));
-    select_kernel<false><<<grid_q, kSelThreads, 0, stream>>>(a, f);
+    RVO_CUDA(launch_pdl(select_kernel<false>, dim3(grid_q), dim3(kSelThreads), 0, stream, a, f));
     RVO_LAUNCHED();
     return RVO_OK;
 }
 
 int launch_select_final(const SelectArgs& a, const FinalArgs& f, int nq, cudaStream_t stream) {
     if (nq <= 0) return RVO_OK;
-    select_kernel<true><<<nq, kSelThreads, 0, stream>>>(a, f);
+    RVO_CUDA(launch_pdl(select_kernel<true>, dim3(nq), dim3(kSelThreads), 0, stream, a, f));
     RVO_LAUNCHED();
     return RVO_OK;
 }

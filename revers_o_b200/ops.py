@@ -12,6 +12,7 @@ from ._lib import RVO_MAX_K, RVO_SMALL_Q, RvoError, check
 
 _ws_lock = threading.Lock()
 _workspaces: dict = {}
+_ws_bytes: dict = {}      # (n_rows, d, nq, k) -> rvo_search_workspace_bytes (depends on the tuning options: see set_option)
 
 
 def _stream(device) -> int:
@@ -145,10 +146,16 @@ def search_topk(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, k:
     else:
         ids, scores, counts = out
     lib = _lib.load()
-    nbytes = lib.rvo_search_workspace_bytes(n_rows, d, nq, k)
-    if nbytes == 0:
-        raise RvoError(f"rvo_search_workspace_bytes rejected n_rows={n_rows} d={d} nq={nq} k={k}: "
-                       + lib.rvo_last_error().decode())
+    wkey = (n_rows, d, nq, k, _lib.option_epoch)
+    nbytes = _ws_bytes.get(wkey)
+    if nbytes is None:
+        nbytes = lib.rvo_search_workspace_bytes(n_rows, d, nq, k)
+        if nbytes == 0:
+            raise RvoError(f"rvo_search_workspace_bytes rejected n_rows={n_rows} d={d} nq={nq} k={k}: "
+                           + lib.rvo_last_error().decode())
+        if len(_ws_bytes) > 256:
+            _ws_bytes.clear()
+        _ws_bytes[wkey] = nbytes
     ws = workspace(dev, nbytes)
     thr = -math.inf if score_threshold is None else float(score_threshold)
     check(lib.rvo_search_topk(_ptr(db), n_rows, d, d_pad_of(d), _ptr(queries), nq, k, thr, int(id_offset), _ptr(ids),
