@@ -208,7 +208,12 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
             sp->seed_stride = 1;
             sp->n_levels = 0;
         } else {
-            sp->seed_stride = supers / (kSeedRows / T);
+            // seed sample: ~1/32 of the shard, between 4k and 16k rows (a small shard — e.g. 1M rows over 8 GPUs — does not
+            // pay a 16k-row pre-pass; the looser threshold only adds a few thousand candidates per query)
+            long long seed_rows = n_rows / 32;
+            if (seed_rows < 4096) seed_rows = 4096;
+            if (seed_rows > kSeedRows) seed_rows = kSeedRows;
+            sp->seed_stride = supers / ((seed_rows + T - 1) / T);
             if (sp->seed_stride < 1) sp->seed_stride = 1;
             long long ratio = opt_final_ratio.load();
             if (ratio < 2) ratio = 2;
