@@ -336,6 +336,13 @@ def run_b200(args):
             ns_steps, ns_warm = (5, 3) if ns_q >= 1024 else (20, 20)
             ns_ms, _, ns_out = timed(lambda: ns_index.search(qd_, 100), ns_steps, ns_warm)
             r_h, r_t = scan_rooflines(ns_index, qd_, 100, ns_ms, 3)
+            ns_traffic = {4096: "cfg3shard", 64: "cfg3shardq64", 16: "cfg3shardq16"}[ns_q]
+            try:
+                r_h["traffic"] = json.load(open(tp)).get(ns_traffic)
+                if r_t is not None:
+                    r_t["traffic"] = r_h["traffic"]
+            except Exception:
+                pass
             north["points"].append({
                 "queries": ns_q, "value": ns_q / (ns_ms / 1e3), "unit": "queries/s", "ms_per_step": ns_ms, "steps": ns_steps,
                 "results_ok": bool((ns_out[2] == 100).all().item()),
