@@ -32,6 +32,7 @@ extern "C" {
 #define RVO_E_CUDA         (-2)  /* a CUDA runtime/driver call failed                                */
 #define RVO_E_NO_DEVICE    (-3)  /* no sm_100 device / driver entry point missing                    */
 #define RVO_E_WORKSPACE    (-4)  /* workspace too small (call rvo_*_workspace_bytes)                 */
+#define RVO_E_UNSUPPORTED  (-5)  /* shape not covered by this fused entry point: use the two-call form */
 
 /* Limits of the fused search path. */
 #define RVO_MAX_K          512   /* largest `limit` served by rvo_search_topk                        */
@@ -92,6 +93,23 @@ size_t rvo_mask_pool_workspace_bytes(int32_t B, int32_t M, int32_t P, int32_t D)
 int rvo_mask_pool(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
                   int32_t max_regions, float* out, int32_t* out_counts, int32_t* out_src, int32_t* out_total,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 fused with ingest — mask-pooled region embeddings written straight into the tiled bf16 DB.
+ * Replaces: the whole ingest tail of create_database for a batch of images — the per-region loop of
+ *           core_system.py:363-408 PLUS the list-of-floats PointStruct + upsert of :596-622 (qdrant COSINE
+ *           upsert = normalise + append) — without the fp32 embeddings ever reaching HBM.
+ *   feats / masks / max_regions / out_counts / out_src / out_total / workspace: as rvo_mask_pool
+ *   db        [dev] bf16 tiled DB storage (see "DB storage layout"), d_pad = D rounded up to 64; the kept
+ *             regions land, compacted in (image, region) order, at DB rows db_row0, db_row0 + 1, ...;
+ *             capacity needed: db_row0 + B * min(M, max_regions) rows
+ *   out_f32   [dev] float32 [B*M, D] optional copy of the embeddings (as rvo_mask_pool's `out`); may be NULL
+ * Returns RVO_E_UNSUPPORTED for shapes outside the tensor-core kernel (D % 128 != 0, more than 64 regions
+ * per image, D/128 * M_pad > 512, more than 1024 patches): call rvo_mask_pool + rvo_normalize_rows instead.
+ * ---------------------------------------------------------------------------------------------- */
+int rvo_mask_pool_to_db(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
+                        int32_t max_regions, uint16_t* db, int64_t db_row0, float* out_f32, int32_t* out_counts,
+                        int32_t* out_src, int32_t* out_total, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2 — exact cosine top-k over one DB shard.

@@ -208,11 +208,10 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
             sp->seed_stride = 1;
             sp->n_levels = 0;
         } else {
-            // seed sample: ~1/32 of the shard, between 4k and 16k rows (a small shard — e.g. 1M rows over 8 GPUs — does not
-            // pay a 16k-row pre-pass; the looser threshold only adds a few thousand candidates per query)
-            long long seed_rows = n_rows / 32;
-            if (seed_rows < 4096) seed_rows = 4096;
-            if (seed_rows > kSeedRows) seed_rows = kSeedRows;
+            // seed sample: a fixed 16k rows whatever the shard size.  Survivors per scanned row = Q * k / seed_rows, so a
+            // smaller seed on a smaller shard (tried: n/32) makes the candidate appends, not HBM, the limit of the scan
+            // (1M x 1024 over 8 GPUs: scan 54 -> 116 us per shard with a 4k-row seed).
+            const long long seed_rows = kSeedRows;
             sp->seed_stride = supers / ((seed_rows + T - 1) / T);
             if (sp->seed_stride < 1) sp->seed_stride = 1;
             long long ratio = opt_final_ratio.load();
@@ -336,6 +335,30 @@ int rvo_mask_pool(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_
     if (rc) return rc;
     return launch_mask_pool(feats, masks, B, M, P, D, max_regions, out, out_counts, out_src, out_total, workspace,
                             workspace_bytes, sm, (cudaStream_t)stream);
+}
+
+int rvo_mask_pool_to_db(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
+                        int32_t max_regions, uint16_t* db, int64_t db_row0, float* out_f32, int32_t* out_counts,
+                        int32_t* out_src, int32_t* out_total, void* workspace, size_t workspace_bytes, void* stream) {
+    RVO_REQUIRE(feats && masks && db && out_counts && out_total && workspace, "mask_pool_to_db: null pointer");
+    RVO_REQUIRE(B > 0 && M > 0 && P > 0 && D > 0 && db_row0 >= 0, "mask_pool_to_db: bad shape B=%d M=%d P=%d D=%d row0=%lld", B,
+                M, P, D, (long long)db_row0);
+    RVO_REQUIRE(((uintptr_t)feats & 15) == 0 && ((uintptr_t)db & 15) == 0 && ((uintptr_t)masks & 3) == 0 &&
+                    (!out_f32 || ((uintptr_t)out_f32 & 15) == 0),
+                "mask_pool_to_db: feats/db/out must be 16-byte aligned, masks 4-byte aligned");
+    int sm = 0;
+    int rc = select_device_of(feats, &sm);
+    if (rc) return rc;
+    if (D % 128 != 0) {
+        set_error("mask_pool_to_db: D=%d is outside the fused kernel (D %% 128 != 0): use rvo_mask_pool + rvo_normalize_rows", D);
+        return RVO_E_UNSUPPORTED;
+    }
+    rc = launch_mask_pool(feats, masks, B, M, P, D, max_regions, out_f32, out_counts, out_src, out_total, workspace,
+                          workspace_bytes, sm, (cudaStream_t)stream, db, db_row0);
+    if (rc == RVO_E_UNSUPPORTED)
+        set_error("mask_pool_to_db: shape B=%d M=%d P=%d D=%d is outside the fused kernel: use rvo_mask_pool + rvo_normalize_rows",
+                  B, M, P, D);
+    return rc;
 }
 
 size_t rvo_search_workspace_bytes(int64_t n_rows, int32_t d, int32_t nq, int32_t k) {

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) mask_scale_kernel(float* __restrict__ out
 
 int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int lim, float* out,
                         int32_t* out_counts, int32_t* out_src, int32_t* out_total, int* img_base, int* area,
-                        unsigned int* ticket, int sm_count, cudaStream_t stream);
+                        unsigned int* ticket, int sm_count, cudaStream_t stream, uint16_t* db, long long db_row0);
 
 size_t mask_pool_workspace_bytes(int B, int M, int P, int D) {
     (void)D;
@@ -207,7 +207,7 @@ size_t mask_pool_workspace_bytes(int B, int M, int P, int D) {
 
 int launch_mask_pool(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int max_regions, float* out,
                      int32_t* out_counts, int32_t* out_src, int32_t* out_total, void* workspace, size_t workspace_bytes,
-                     int sm_count, cudaStream_t stream) {
+                     int sm_count, cudaStream_t stream, uint16_t* db, long long db_row0) {
     if (D % kSlab != 0) {
         set_error("mask_pool: D=%d must be a multiple of %d", D, kSlab);
         return RVO_E_INVALID;
@@ -233,9 +233,10 @@ int launch_mask_pool(const uint16_t* feats, const uint8_t* masks, int B, int M, 
     if (!g_force_cuda_core_pool) {
         // tensor-core path (mask_pool_tc.cu) whenever the image's whole output fits TMEM
         const int rc = launch_mask_pool_tc(feats, masks, B, M, P, D, lim, out, out_counts, out_src, out_total, img_base,
-                                           area, ticket, sm_count, stream);
+                                           area, ticket, sm_count, stream, db, db_row0);
         if (rc <= 0) return rc;
     }
+    if (db) return RVO_E_UNSUPPORTED;   // the fused ingest exists on the tensor-core kernel only
     const int p_pad = (P + 7) & ~7;
     const size_t smem = (size_t)P * kSlab * 4 + (size_t)kPoolWarps * p_pad * 2;
     if (smem > 220 * 1024) {

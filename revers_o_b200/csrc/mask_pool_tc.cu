@@ -40,7 +40,9 @@ struct PoolTcParams {
     int* area;             // [B*M] set patches per region, 0 for regions at or beyond the cap
     int* out_total;        // sum of counts
     unsigned int* arrived; // grid-wide arrival counter (zeroed by the launcher): CTAs that have published their counts
-    float* out;
+    float* out;            // fp32 embeddings [B*M, D], compacted (may be null when db is given)
+    uint16_t* db;          // optional: tiled bf16 DB storage receiving the same rows at db_row0 + output row (fused ingest)
+    long long db_row0;
     int* out_src;
     int B, M, P, D, lim, n_pad, num_pc, num_slab, num_stages;
     uint32_t off_b, b_buf_bytes, off_misc;
@@ -359,10 +361,26 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
                             if (j < ns) {
                                 tmem_ld_wait();
                                 if (jj < 3 && j + 1 < ns) tmem_ld_x16(taddr + (uint32_t)((s0 + j + 1) * n_pad + m0), v[(jj + 1) & 1]);
-                                float* __restrict__ o = gout + (size_t)(s0 + j0) * 128 + jj * 128;
+                                if (p.out) {
+                                    float* __restrict__ o = gout + (size_t)(s0 + j0) * 128 + jj * 128;
 #pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (rr[i] >= 0) __stcs(o + (size_t)rr[i] * (size_t)p.D, __uint_as_float(v[jj & 1][i]) * sc[i]);
+                                    for (int i = 0; i < 16; ++i)
+                                        if (rr[i] >= 0) __stcs(o + (size_t)rr[i] * (size_t)p.D, __uint_as_float(v[jj & 1][i]) * sc[i]);
+                                }
+                                if (p.db) {
+                                    // tiled DB storage [row/128][col/64][row%128][col%64]: the warp's 32 channels of one
+                                    // region are 64 contiguous bytes
+                                    const int col = (s0 + j) * 128 + ch;
+                                    const size_t nk = (size_t)(p.D >> 6);
+                                    uint16_t* __restrict__ t0 = p.db + (size_t)(col >> 6) * (kTileRows * kTileCols) + (col & 63);
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i)
+                                        if (rr[i] >= 0) {
+                                            const long long row = p.db_row0 + rr[i];
+                                            t0[((size_t)(row >> 7) * nk) * (kTileRows * kTileCols) + (size_t)(row & 127) * kTileCols] =
+                                                __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(v[jj & 1][i]) * sc[i]));
+                                        }
+                                }
                             }
                         }
                     }
@@ -487,7 +505,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 // CUDA-core kernel — same results), <0 on error.
 int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int lim, float* out,
                         int32_t* out_counts, int32_t* out_src, int32_t* out_total, int* img_base, int* area,
-                        unsigned int* ticket, int sm_count, cudaStream_t stream) {
+                        unsigned int* ticket, int sm_count, cudaStream_t stream, uint16_t* db, long long db_row0) {
     const int n_pad = (M + 15) / 16 * 16;
     const int num_pc = (P + 63) / 64, num_slab = D / 128;
     if (D % 128 != 0 || n_pad > 64 || num_slab * n_pad > 512) return 1;
@@ -531,6 +549,8 @@ int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int 
     p.out_total = out_total;
     p.arrived = ticket;
     p.out = out;
+    p.db = db;
+    p.db_row0 = db_row0;
     p.out_src = out_src;
     p.B = B; p.M = M; p.P = P; p.D = D; p.lim = lim;
     p.n_pad = n_pad; p.num_pc = num_pc; p.num_slab = num_slab; p.num_stages = stages;

@@ -125,6 +125,44 @@ def mask_pool(feats: torch.Tensor, masks: torch.Tensor, max_regions: int = 0):
     return out, counts, src, total
 
 
+def mask_pool_to_db(feats: torch.Tensor, masks: torch.Tensor, db: torch.Tensor, row0: int, max_regions: int = 0,
+                    want_f32: bool = False):
+    """K1 fused with ingest: the kept regions' normalised embeddings go straight into the tiled bf16 DB at rows
+    row0, row0+1, ... (compacted, (image, region) order).  Returns (counts int32 [B], src int32 [B*M], total int32 [1],
+    f32 [B*M, D] | None) — device tensors, no host sync.  Shapes outside the tensor-core kernel take two CUDA calls
+    (rvo_mask_pool + rvo_normalize_rows, one host sync) with the same result."""
+    require_cuda(feats, "feats")
+    require_cuda(masks, "masks")
+    require_cuda(db, "db")
+    assert feats.dtype == torch.bfloat16 and feats.is_contiguous() and feats.dim() == 3
+    assert masks.dtype == torch.uint8 and masks.is_contiguous() and masks.dim() == 3
+    assert db.dtype == torch.bfloat16 and db.is_contiguous() and db.dim() == 4
+    B, P, D = feats.shape
+    M = masks.shape[1]
+    assert masks.shape == (B, M, P) and db.shape[1] * TILE_COLS == d_pad_of(D)
+    lim = M if max_regions <= 0 else min(M, max_regions)
+    if row0 + B * lim > db_capacity(db):
+        raise RvoError(f"mask_pool_to_db: DB capacity {db_capacity(db)} rows < row0 {row0} + {B * lim}")
+    dev = feats.device
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    src = torch.empty((B * M,), dtype=torch.int32, device=dev)
+    total = torch.empty((1,), dtype=torch.int32, device=dev)
+    f32 = torch.empty((B * M, D), dtype=torch.float32, device=dev) if want_f32 else None
+    lib = _lib.load()
+    nbytes = lib.rvo_mask_pool_workspace_bytes(B, M, P, D)
+    ws = workspace(dev, nbytes)
+    rc = lib.rvo_mask_pool_to_db(_ptr(feats), _ptr(masks), B, M, P, D, int(max_regions), _ptr(db), int(row0), _ptr(f32),
+                                 _ptr(counts), _ptr(src), _ptr(total), _ptr(ws), nbytes, _stream(dev))
+    if rc == _lib.RVO_E_UNSUPPORTED:
+        out, counts, src, total = mask_pool(feats, masks, max_regions)
+        t = int(total.item())          # this (rare-shape) route synchronises: only the kept rows may be written
+        if t:
+            normalize_rows(out[:t], db=db, row0=row0)
+        return counts, src, total, (out if want_f32 else None)
+    check(rc, "rvo_mask_pool_to_db")
+    return counts, src, total, f32
+
+
 def search_topk(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, k: int,
                 score_threshold: float | None = None, id_offset: int = 0, out=None):
     """K2.  db: tiled bf16 DB storage (`db_alloc`) holding >= n_rows normalised rows, queries f32 [nq, d].

@@ -243,6 +243,35 @@ class B200VectorDB:
             self._write_rows(c, rows, v)
             c.n = len(c.ids)
 
+    def ingest_regions(self, collection_name: str, feats: torch.Tensor, masks: torch.Tensor, payload_fn=None,
+                       max_regions: int = 0):
+        """Batched ingest: patch features [B,P,D] bf16 + patch-grid masks [B,M,P] uint8 on the GPU ->
+        every non-empty region's mask-pooled, L2-normalised embedding appended to the collection by ONE kernel that writes
+        bf16 rows straight into the tiled DB (no fp32 embeddings in HBM, no python float lists, core_system.py:363-408 +
+        :596-622).  `payload_fn(image_index, region_index) -> (id, payload)`; default: uuid4 id, {"image": b, "region": m}.
+        Returns the number of rows appended."""
+        import uuid
+        with self._lock:
+            c = self._coll(collection_name)
+            B, P, D = feats.shape
+            M = masks.shape[1]
+            if D != c.dim:
+                raise RvoError(f"Wrong input: Vector dimension error: expected dim: {c.dim}, got {D}")
+            lim = M if max_regions <= 0 else min(M, max_regions)
+            row0 = len(c.ids)
+            c.reserve(row0 + B * lim)
+            counts, src, total, _ = ops.mask_pool_to_db(feats, masks, c.vectors, row0, max_regions)
+            m = int(total.item())                      # the one host sync of an ingest batch
+            origin = src[:m].cpu().numpy()
+            for o in origin:
+                b, r = divmod(int(o), M)
+                pid, pay = payload_fn(b, r) if payload_fn else (str(uuid.uuid4()), {"image": b, "region": r})
+                c.row_of[pid] = len(c.ids)
+                c.ids.append(pid)
+                c.payloads.append(pay)
+            c.n = len(c.ids)
+            return m
+
     def find_near_duplicates(self, collection_name: str, threshold: float = 0.95, max_pairs: int = 1 << 22):
         """All pairs of stored points with cosine >= threshold (BASELINE config 4: keyframe near-duplicate self-join;
         generalises `score_threshold`, core_system.py:663).  Returns (list of (id_a, id_b), scores float32 [n])."""

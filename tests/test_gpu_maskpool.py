@@ -99,3 +99,56 @@ def test_config2_full_shape(dev):
         got = out[lo: lo + rc[j]].cpu().numpy()
         ref = emb[sum(rc[:j]): sum(rc[:j]) + rc[j]]
         assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)) < 1e-3
+
+
+# ---- K1 fused with ingest: embeddings straight into the tiled bf16 DB ------------------------------------------------
+@pytest.mark.parametrize("B,M,grid,D,row0", [(7, 64, 24, 1024, 0), (200, 20, 24, 256, 1000), (3, 50, 16, 1280, 128)])
+def test_mask_pool_to_db_matches_two_step_ingest(dev, B, M, grid, D, row0):
+    """rvo_mask_pool_to_db == rvo_mask_pool followed by rvo_normalize_rows into the DB (what qdrant's COSINE upsert of the
+    reference does with the region embeddings, core_system.py:608-621): same rows, at most one bf16 ulp apart."""
+    from revers_o_b200 import ops, synth
+    feats, masks = synth.make_maskpool_inputs(B, M, grid, D, seed=5 + B, device=dev, n_empty=2)
+    cap = row0 + B * M
+    db = ops.db_alloc(cap, D, dev)
+    counts, src, total, f32 = ops.mask_pool_to_db(feats, masks, db, row0, want_f32=True)
+    out, counts2, src2, total2 = ops.mask_pool(feats, masks)
+    torch.cuda.synchronize()
+    t = int(total.item())
+    assert t == int(total2.item()) and torch.equal(counts, counts2) and torch.equal(src[:t], src2[:t])
+    got = ops.untile_rows(db, cap, D)[row0: row0 + t].float()
+    ref_db = ops.db_alloc(cap, D, dev)
+    ops.normalize_rows(out[:t].contiguous(), db=ref_db, row0=row0)
+    ref = ops.untile_rows(ref_db, cap, D)[row0: row0 + t].float()
+    assert torch.max(torch.abs(got - ref)).item() <= 2 ** -8 * float(ref.abs().max())      # one bf16 ulp at most
+    assert (got != ref).float().mean().item() < 1e-3
+    assert torch.allclose(f32[:t], out[:t], atol=1e-6)
+    emb, rc, _ = O.mask_pool(feats.float().cpu().numpy(), masks.cpu().numpy())
+    assert np.max(np.abs(got.cpu().numpy() - O.round_to_bf16(emb))) <= 2 ** -8
+    assert float(ops.untile_rows(db, cap, D)[:row0].abs().sum()) == 0.0                      # rows before row0 untouched
+
+
+def test_ingest_regions_then_search(dev):
+    """Batched ingest through the vector DB, then every stored region finds itself (score ~1) with its own payload."""
+    from revers_o_b200 import ops, synth
+    from revers_o_b200.vector_db import B200VectorDB, models
+    B, M, grid, D = 12, 16, 24, 1024
+    feats, masks = synth.make_maskpool_inputs(B, M, grid, D, seed=3, device=dev, n_empty=1)
+    vdb = B200VectorDB(device=dev)
+    vdb.recreate_collection("r", vectors_config=models.VectorParams(size=D, distance=models.Distance.COSINE))
+    n1 = vdb.ingest_regions("r", feats[:5].contiguous(), masks[:5].contiguous())
+    n2 = vdb.ingest_regions("r", feats[5:].contiguous(), masks[5:].contiguous(),
+                            payload_fn=lambda b, m: (f"img{b + 5}-r{m}", {"image": b + 5, "region": m}))
+    assert n1 == 5 * (M - 1) and n2 == 7 * (M - 1) and vdb.count("r") == n1 + n2
+    out, counts, src, total = ops.mask_pool(feats, masks)
+    q = out[: n1 + n2]
+    ids, sc, cnt = vdb.search_batch("r", q, 1)
+    assert np.all(sc[:, 0] > 0.999)
+    same = ids[:, 0] == np.arange(n1 + n2)
+    assert same.mean() > 0.9
+    for j in np.nonzero(~same)[0]:      # two regions of an image may be the same rectangle: identical embeddings, lower id wins
+        assert ids[j, 0] < j and torch.allclose(out[int(ids[j, 0])], out[int(j)], atol=1e-6)
+    j = int(np.nonzero(same)[0][-1])
+    hit = vdb.search("r", q[j].cpu().numpy(), limit=1)[0]
+    b, m = divmod(int(src[j]), M)
+    expect_id = f"img{b}-r{m}" if j >= n1 else None
+    assert hit.payload == {"image": b, "region": m} and (expect_id is None or hit.id == expect_id)
