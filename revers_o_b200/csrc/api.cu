@@ -19,6 +19,7 @@ int launch_selfjoin(const uint16_t* db, long long n_rows, int d, long long row_l
                     cudaStream_t stream);
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_use_pdl{0};   // measured: no gain on configs[1] (0.487 vs 0.478 ms), 30 us WORSE on configs[0]
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -292,6 +293,7 @@ int rvo_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "final_ratio")) opt_final_ratio = value;
     else if (!strcmp(name, "time_scan")) opt_time_scan = value;
     else if (!strcmp(name, "pool_path")) g_force_cuda_core_pool = value == 1;
+    else if (!strcmp(name, "pdl")) g_use_pdl = value;
     else if (!strcmp(name, "pool_trace")) g_pool_trace = (void*)(uintptr_t)value;
     else {
         set_error("unknown option '%s'", name);

@@ -44,6 +44,7 @@ int select_device_of(const void* dev_ptr, int* sm_count);
 
 // Launch with programmatic stream serialization (see ptx.cuh): the kernel must call grid_dependency_wait() before it
 // reads or writes global memory.
+extern std::atomic<long long> g_use_pdl;   // option "pdl": 1 = programmatic dependent launch along the chain; default 0 (measured slower)
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                      Args... args) {
@@ -57,7 +58,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_use_pdl.load() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

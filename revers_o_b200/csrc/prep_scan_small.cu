@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(256) scan_small_kernel(const uint4* __restrict
     const int lane = threadIdx.x & 31;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // the normalised queries come from the previous kernel
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (programmatic dependent launch, see ptx.cuh)
 
     float qr[NQ][CPL][8];
 #pragma unroll
@@ -198,8 +200,8 @@ static int launch_small_t(const uint16_t* db, long long n_rows, int d_pad, const
     long long want = (n_rows + 15) / 16;  // 8 warps x 2 rows per block per iteration
     long long grid = (long long)sm_count * per_sm;
     if (grid > want) grid = want;
-    scan_small_kernel<NQ, CPL><<<(unsigned)grid, 256, 0, stream>>>((const uint4*)db, n_rows, d_pad / kTileCols, d_pad / 8,
-                                                                  qn, qn_ld, out, out_ld);
+    RVO_CUDA(launch_pdl(scan_small_kernel<NQ, CPL>, dim3((unsigned)grid), dim3(256), 0, stream, (const uint4*)db, n_rows,
+                        d_pad / kTileCols, d_pad / 8, qn, qn_ld, out, out_ld));
     RVO_LAUNCHED();
     return RVO_OK;
 }

@@ -357,7 +357,7 @@ int launch_scan_tc2(int mode, const uint16_t* db, long long n_rows, long long su
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see ptx.cuh grid_dependency_wait
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 2;
+    cfg.numAttrs = g_use_pdl.load() ? 2 : 1;
     if (mode == kModeDense) {
         RVO_CUDA(cudaFuncSetAttribute(scan_tc2_kernel<kModeDense>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));

@@ -72,6 +72,8 @@ __device__ __forceinline__ int next_pow2(int x) {
 // grid (num_chunks, nq): chunk c of query q -> its K best keys, sorted descending, zero padded.
 __global__ void __launch_bounds__(kSelThreads) chunk_topk_kernel(const ChunkTopkArgs a) {
     __shared__ unsigned long long s[kChunk];
+    grid_dependency_wait();      // scores / keys come from the previous kernel of the chain
+    grid_launch_dependents();
     const int q = blockIdx.y;
     const long long c0 = (long long)blockIdx.x * kChunk;
     long long n = a.n_fixed;
@@ -185,6 +187,8 @@ __device__ __forceinline__ void emit_overflow(const FinalArgs& a, int q) {
 __global__ void __launch_bounds__(512) final_kernel(const FinalArgs a) {
     __shared__ unsigned long long s[1024];
     __shared__ int s_flag;
+    grid_dependency_wait();
+    grid_launch_dependents();
     const int q = blockIdx.x;
     const int K2 = a.K2;
     const unsigned long long* src = a.top + (size_t)q * (size_t)a.top_ld;
@@ -616,13 +620,13 @@ __global__ void __launch_bounds__(256) merge_kernel(const int64_t* ids, const fl
 // ---- host wrappers ------------------------------------------------------------------------------
 int launch_chunk_topk(const ChunkTopkArgs& a, int num_chunks, int nq, cudaStream_t stream) {
     if (num_chunks <= 0 || nq <= 0) return RVO_OK;
-    chunk_topk_kernel<<<dim3(num_chunks, nq), kSelThreads, 0, stream>>>(a);
+    RVO_CUDA(launch_pdl(chunk_topk_kernel, dim3(num_chunks, nq), dim3(kSelThreads), 0, stream, a));
     RVO_LAUNCHED();
     return RVO_OK;
 }
 
 int launch_final(const FinalArgs& a, int nq, cudaStream_t stream) {
-    final_kernel<<<nq, 512, 0, stream>>>(a);
+    RVO_CUDA(launch_pdl(final_kernel, dim3(nq), dim3(512), 0, stream, a));
     RVO_LAUNCHED();
     return RVO_OK;
 }

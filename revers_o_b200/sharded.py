@@ -86,6 +86,29 @@ class ShardedIndex:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self._bufs: dict = {}
 
+    @classmethod
+    def from_disk(cls, path: str, collection_name: str, device, rank: int | None = None, world: int | None = None,
+                  group=None, chunk_blocks: int = 4096):
+        """Load this rank's row shard of a saved collection (`B200VectorDB.save`) straight to its GPU: the tiled file is
+        memory-mapped and only the rank's 128-row blocks are read, `chunk_blocks` blocks at a time through a pinned
+        staging buffer (replaces qdrant's sqlite + pickle load behind core_system.py:90-119)."""
+        from .vector_db import read_shard_blocks
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+        view, n_local, row0, dim = read_shard_blocks(path, collection_name, world, rank)
+        dev = torch.device(device)
+        db = ops.db_alloc(max(n_local, 1) if view.shape[0] == 0 else view.shape[0] * ops.TILE_ROWS, dim, dev)
+        if view.shape[0]:
+            stage = torch.empty((min(chunk_blocks, view.shape[0]),) + tuple(view.shape[1:]), dtype=torch.int16).pin_memory()
+            for b0 in range(0, view.shape[0], chunk_blocks):
+                b1 = min(view.shape[0], b0 + chunk_blocks)
+                stage[: b1 - b0].numpy()[...] = view[b0:b1]
+                db[b0:b1].copy_(stage[: b1 - b0].view(torch.bfloat16), non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()      # the staging buffer is reused by the next chunk
+        return cls(db, n_local, dim, row0, group)
+
     def search_local(self, queries: torch.Tensor, k: int, score_threshold=None):
         return ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset)
 

@@ -149,8 +149,9 @@ class B200VectorDB:
     # ---- batched entry point (new) -------------------------------------------------------------
     def search_batch(self, collection_name: str, queries, limit: int = 10, score_threshold: float | None = None,
                      as_device: bool = False):
-        """queries: [Q, D] float32 (numpy / torch, host or device).  Returns (ids [Q,k] int64 row numbers,
-        scores [Q,k] float32, counts [Q] int32); numpy unless `as_device`."""
+        """queries: [Q, D] float32 (numpy / torch, host or device; a PINNED torch CPU tensor is copied to the GPU without
+        a staging copy).  Returns (ids [Q,k] int64 row numbers, scores [Q,k] float32, counts [Q] int32); numpy unless
+        `as_device`."""
         with self._lock:
             c = self._coll(collection_name)
             n = c.n
@@ -167,6 +168,16 @@ class B200VectorDB:
             if as_device:
                 return ops.search_topk_exact(vectors, n, c.dim, qd, k, score_threshold)
             io = self._io_plan(qd.shape[0], c.dim, k)
+        elif (isinstance(queries, torch.Tensor) and queries.is_pinned() and queries.dtype == torch.float32
+              and queries.dim() == 2 and queries.is_contiguous()):
+            # caller-owned pinned host memory: DMA straight from it, no staging copy
+            if queries.shape[1] != c.dim:
+                raise RvoError(f"Wrong input: Vector dimension error: expected dim: {c.dim}, got {queries.shape[1]}")
+            io = self._io_plan(queries.shape[0], c.dim, k)
+            io.q_dev.copy_(queries, non_blocking=True)
+            qd = io.q_dev
+            if as_device:
+                return ops.search_topk_exact(vectors, n, c.dim, qd, k, score_threshold)
         else:
             qh = queries.detach().cpu().numpy() if isinstance(queries, torch.Tensor) else queries
             qh = np.ascontiguousarray(qh, dtype=np.float32)
@@ -378,6 +389,29 @@ class B200VectorDB:
                 j += 1
             ops.normalize_rows(src[i:j], db=c.vectors, row0=rows[i])
             i = j
+
+
+def read_shard_blocks(path: str, collection_name: str, world: int, rank: int):
+    """On-disk format, shard-wise: memory-map `<path>/<collection>.bf16` (the tiled storage as is) and
+    return (view int16 [blocks_of_this_rank, d_pad/64, 128, 64], n_local, first_global_row, dim) for rank `rank` of `world`
+    — whole 128-row blocks, the same split as `sharded.shard_bounds`.  Pure host code (numpy), no copy until the caller
+    reads the view; each GPU process of a box maps only its slice of the file."""
+    from .sharded import shard_bounds
+    with open(os.path.join(path, "meta.json")) as f:
+        meta = json.load(f)
+    m = meta.get("collections", {}).get(collection_name)
+    if m is None:
+        raise RvoError(f"Collection {collection_name} not found")
+    n, dim, d_pad = int(m["n"]), int(m["dim"]), int(m["d_pad"])
+    nk = d_pad // ops.TILE_COLS
+    blocks = (n + ops.TILE_ROWS - 1) // ops.TILE_ROWS
+    lo, hi = shard_bounds(n, world, rank)
+    b0, b1 = lo // ops.TILE_ROWS, (hi + ops.TILE_ROWS - 1) // ops.TILE_ROWS
+    if blocks == 0 or hi <= lo:
+        return np.zeros((0, nk, ops.TILE_ROWS, ops.TILE_COLS), np.int16), 0, lo, dim
+    mm = np.memmap(os.path.join(path, f"{collection_name}.bf16"), dtype=np.int16, mode="r",
+                   shape=(blocks, nk, ops.TILE_ROWS, ops.TILE_COLS))
+    return mm[b0:b1], hi - lo, lo, dim
 
 
 def _get(p, name):

@@ -156,3 +156,42 @@ def test_vector_db_upsert_overwrite_and_batch(dev):
     assert sorted(map(sorted, dup)) == [["p3", "p7"]] and dsc[0] > 0.999
     with pytest.raises(Exception):
         db.upsert("c", [models.PointStruct(id="bad", vector=[1.0, 2.0], payload=None)])
+
+
+def test_saved_collection_loads_shard_wise(dev, tmp_path):
+    """save() -> ShardedIndex.from_disk for each of 3 virtual ranks -> per-shard search + K3 merge == search of the whole DB."""
+    import numpy as np
+    from revers_o_b200 import ops
+    from revers_o_b200.sharded import ShardedIndex
+    from revers_o_b200.vector_db import B200VectorDB, models
+    rs = np.random.RandomState(0)
+    n, d, nq, k = 5000, 256, 9, 20
+    vdb = B200VectorDB(device=dev)
+    vdb.recreate_collection("c", vectors_config=models.VectorParams(size=d, distance=models.Distance.COSINE))
+    vdb.upsert_batch("c", [f"id{i}" for i in range(n)], rs.randn(n, d).astype(np.float32))
+    vdb.save(str(tmp_path))
+    q = torch.from_numpy(rs.randn(nq, d).astype(np.float32)).to(dev)
+    fi, fs, fc = vdb.search_batch("c", q, k, as_device=True)
+    parts = []
+    for r in range(3):
+        idx = ShardedIndex.from_disk(str(tmp_path), "c", dev, rank=r, world=3)
+        parts.append(idx.search_local(q, k))
+    mi, ms, mc = ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]),
+                                torch.stack([p[2] for p in parts]), k)
+    torch.cuda.synchronize()
+    assert torch.equal(mi, fi) and torch.equal(mc, fc) and torch.allclose(ms, fs, atol=1e-6)
+
+
+def test_search_batch_input_kinds_agree(dev):
+    """numpy, pageable torch, PINNED torch (no staging copy) and device tensors give the same answer."""
+    from revers_o_b200.vector_db import B200VectorDB, models
+    rs = np.random.RandomState(1)
+    n, d, nq, k = 3000, 128, 7, 5
+    vdb = B200VectorDB(device=dev)
+    vdb.recreate_collection("c", vectors_config=models.VectorParams(size=d, distance=models.Distance.COSINE))
+    vdb.upsert_batch("c", list(range(n)), rs.randn(n, d).astype(np.float32))
+    q = rs.randn(nq, d).astype(np.float32)
+    ref = vdb.search_batch("c", q, k)
+    for other in (torch.from_numpy(q), torch.from_numpy(q).pin_memory(), torch.from_numpy(q).to(dev)):
+        got = vdb.search_batch("c", other, k)
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got))

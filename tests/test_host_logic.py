@@ -74,3 +74,31 @@ def test_status_string_convention_without_gpu(tmp_path):
     assert r.create_database(str(tmp_path / "nope"), "d").startswith("❌ Folder not found")
     r.request_stop()
     assert r._stop_requested is True
+
+
+def test_read_shard_blocks_covers_the_file_exactly(tmp_path):
+    """Shard-wise view of the on-disk tiled format: the ranks' block ranges partition the file, row counts add up, the first
+    global row of a rank is the end of the previous one (host logic only — no GPU)."""
+    import json
+    import numpy as np
+    from revers_o_b200.vector_db import read_shard_blocks
+    n, dim, d_pad = 1000, 100, 128
+    blocks, nk = (n + 127) // 128, d_pad // 64
+    raw = np.arange(blocks * nk * 128 * 64, dtype=np.int64).astype(np.int16).reshape(blocks, nk, 128, 64)
+    raw.tofile(tmp_path / "c.bf16")
+    (tmp_path / "meta.json").write_text(json.dumps({"format": "revers_o_b200/1", "collections": {
+        "c": {"dim": dim, "d_pad": d_pad, "n": n, "distance": "Cosine", "blocks": blocks}}}))
+    for world in (1, 2, 3, 8, 11):
+        got, rows, nxt = [], 0, 0
+        for r in range(world):
+            view, n_local, row0, d = read_shard_blocks(str(tmp_path), "c", world, r)
+            assert d == dim and row0 == nxt and (row0 % 128 == 0 or n_local == 0)
+            assert view.shape[0] == (n_local + 127) // 128
+            got.append(np.asarray(view))
+            rows += n_local
+            nxt = row0 + n_local
+        assert rows == n and np.array_equal(np.concatenate(got), raw)
+    import pytest
+    from revers_o_b200._lib import RvoError
+    with pytest.raises(RvoError):
+        read_shard_blocks(str(tmp_path), "missing", 2, 0)
