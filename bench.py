@@ -67,6 +67,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone with all host threads
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = str(os.cpu_count())
     import numpy as np
     from oracle import reverso_oracle as O
     n, d, nq, k, desc = WORKLOADS[args.workload]

@@ -326,3 +326,39 @@ def test_overflow_beyond_capacity_falls_back_exactly(dev):
     ids2, sc2, cnt2 = ops.search_topk_exact(db, n, d, q, k)
     torch.cuda.synchronize()
     assert_topk_match(ids2.cpu().numpy(), sc2.cpu().numpy(), cnt2.cpu().numpy(), _oracle(db, n, d, q, k), k, TOL, "fallback")
+
+
+def test_config3_shard_size_against_fp32_reference(dev):
+    """One configs[3] shard at full size (12.5M x 1280 bf16 = 32 GB, the per-GPU share of the 100M x 1280 DB at 8 GPUs):
+    the oracle cannot hold it, so the check is a plain fp32 GPU reference of the same definition (normalise the query,
+    fp32 dot with every stored row, descending top-k) computed chunk by chunk, on the bandwidth-regime batch (Q = 16),
+    the Q = 1 path and a slice of the tensor-regime batch (Q = 4096).  Tolerances as everywhere: scores 1e-3, id sets
+    equal except ties within 1e-3."""
+    from revers_o_b200 import ops, synth
+    if torch.cuda.get_device_properties(dev).total_memory < 100e9:
+        pytest.skip("needs a full-size B200")
+    n, d, k = 12_500_000, 1280, 100
+    q_all = synth.make_queries(4096, d, seed=7, device=dev)
+    db = synth.make_db(n, d, q_all, n_plant=16, seed=2000, device=dev)
+    qn = q_all[:16] / q_all[:16].norm(dim=1, keepdim=True)
+    best_s = torch.full((16, 0), 0.0, device=dev)
+    best_i = torch.zeros((16, 0), dtype=torch.int64, device=dev)
+    nb = db.shape[0]
+    for b0 in range(0, nb, 2048):                                   # 262k rows per chunk
+        b1 = min(nb, b0 + 2048)
+        rows = db[b0:b1].permute(0, 2, 1, 3).reshape((b1 - b0) * 128, -1)[:, :d].float()
+        s = qn @ rows.T
+        valid = (torch.arange(b0 * 128, b1 * 128, device=dev) < n)
+        s[:, ~valid] = -2.0
+        cs, ci = torch.cat([best_s, s], 1), torch.cat([best_i, torch.arange(b0 * 128, b1 * 128, device=dev).expand(16, -1)], 1)
+        top = cs.topk(k, dim=1)
+        best_s, best_i = top.values, torch.gather(ci, 1, top.indices)
+        del rows, s, cs, ci
+    ref = [(best_i[i].cpu().numpy(), best_s[i].cpu().numpy()) for i in range(16)]
+    ids, sc, cnt = _run(db, n, d, q_all[:16].contiguous(), k)
+    assert_topk_match(ids, sc, cnt, ref, k, TOL, "cfg3-q16")
+    ids1, sc1, cnt1 = _run(db, n, d, q_all[:1].contiguous(), k)
+    assert_topk_match(ids1, sc1, cnt1, ref[:1], k, TOL, "cfg3-q1")
+    idsL, scL, cntL = _run(db, n, d, q_all, k)
+    assert np.all(cntL == k) and np.all(np.diff(scL, axis=1) <= 1e-7)
+    assert_topk_match(idsL[:16], scL[:16], cntL[:16], ref, k, TOL, "cfg3-q4096")
