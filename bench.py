@@ -44,6 +44,7 @@ WORKLOADS = {
     "cfg3shardq16": (12_500_000, 1280, 16, 100, "configs[3] per-GPU shard, bandwidth regime: 12.5M x 1280, 16 queries"),
     "cfg3shardq64": (12_500_000, 1280, 64, 100, "configs[3] per-GPU shard, bandwidth regime: 12.5M x 1280, 64 queries"),
     "cfg3shardq1": (12_500_000, 1280, 1, 100, "configs[3] per-GPU shard, the reference's operating point: 12.5M x 1280, 1 query"),
+    "cfg1shard8": (125_000, 1024, 256, 100, "configs[1] per-GPU shard at 8 GPUs: 125k x 1024, 256 queries (fixed-chain diagnostics)"),
     "cfg1q1": (1_000_000, 1024, 1, 10, "configs[1] DB, the reference's operating point: 1M x 1024, 1 query, top-10"),
 }
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
@@ -206,6 +207,10 @@ def run_b200(args):
     q_dev = synth.make_queries(nq, d, seed=7, device=dev)
     db = synth.make_db(n_local, d, q_dev, n_plant=max(1, 128 // world), seed=1000 + rank, device=dev)
     index = ShardedIndex(db, n_local, d, lo)
+    exchange = "none"
+    if world > 1:
+        exchange = "peer-memory push fused into K2 (NVLink stores + epoch flags)" if (
+            args.exchange != "nccl" and index.enable_peer_exchange(nq, k)) else "NCCL all_gather_into_tensor"
     lib = _lib.load()
     for kv in filter(None, os.environ.get("RVO_OPTS", "").split(",")):  # tuning sweeps only (scripts/gpu_sweep.sh)
         name, val = kv.split("=")
@@ -274,6 +279,11 @@ def run_b200(args):
     value = nq / (ms_step / 1e3)
     counts_ok = bool((out[2] == k).all().item())
 
+    # N > 1: the same step without the exchange + merge (K2 on the local shard only), to show what the exchange costs
+    local_ms = None
+    if world > 1:
+        local_ms, _, _ = timed(lambda: index.search_local(q_dev, k), args.steps, 3)
+
     # ---- roofline: the dominant kernel (full-shard scan) ------------------------------------------------
     roofline, roofline_tensor = scan_rooflines(index, q_dev, k, ms_step, max(5, min(args.steps, 30)))
     small = nq <= _lib.RVO_SMALL_Q
@@ -323,6 +333,7 @@ def run_b200(args):
     # ---- north star series (BASELINE.json metric: 100M x 1280 at 1/2/4/8 GPUs): the 100M x 1280 DB does not fit
     # one GPU, so every rank holds ITS 12.5M-row shard of the 8-GPU layout (weak scaling: N = 8 IS configs[3]) ----
     north = None
+    index.disable_peer_exchange()
     if args.workload == "cfg1" and not args.no_north_star:
         del index, db
         if world == 1:
@@ -335,6 +346,8 @@ def run_b200(args):
         q_all = synth.make_queries(4096, ns_d, seed=7, device=dev)
         ns_db = synth.make_db(ns_n, ns_d, q_all, n_plant=16, seed=2000 + rank, device=dev)
         ns_index = ShardedIndex(ns_db, ns_n, ns_d, rank * ns_n)
+        if world > 1 and args.exchange != "nccl":
+            ns_index.enable_peer_exchange(4096, 100)
         for ns_q in (4096, 64, 16):
             qd_ = q_all[:ns_q].contiguous()
             # small batches: the first ~20 steps after the tensor-bound phase run up to 20 % slower (measured; clocks
@@ -353,6 +366,7 @@ def run_b200(args):
                 "queries": ns_q, "value": ns_q / (ns_ms / 1e3), "unit": "queries/s", "ms_per_step": ns_ms, "steps": ns_steps,
                 "results_ok": bool((ns_out[2] == 100).all().item()),
                 "roofline": r_t if ns_q >= 1024 else r_h})
+        ns_index.disable_peer_exchange()
         del ns_db, ns_index
         torch.cuda.empty_cache()
 
@@ -392,13 +406,13 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": desc, "rows": n, "dim": d, "queries": nq, "k": k, "rows_per_gpu": n_local,
-                       "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+                       "parallelism": f"row-shard x{world}" if world > 1 else "single GPU", "exchange": exchange,
                        "l2": f"inputs larger than L2: each step streams the {alg_bytes / 1e9:.2f} GB shard",
                        "path": "small-q fp32 scan" if small else "tcgen05 scan + fused threshold select + fp32 rescore"},
             "e2e": {"value": nq / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "api": "B200VectorDB.search_batch(pinned host tensor) -> numpy ids/scores/counts" if world == 1 else "pinned H2D + ShardedIndex.search + D2H"},
-            "gpu_launches": int(launches),
+                    "api": "B200VectorDB.search_batch(pinned host tensor) -> numpy ids/scores/counts" if world == 1 else "pinned H2D + ShardedIndex.search (K2 + exchange + K3) + D2H"},
+            "gpu_launches": int(launches), "local_shard_ms_per_step": local_ms,
             "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_hbm": roofline_hbm,
             "north_star": north, "mask_pool": pool, "cpu_baseline": cpu, "clocks": clocks,
             "results_ok": counts_ok,
@@ -419,6 +433,8 @@ def main():
     ap.add_argument("--sample-queries", type=int, default=8, help="queries per CPU step (bounded sample)")
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "push", "nccl"],
+                    help="N > 1: per-shard lists exchanged by the fused peer-memory push (default when available) or NCCL")
     ap.add_argument("--no-north-star", action="store_true", help="skip the 12.5M x 1280 rows/GPU north-star series")
     args = ap.parse_args()
     if args.impl == "reference":

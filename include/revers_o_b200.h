@@ -159,7 +159,9 @@ int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pa
  * No reference counterpart (the reference is single-process); semantics = K2 over the union.
  *   ids [dev] int64 [G, nq, k], scores [dev] float32 [G, nq, k], counts [dev] int32 [G, nq]
  *   (a count of -1 marks an overflowed shard list and propagates to out_counts)
- *   out_* as in rvo_search_topk.   G*k <= 4096.
+ *   every list must be ordered as rvo_search_topk emits it (score descending, ties by lower id) and global ids
+ *   must be unique across lists: the merge ranks each element by binary searches in the other lists.
+ *   out_* as in rvo_search_topk.   G <= 64, G*k <= 4096.
  * ---------------------------------------------------------------------------------------------- */
 int rvo_merge_topk(const int64_t* ids, const float* scores, const int32_t* counts,
                    int32_t G, int32_t nq, int32_t k,
@@ -171,6 +173,35 @@ int rvo_merge_topk(const int64_t* ids, const float* scores, const int32_t* count
 size_t rvo_packed_result_bytes(int32_t nq, int32_t k);
 int rvo_merge_topk_packed(const void* gathered, int64_t rank_stride_bytes, int32_t G, int32_t nq, int32_t k,
                           int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Peer-memory exchange for the row-sharded search: K2's last kernel stores each query's list straight into
+ * every peer GPU's exchange region over NVLink and the last CTA publishes an epoch flag; K3 waits for the G
+ * flags and merges.  Replaces the NCCL all-gather between rvo_search_topk and rvo_merge_topk_packed (same
+ * results; no collective launch).  No reference counterpart.
+ *   region: rvo_exchange_bytes(world, nq_max, k_max) bytes from rvo_exchange_alloc (a cudaMalloc allocation,
+ *           zeroed) on each rank; exported with rvo_exchange_export (64-byte CUDA IPC handle, exchanged by the
+ *           host, e.g. torch.distributed.all_gather_object) and mapped by every peer with rvo_exchange_import.
+ *   regions [host] array of `world` device pointers valid in THIS process: regions[rank] is the local region,
+ *           regions[g] the imported mapping of rank g's.
+ *   epoch   1, 2, 3, ... — the same value on every rank for the same search (every rank calls in the same
+ *           order); parity selects one of two slot sets, so a rank may run one search ahead of its peers.
+ * rvo_search_topk_push = rvo_search_topk with the result written to this rank's slot of every region; returns
+ * RVO_E_UNSUPPORTED for nq <= RVO_SMALL_Q or an empty shard (take the all-gather path on ALL ranks then).
+ * rvo_merge_topk_exchange = rvo_merge_topk over the local region once all `world` flags show `epoch`.
+ * ---------------------------------------------------------------------------------------------- */
+size_t rvo_exchange_bytes(int32_t world, int32_t nq_max, int32_t k_max);
+int rvo_exchange_alloc(size_t bytes, void** out_region);
+int rvo_exchange_free(void* region);
+int rvo_exchange_export(void* region, void* out_handle64);
+int rvo_exchange_import(const void* handle64, void** out_region);
+int rvo_exchange_unimport(void* region);
+int rvo_search_topk_push(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad,
+                         const float* queries, int32_t nq, int32_t k, float score_threshold, int64_t id_offset,
+                         void* const* regions, int32_t world, int32_t rank, int32_t nq_max, int32_t k_max, uint64_t epoch,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int rvo_merge_topk_exchange(const void* local_region, int32_t world, int32_t nq, int32_t k, int32_t nq_max, int32_t k_max,
+                            uint64_t epoch, int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Near-duplicate self-join (BASELINE.json config 4): all pairs (i, j), row_lo <= i < row_hi, i < j < n_rows,

@@ -29,6 +29,17 @@ PROTOTYPES = {
     "rvo_mask_pool_to_db": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_size_t, C.c_void_p]),
+    "rvo_exchange_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "rvo_exchange_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rvo_exchange_free": (C.c_int, [C.c_void_p]),
+    "rvo_exchange_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rvo_exchange_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rvo_exchange_unimport": (C.c_int, [C.c_void_p]),
+    "rvo_search_topk_push": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
+                                       C.c_int64, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
+                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rvo_merge_topk_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rvo_search_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "rvo_search_topk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                   C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -370,9 +370,9 @@ size_t rvo_search_workspace_bytes(int64_t n_rows, int32_t d, int32_t nq, int32_t
     return sp.bytes;
 }
 
-int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad_in, const float* queries, int32_t nq,
-                    int32_t k, float score_threshold, int64_t id_offset, int64_t* out_ids, float* out_scores,
-                    int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream_) {
+static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad_in, const float* queries, int32_t nq,
+                       int32_t k, float score_threshold, int64_t id_offset, int64_t* out_ids, float* out_scores,
+                       int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream_, const PushArgs* push) {
     cudaStream_t stream = (cudaStream_t)stream_;
     RVO_REQUIRE(queries && out_ids && out_scores && out_counts && workspace, "search_topk: null pointer");
     RVO_REQUIRE(n_rows >= 0 && d > 0 && nq > 0, "search_topk: bad shape n_rows=%lld d=%d nq=%d", (long long)n_rows, d, nq);
@@ -387,6 +387,11 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
     int rc = select_device_of(queries, &sm);
     if (rc) return rc;
 
+    if (push && (n_rows == 0 || nq <= RVO_SMALL_Q)) {
+        set_error("search_topk_push: the fused exchange needs a non-empty shard and nq > %d (use the all-gather path)",
+                  RVO_SMALL_Q);
+        return RVO_E_UNSUPPORTED;
+    }
     if (n_rows == 0) {
         const long long n = (long long)nq * k;
         fill_outputs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(out_ids, out_scores, out_counts, n, nq);
@@ -413,6 +418,7 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
     fa.out_ids = out_ids;
     fa.out_scores = out_scores;
     fa.out_counts = out_counts;
+    if (push) fa.push = *push;
 
     if (sp.small) {
         // exact fp32 scan -> dense scores -> chunked exact top-k (never overflows)
@@ -494,6 +500,119 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
         }
     }
     return RVO_OK;
+}
+
+int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad, const float* queries, int32_t nq,
+                    int32_t k, float score_threshold, int64_t id_offset, int64_t* out_ids, float* out_scores,
+                    int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    return search_impl(db, n_rows, d, d_pad, queries, nq, k, score_threshold, id_offset, out_ids, out_scores, out_counts,
+                       workspace, workspace_bytes, stream, nullptr);
+}
+
+// ---- peer-memory exchange ------------------------------------------------------------------------------
+// Region of one rank: [2 parities][world slots of slot_bytes] | flags u64 [2][world] | done u32 [2].  Slot g of a parity
+// receives rank g's packed result blob [ids | scores | counts] of one search; flag g its epoch.
+struct ExchangeLayout {
+    size_t slot_bytes, flags_off, done_off, bytes;
+};
+static ExchangeLayout exchange_layout(int world, int nq_max, int k_max) {
+    ExchangeLayout L;
+    L.slot_bytes = align_up(rvo_packed_result_bytes(nq_max, k_max), 256);
+    L.flags_off = 2 * (size_t)world * L.slot_bytes;
+    L.done_off = L.flags_off + 2 * (size_t)world * 8;
+    L.bytes = L.done_off + 64;
+    return L;
+}
+
+size_t rvo_exchange_bytes(int32_t world, int32_t nq_max, int32_t k_max) {
+    if (world < 1 || world > kMaxPeers || nq_max <= 0 || k_max <= 0 || k_max > RVO_MAX_K) return 0;
+    return exchange_layout(world, nq_max, k_max).bytes;
+}
+
+int rvo_exchange_alloc(size_t bytes, void** out_region) {
+    RVO_REQUIRE(out_region && bytes > 0, "exchange_alloc: bad argument");
+    void* p = nullptr;
+    RVO_CUDA(cudaMalloc(&p, bytes));       // a plain cudaMalloc allocation: the unit cudaIpcGetMemHandle exports
+    RVO_CUDA(cudaMemset(p, 0, bytes));
+    RVO_CUDA(cudaDeviceSynchronize());
+    *out_region = p;
+    return RVO_OK;
+}
+
+int rvo_exchange_free(void* region) {
+    if (region) RVO_CUDA(cudaFree(region));
+    return RVO_OK;
+}
+
+int rvo_exchange_export(void* region, void* out_handle64) {
+    RVO_REQUIRE(region && out_handle64, "exchange_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    RVO_CUDA(cudaIpcGetMemHandle(&h, region));
+    memcpy(out_handle64, &h, 64);
+    return RVO_OK;
+}
+
+int rvo_exchange_import(const void* handle64, void** out_region) {
+    RVO_REQUIRE(handle64 && out_region, "exchange_import: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    RVO_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *out_region = p;
+    return RVO_OK;
+}
+
+int rvo_exchange_unimport(void* region) {
+    if (region) RVO_CUDA(cudaIpcCloseMemHandle(region));
+    return RVO_OK;
+}
+
+int rvo_search_topk_push(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad, const float* queries, int32_t nq,
+                         int32_t k, float score_threshold, int64_t id_offset, void* const* regions, int32_t world,
+                         int32_t rank, int32_t nq_max, int32_t k_max, uint64_t epoch, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    RVO_REQUIRE(regions && world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world, "search_topk_push: bad world/rank");
+    RVO_REQUIRE(nq > 0 && nq <= nq_max && k > 0 && k <= k_max && epoch > 0, "search_topk_push: nq/k beyond the region's maxima");
+    for (int g = 0; g < world; ++g) RVO_REQUIRE(regions[g], "search_topk_push: null region %d", g);
+    const ExchangeLayout L = exchange_layout(world, nq_max, k_max);
+    const int par = (int)(epoch & 1);
+    PushArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.world = world;
+    pa.rank = rank;
+    pa.nq = nq;
+    pa.k = k;
+    pa.epoch = epoch;
+    for (int g = 0; g < world; ++g) {
+        unsigned char* base = (unsigned char*)regions[g];
+        pa.peer_slot[g] = base + ((size_t)par * world + rank) * L.slot_bytes;
+        pa.peer_flag[g] = (unsigned long long*)(base + L.flags_off) + (size_t)par * world + rank;
+    }
+    unsigned char* local = (unsigned char*)regions[rank];
+    pa.done = (unsigned int*)(local + L.done_off) + par;
+    unsigned char* slot = pa.peer_slot[rank];
+    int64_t* out_ids = (int64_t*)slot;
+    float* out_scores = (float*)(slot + (size_t)nq * k * 8);
+    int32_t* out_counts = (int32_t*)(slot + (size_t)nq * k * 12);
+    return search_impl(db, n_rows, d, d_pad, queries, nq, k, score_threshold, id_offset, out_ids, out_scores, out_counts,
+                       workspace, workspace_bytes, stream, &pa);
+}
+
+int rvo_merge_topk_exchange(const void* local_region, int32_t world, int32_t nq, int32_t k, int32_t nq_max, int32_t k_max,
+                            uint64_t epoch, int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream) {
+    RVO_REQUIRE(local_region && out_ids && out_scores && out_counts, "merge_topk_exchange: null pointer");
+    RVO_REQUIRE(world >= 2 && world <= kMaxPeers && nq > 0 && nq <= nq_max && k > 0 && k <= k_max && (long long)world * k <= 4096,
+                "merge_topk_exchange: bad shape");
+    int rc = select_device_of(local_region, nullptr);
+    if (rc) return rc;
+    const ExchangeLayout L = exchange_layout(world, nq_max, k_max);
+    const int par = (int)(epoch & 1);
+    const unsigned char* base = (const unsigned char*)local_region + (size_t)par * world * L.slot_bytes;
+    const unsigned long long* flags = (const unsigned long long*)((const unsigned char*)local_region + L.flags_off) + (size_t)par * world;
+    return launch_merge((const int64_t*)base, (const float*)(base + (size_t)nq * k * 8), (const int32_t*)(base + (size_t)nq * k * 12),
+                        (long long)(L.slot_bytes / 8), (long long)(L.slot_bytes / 4), (long long)(L.slot_bytes / 4), world, nq, k,
+                        out_ids, out_scores, out_counts, (cudaStream_t)stream, flags, epoch);
 }
 
 int rvo_padded_queries(int32_t nq, int32_t d) {

@@ -154,6 +154,47 @@ __device__ __forceinline__ void rescore_candidates(unsigned long long* s, int ha
     }
 }
 
+// ---- peer-memory exchange (PushArgs) ----------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// element i of query q's list (and, from thread 0, its count) into this rank's slot of every peer
+__device__ __forceinline__ void push_element(const PushArgs& pa, int q, int i, long long id, float score) {
+    const size_t e = (size_t)q * pa.k + i, nk = (size_t)pa.nq * pa.k;
+    for (int g = 0; g < pa.world; ++g) {
+        if (g == pa.rank) continue;
+        unsigned char* slot = pa.peer_slot[g];
+        ((long long*)slot)[e] = id;
+        ((float*)(slot + nk * 8))[e] = score;
+    }
+}
+__device__ __forceinline__ void push_count(const PushArgs& pa, int q, int count) {
+    const size_t nk = (size_t)pa.nq * pa.k;
+    for (int g = 0; g < pa.world; ++g)
+        if (g != pa.rank) ((int*)(pa.peer_slot[g] + nk * 12))[q] = count;
+}
+// Whole block, after the CTA's last store: the last CTA of the grid publishes the epoch in every peer's flag.  Each
+// thread's stores are fenced at system scope before the block barrier; thread 0's counter increment orders after them.
+__device__ __forceinline__ void push_complete(const PushArgs& pa) {
+    if (pa.world <= 1) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(pa.done, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence_system();
+            *pa.done = 0u;                     // ready for the next use of this parity (two searches later)
+            for (int g = 0; g < pa.world; ++g) st_release_sys_u64(pa.peer_flag[g], pa.epoch);
+        }
+    }
+}
+
 // emit: first k keys of the sorted list with score >= score_threshold (the reference's walk stops at the first score
 // below it; `score == threshold` is kept).  s_n must be 0 on entry; whole block.
 __device__ __forceinline__ void emit_topk(const unsigned long long* s, int n_sorted, const FinalArgs& a, int q, int* s_n) {
@@ -163,13 +204,20 @@ __device__ __forceinline__ void emit_topk(const unsigned long long* s, int n_sor
     for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
         const unsigned long long key = i < n_sorted ? s[i] : 0ull;
         const bool ok = key != 0ull && key_score(key) >= a.score_threshold;
-        oid[i] = ok ? (int64_t)key_row(key) + a.id_offset : -1;
-        osc[i] = ok ? key_score(key) : -__int_as_float(0x7f800000);
+        const long long id = ok ? (long long)key_row(key) + a.id_offset : -1;
+        const float sc = ok ? key_score(key) : -__int_as_float(0x7f800000);
+        oid[i] = id;
+        osc[i] = sc;
+        if (a.push.world > 1) push_element(a.push, q, i, id, sc);
         n_out_local += ok;
     }
     if (n_out_local) atomicAdd(s_n, n_out_local);
     __syncthreads();
-    if (threadIdx.x == 0) a.out_counts[q] = *s_n;
+    if (threadIdx.x == 0) {
+        a.out_counts[q] = *s_n;
+        if (a.push.world > 1) push_count(a.push, q, *s_n);
+    }
+    push_complete(a.push);
 }
 
 __device__ __forceinline__ void emit_overflow(const FinalArgs& a, int q) {
@@ -178,8 +226,13 @@ __device__ __forceinline__ void emit_overflow(const FinalArgs& a, int q) {
     for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
         oid[i] = -1;
         osc[i] = -__int_as_float(0x7f800000);
+        if (a.push.world > 1) push_element(a.push, q, i, -1, -__int_as_float(0x7f800000));
     }
-    if (threadIdx.x == 0) a.out_counts[q] = -1;
+    if (threadIdx.x == 0) {
+        a.out_counts[q] = -1;
+        if (a.push.world > 1) push_count(a.push, q, -1);
+    }
+    push_complete(a.push);
 }
 
 // grid (nq), 512 threads.  `top` holds the K2 best candidates of the query, sorted descending (small-Q path: exact fp32
@@ -555,66 +608,90 @@ int launch_select_final(const SelectArgs& a, const FinalArgs& f, int nq, cudaStr
 }
 
 // ---- K3: merge of per-shard lists -------------------------------------------------------------
+constexpr int kMaxMergeLists = 64;
 __device__ __forceinline__ bool before(float sa, long long ia, float sb, long long ib) {
     return sa > sb || (sa == sb && ia < ib);
 }
 
-// per-shard blocks are `*_gs` elements apart (contiguous [G,nq,k] arrays or the packed all-gather buffer)
+// per-shard blocks are `*_gs` elements apart (contiguous [G,nq,k] arrays, the packed all-gather buffer or the exchange region).
+// Every shard list arrives sorted by (score desc, id asc) and global ids are unique, so the merged position of an element is
+// its own index plus, for every other list, the number of that list's elements ranked before it (one binary search each):
+// no sorting network, two block barriers.
 __global__ void __launch_bounds__(256) merge_kernel(const int64_t* ids, const float* scores, const int32_t* counts,
                                                     long long ids_gs, long long scores_gs, long long counts_gs,
                                                     int G, int nq, int k, int n_pow2, int64_t* out_ids,
-                                                    float* out_scores, int32_t* out_counts) {
+                                                    float* out_scores, int32_t* out_counts,
+                                                    const unsigned long long* wait_flags, unsigned long long wait_epoch) {
     extern __shared__ unsigned char sm[];
-    long long* sid = (long long*)sm;
-    float* ssc = (float*)(sid + n_pow2);
-    __shared__ int s_total, s_bad;
-    const int q = blockIdx.x;
-    if (threadIdx.x == 0) { s_total = 0; s_bad = 0; }
-    __syncthreads();
-    int local = 0;
-    for (int e = threadIdx.x; e < n_pow2; e += blockDim.x) {
-        float sc = -__int_as_float(0x7f800000);
-        long long id = 0x7FFFFFFFFFFFFFFFll;
-        if (e < G * k) {
-            const int g = e / k, i = e - g * k;
-            const int c = counts[(size_t)g * counts_gs + q];
-            if (c < 0 && i == 0) s_bad = 1;
-            if (i < c) {
-                sc = scores[(size_t)g * scores_gs + (size_t)q * k + i];
-                id = ids[(size_t)g * ids_gs + (size_t)q * k + i];
-                ++local;
-            }
-        }
-        ssc[e] = sc;
-        sid[e] = id;
-    }
-    if (local) atomicAdd(&s_total, local);
-    __syncthreads();
-    for (int kk = 2; kk <= n_pow2; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int ixj = i | j;
-                const bool desc = (i & kk) == 0;
-                const float sa = ssc[i], sb = ssc[ixj];
-                const long long ia = sid[i], ib = sid[ixj];
-                // descending block: element that ranks first must sit at i
-                const bool swap = desc ? before(sb, ib, sa, ia) : before(sa, ia, sb, ib);
-                if (swap) {
-                    ssc[i] = sb; ssc[ixj] = sa;
-                    sid[i] = ib; sid[ixj] = ia;
+    if (wait_flags) {
+        // peer-memory exchange: rank g's push of this search has landed in the local region once its flag shows the epoch
+        if (threadIdx.x < G) {
+            unsigned int spins = 0;
+            while (ld_acquire_sys_u64(wait_flags + threadIdx.x) < wait_epoch) {
+                __nanosleep(100);
+                if (++spins == (1u << 25)) {
+                    printf("rvo: merge wait for rank %d timed out (epoch %llu)\n", (int)threadIdx.x, wait_epoch);
+                    __trap();
                 }
             }
-            __syncthreads();
+        }
+        __syncthreads();
+    }
+    long long* sid = (long long*)sm;                 // [G][k]
+    float* ssc = (float*)(sid + (size_t)G * k);      // [G][k]
+    __shared__ int s_cnt[kMaxMergeLists], s_bad;
+    const int q = blockIdx.x;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int c = __ldcg(counts + (size_t)threadIdx.x * counts_gs + q);
+        if (c < 0) s_bad = 1;
+        s_cnt[threadIdx.x] = c < 0 ? 0 : (c > k ? k : c);
+    }
+    __syncthreads();
+    const int n = G * k;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int g = e / k, i = e - g * k;
+        if (i < s_cnt[g]) {
+            ssc[e] = __ldcg(scores + (size_t)g * scores_gs + (size_t)q * k + i);
+            sid[e] = __ldcg(ids + (size_t)g * ids_gs + (size_t)q * k + i);
         }
     }
-    const int total = s_total < k ? s_total : k;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const bool ok = i < total && !s_bad;
-        out_ids[(size_t)q * k + i] = ok ? sid[i] : -1;
-        out_scores[(size_t)q * k + i] = ok ? ssc[i] : -__int_as_float(0x7f800000);
+    __syncthreads();
+    int total = 0;
+    for (int g = 0; g < G; ++g) total += s_cnt[g];
+    const int n_out = s_bad ? 0 : (total < k ? total : k);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int g = e / k, i = e - g * k;
+        if (i >= s_cnt[g] || s_bad) continue;
+        const float sc = ssc[e];
+        const long long id = sid[e];
+        int pos = i;
+        for (int h = 0; h < G && pos < k; ++h) {
+            if (h == g) continue;
+            // number of elements of list h ranked before (sc, id): first index whose element is NOT before it
+            int lo = 0, hi = s_cnt[h];
+            const float* hs = ssc + h * k;
+            const long long* hi_ids = sid + h * k;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (before(hs[mid], hi_ids[mid], sc, id)) lo = mid + 1;
+                else hi = mid;
+            }
+            pos += lo;
+        }
+        if (pos < k) {
+            out_ids[(size_t)q * k + pos] = id;
+            out_scores[(size_t)q * k + pos] = sc;
+        }
     }
-    if (threadIdx.x == 0) out_counts[q] = s_bad ? -1 : total;
+    for (int i = n_out + threadIdx.x; i < k; i += blockDim.x) {
+        out_ids[(size_t)q * k + i] = -1;
+        out_scores[(size_t)q * k + i] = -__int_as_float(0x7f800000);
+    }
+    if (threadIdx.x == 0) out_counts[q] = s_bad ? -1 : n_out;
+    (void)n_pow2;
+    (void)nq;
 }
 
 // ---- host wrappers ------------------------------------------------------------------------------
@@ -633,14 +710,17 @@ int launch_final(const FinalArgs& a, int nq, cudaStream_t stream) {
 
 int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts, long long ids_gs, long long scores_gs,
                  long long counts_gs, int G, int nq, int k, int64_t* out_ids, float* out_scores, int32_t* out_counts,
-                 cudaStream_t stream) {
-    int n_pow2 = 2;
-    while (n_pow2 < G * k) n_pow2 <<= 1;
-    const size_t smem = (size_t)n_pow2 * 12;
+                 cudaStream_t stream, const unsigned long long* wait_flags, unsigned long long wait_epoch) {
+    if (G > kMaxMergeLists) {
+        set_error("merge: at most %d lists (G=%d)", kMaxMergeLists, G);
+        return RVO_E_INVALID;
+    }
+    const int n_pow2 = 0;
+    const size_t smem = (size_t)G * k * 12;
     if (smem > 48 * 1024)
         RVO_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_kernel<<<nq, 256, smem, stream>>>(ids, scores, counts, ids_gs, scores_gs, counts_gs, G, nq, k, n_pow2, out_ids,
-                                            out_scores, out_counts);
+                                            out_scores, out_counts, wait_flags, wait_epoch);
     RVO_LAUNCHED();
     return RVO_OK;
 }

@@ -48,6 +48,19 @@ struct SelectArgs {
     const float* range_lo;              // optional per-query lower bound of every key's score (finer first bins)
 };
 
+// Peer-memory exchange fused into the last kernel of the sharded search: besides its own result arrays the
+// CTA of query q stores its k (id, score) pairs and its count into the slot of THIS rank in every peer's exchange
+// region (NVLink stores), and the last CTA of the grid to finish publishes `epoch` in every peer's flag for this rank.
+constexpr int kMaxPeers = 8;
+struct PushArgs {
+    int world, rank;                           // world <= 1: no exchange
+    int nq, k;                                 // blob layout [ids int64 nq*k | scores f32 nq*k | counts i32 nq]
+    unsigned long long epoch;
+    unsigned char* peer_slot[kMaxPeers];       // this rank's slot (current parity) in peer g's region; [rank] unused
+    unsigned long long* peer_flag[kMaxPeers];  // this rank's flag (current parity) in peer g's region; [rank] = local
+    unsigned int* done;                        // local CTA counter of the current parity (zero between uses)
+};
+
 struct FinalArgs {
     const unsigned long long* top;      // [nq][top_ld], first K2 sorted descending
     long long top_ld;
@@ -64,6 +77,7 @@ struct FinalArgs {
     int64_t* out_ids;
     float* out_scores;
     int32_t* out_counts;
+    PushArgs push;
 };
 
 int launch_chunk_topk(const ChunkTopkArgs& a, int num_chunks, int nq, cudaStream_t stream);
@@ -72,8 +86,9 @@ int launch_select(const SelectArgs& a, int grid_q, cudaStream_t stream);
 // `f` supplies k, score_threshold, margin, db/qn and the outputs (f.top / f.cnt / f.K2 unused)
 int launch_select_final(const SelectArgs& a, const FinalArgs& f, int nq, cudaStream_t stream);
 int launch_final(const FinalArgs& a, int nq, cudaStream_t stream);
+// wait_flags != nullptr: every CTA first waits until wait_flags[g] >= wait_epoch for all g < G (peer pushes landed)
 int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts, long long ids_gs, long long scores_gs,
                  long long counts_gs, int G, int nq, int k, int64_t* out_ids, float* out_scores, int32_t* out_counts,
-                 cudaStream_t stream);
+                 cudaStream_t stream, const unsigned long long* wait_flags = nullptr, unsigned long long wait_epoch = 0);
 
 }  // namespace rvo

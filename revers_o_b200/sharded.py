@@ -11,6 +11,8 @@ product path.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -84,7 +86,93 @@ class ShardedIndex:
         ops.require_cuda(local_db, "local_db")
         self.db, self.n_local, self.d, self.id_offset, self.group = local_db, int(n_local), int(d), int(id_offset), group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
         self._bufs: dict = {}
+        self._xchg = None          # peer-memory exchange state (enable_peer_exchange)
+
+    # ---- peer-memory exchange: K2's last kernel pushes the result into every peer's region over NVLink ----------------
+    def enable_peer_exchange(self, nq_max: int, k_max: int) -> bool:
+        """Collective (every rank of the group calls it).  Allocates this rank's exchange region, swaps CUDA IPC handles with
+        the peers and maps theirs.  Afterwards `search` replaces the NCCL all-gather by stores into peer memory fused into
+        the last kernel of the shard search, and K3 waits on epoch flags (include/revers_o_b200.h, "Peer-memory exchange").
+        Returns False (and changes nothing) when the box/topology does not allow it; all ranks get the same answer."""
+        if self.world < 2 or self.world > 8:
+            return False
+        lib = _lib.load()
+        dev = self.db.device
+        ok, region, peers = 1, C.c_void_p(), []
+        nbytes = lib.rvo_exchange_bytes(self.world, int(nq_max), int(k_max))
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(dev):
+            if nbytes == 0 or self.n_local == 0 or lib.rvo_exchange_alloc(nbytes, C.byref(region)) != 0 \
+                    or lib.rvo_exchange_export(region, handle) != 0:
+                ok = 0
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (ok, bytes(handle)), group=self.group)
+        ok = int(all(g[0] for g in gathered))
+        table = (C.c_void_p * self.world)()
+        if ok:
+            with torch.cuda.device(dev):
+                for g, (_, h) in enumerate(gathered):
+                    if g == self.rank:
+                        table[g] = region.value
+                        continue
+                    p = C.c_void_p()
+                    if lib.rvo_exchange_import((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)) != 0:
+                        ok = 0
+                        break
+                    table[g] = p.value
+                    peers.append(p)
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=self.group)       # every mapping must have worked on every rank
+        if not all(flags):
+            with torch.cuda.device(dev):
+                for p in peers:
+                    lib.rvo_exchange_unimport(p)
+                if region.value:
+                    lib.rvo_exchange_free(region)
+            return False
+        self._xchg = {"region": region, "peers": peers, "table": table, "nq_max": int(nq_max), "k_max": int(k_max), "epoch": 0}
+        return True
+
+    def disable_peer_exchange(self) -> None:
+        """Collective.  Unmaps the peers' regions and frees the local one (after every rank has stopped using them)."""
+        if self._xchg is None:
+            return
+        torch.cuda.synchronize(self.db.device)
+        dist.barrier(group=self.group)
+        lib = _lib.load()
+        with torch.cuda.device(self.db.device):
+            for p in self._xchg["peers"]:
+                lib.rvo_exchange_unimport(p)
+            dist.barrier(group=self.group)
+            lib.rvo_exchange_free(self._xchg["region"])
+        self._xchg = None
+
+    def _search_push(self, queries: torch.Tensor, k: int, score_threshold):
+        import math
+        x = self._xchg
+        nq = queries.shape[0]
+        dev = queries.device
+        lib = _lib.load()
+        key = ("x", nq, k)
+        if self._bufs.get("key") != key:
+            self._bufs = {"key": key, "oi": torch.empty((nq, k), dtype=torch.int64, device=dev),
+                          "os": torch.empty((nq, k), dtype=torch.float32, device=dev),
+                          "oc": torch.empty((nq,), dtype=torch.int32, device=dev)}
+        b = self._bufs
+        x["epoch"] += 1
+        nbytes = lib.rvo_search_workspace_bytes(self.n_local, self.d, nq, k)
+        ws = ops.workspace(dev, nbytes)
+        thr = -math.inf if score_threshold is None else float(score_threshold)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        check(lib.rvo_search_topk_push(self.db.data_ptr(), self.n_local, self.d, ops.d_pad_of(self.d), queries.data_ptr(), nq, k,
+                                       thr, self.id_offset, x["table"], self.world, self.rank, x["nq_max"], x["k_max"],
+                                       x["epoch"], ws.data_ptr(), nbytes, stream), "rvo_search_topk_push")
+        check(lib.rvo_merge_topk_exchange(x["region"], self.world, nq, k, x["nq_max"], x["k_max"], x["epoch"],
+                                          b["oi"].data_ptr(), b["os"].data_ptr(), b["oc"].data_ptr(), stream),
+              "rvo_merge_topk_exchange")
+        return b["oi"], b["os"], b["oc"]
 
     @classmethod
     def from_disk(cls, path: str, collection_name: str, device, rank: int | None = None, world: int | None = None,
@@ -117,6 +205,9 @@ class ShardedIndex:
         if self.world == 1:
             return self.search_local(queries, k, score_threshold)
         nq = queries.shape[0]
+        x = self._xchg
+        if x is not None and _lib.RVO_SMALL_Q < nq <= x["nq_max"] and k <= x["k_max"]:
+            return self._search_push(queries, k, score_threshold)
         dev = queries.device
         # K2 writes straight into the packed [ids | scores | counts] blob that the all-gather ships (no pack kernels)
         key = (nq, k)

@@ -24,6 +24,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     ok = True
     msgs = []
+    push_note = []
     for (n, d, nq, k, thr) in [(200_000, 1024, 64, 100, None), (150_001, 1280, 300, 50, 0.6), (60_000, 256, 3, 10, None)]:
         q = synth.make_queries(nq, d, seed=7, device=dev)
         full = synth.make_db(n, d, q, n_plant=128, seed=1000, device=dev)      # same DB on every rank (same seed)
@@ -31,6 +32,23 @@ def main():
         local_db = full[lo // 128: (hi + 127) // 128].contiguous()
         idx = ShardedIndex(local_db, hi - lo, d, lo)
         ids, sc, cnt = idx.search_exact(q, k, thr)
+        ids, sc, cnt = ids.clone(), sc.clone(), cnt.clone()
+        # the same search through the peer-memory exchange (NVLink stores fused into K2's last kernel) must agree bit for bit,
+        # repeatedly (both slot parities, reuse of the flags)
+        pushed = idx.enable_peer_exchange(nq_max=max(nq, 8), k_max=k)
+        if pushed:
+            for _ in range(5):
+                pi, ps, pc = idx.search(q, k, thr)
+                torch.cuda.synchronize()
+                bad = (cnt < 0)
+                same_push = bool(torch.equal(pc[~bad], cnt[~bad]) and torch.equal(pi[~bad], ids[~bad]) and torch.equal(ps[~bad], sc[~bad]))
+                if not same_push:
+                    break
+            idx.disable_peer_exchange()
+        else:
+            same_push = True
+        push_note.append(f"push={'on' if pushed else 'unavailable'}:{'ok' if same_push else 'FAIL'}")
+        ok &= same_push
         fi, fs, fc = ops.search_topk_exact(full, n, d, q, k, thr)
         torch.cuda.synchronize()
         same = bool(torch.equal(ids, fi) and torch.equal(cnt, fc) and torch.allclose(sc, fs, atol=1e-6))
@@ -64,7 +82,8 @@ def main():
     ok &= int(total.item()) == 2000
     msgs.append(f"selfjoin pairs {int(total.item())}/2000")
     if rank == 0:
-        print(("SHARDED_NCCL_OK " if ok else "SHARDED_NCCL_FAIL ") + f"world={world} " + " ".join(msgs), flush=True)
+        print(("SHARDED_NCCL_OK " if ok else "SHARDED_NCCL_FAIL ") + f"world={world} " + " ".join(msgs) + " " + " ".join(push_note),
+              flush=True)
     dist.destroy_process_group()
     return 0 if ok else 1
 
