@@ -2,7 +2,7 @@
 # Breadth measurements: other workloads through bench.py and the K1 mask-pool timing.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-for wl in ${WORKLOADS:-cfg0 cfg3small cfg3shard}; do
+for wl in ${WORKLOADS:-cfg0 cfg3shardq16 cfg3shard}; do
   echo "=== $wl"
   timeout 900 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -n 1 | python -c "
 import sys,json
