@@ -362,3 +362,42 @@ def test_config3_shard_size_against_fp32_reference(dev):
     idsL, scL, cntL = _run(db, n, d, q_all, k)
     assert np.all(cntL == k) and np.all(np.diff(scL, axis=1) <= 1e-7)
     assert_topk_match(idsL[:16], scL[:16], cntL[:16], ref, k, TOL, "cfg3-q4096")
+
+
+# ---- degenerate inputs the reference can meet (zero vectors, tiny DBs, extreme k / thresholds) -----------------------
+@pytest.mark.parametrize("nq", [2, 9])
+def test_degenerate_queries_and_shapes(dev, nq):
+    """Zero query (qdrant leaves a zero vector as is: every score 0), a DB smaller than one 128-row tile, k = 1, the
+    maximum k, k > n, a threshold above every score (empty result -> the 'no similar regions' path, core_system.py:666)
+    and below every score — on both the Q <= 4 and the tensor path."""
+    from revers_o_b200 import ops, synth
+    from revers_o_b200._lib import RVO_MAX_K
+    n, d = 90, 128
+    q = synth.make_queries(nq, d, seed=91, device=dev)
+    db = synth.make_db(n, d, q, n_plant=4, seed=92, device=dev)
+    big_n = 70_000
+    db2 = synth.make_db(big_n, d, q, n_plant=8, seed=93, device=dev)     # the same batch on a multi-level shard
+    q[1] = 0.0                                                            # zero query vector (after planting: no NaN rows)
+    for k, thr in ((1, None), (10, None), (RVO_MAX_K, None), (10, 1.5), (10, -1.0), (200, 0.3)):
+        ids, sc, cnt = _run(db, n, d, q, k, thr)
+        ref = _oracle(db, n, d, q, k, thr)
+        for i in (0, 1, nq - 1):
+            c = int(cnt[i])
+            assert c == len(ref[i][0]) or i == 1, (k, thr, i, c, len(ref[i][0]))
+            if i == 1:                                                    # all scores exactly 0: any n ids are a valid answer
+                want = 0 if (thr is not None and thr > 0) else min(k, n)
+                assert c == want and np.all(sc[i, :c] == 0.0) and len(set(ids[i, :c].tolist())) == c
+            elif c:
+                assert np.max(np.abs(sc[i, :c] - ref[i][1])) < TOL and set(ids[i, :c].tolist()) == set(ref[i][0].tolist())
+            assert np.all(ids[i, c:] == -1)
+    # 70k rows all scoring exactly 0 against the zero query is a tie mass beyond the fused path's capacity: it is flagged (-1)
+    # on the tensor path and the documented protocol (search_topk_exact) answers it; the other queries are unaffected
+    raw = _run(db2, big_n, d, q, 50)[2]
+    assert raw[1] in (-1, 50) and np.all(np.delete(raw, 1) == 50)
+    a, b, c = ops.search_topk_exact(db2, big_n, d, q, 50)
+    torch.cuda.synchronize()
+    ids, sc, cnt = a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()
+    ref = _oracle(db2, big_n, d, q, 50)
+    assert cnt[1] == 50 and np.all(sc[1, :50] == 0.0)
+    keep = [i for i in range(nq) if i != 1]
+    assert_topk_match(ids[keep], sc[keep], cnt[keep], [ref[i] for i in keep], 50, TOL, "degenerate")
