@@ -463,7 +463,10 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
     }
     sa.K = k;
     sa.tau_out = sp.tau;
-    rc = launch_select(sa, nq_pad, stream);
+    if (k <= kSeedTauMaxK)   // one pass + one 512-key sort: k-th largest of the per-thread maxima (select.cuh)
+        rc = launch_seed_tau(sp.dense, sp.dense_ld, sp.seed_cols, nq, nq_pad, k, sp.margin, score_threshold, sp.tau, stream);
+    else
+        rc = launch_select(sa, nq_pad, stream);
     if (rc) return rc;
 
     // FILTER levels: each tightens tau on a larger tile sample; the last one scans every row

@@ -591,6 +591,65 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
     }
 }
 
+// ---- seed threshold from per-thread maxima (see select.cuh) ----------------------------------------------------------
+__global__ void __launch_bounds__(512) seed_tau_kernel(const float* __restrict__ dense, long long dense_ld, long long n_dense,
+                                                       int nq, int k, const float* __restrict__ margin, float score_floor,
+                                                       float* __restrict__ tau_out) {
+    __shared__ uint32_t s[512];
+    const int q = blockIdx.x, t = threadIdx.x;
+    grid_dependency_wait();
+    grid_launch_dependents();
+    if (q >= nq) {  // padded query rows of the tensor path never admit anything
+        if (t == 0) tau_out[q] = __int_as_float(0x7f800000);
+        return;
+    }
+    const float NINF = -__int_as_float(0x7f800000);
+    const float* src = dense + (size_t)q * (size_t)dense_ld;
+    float m0 = NINF, m1 = NINF, m2 = NINF, m3 = NINF;            // four independent chains: loads stay in flight
+    long long i = t;
+    for (; i + 3 * 512 < n_dense; i += 4 * 512) {
+        m0 = fmaxf(m0, __ldg(src + i));
+        m1 = fmaxf(m1, __ldg(src + i + 512));
+        m2 = fmaxf(m2, __ldg(src + i + 1024));
+        m3 = fmaxf(m3, __ldg(src + i + 1536));
+    }
+    for (; i < n_dense; i += 512) m0 = fmaxf(m0, __ldg(src + i));
+    uint32_t x = f32_orderable(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));   // fmaxf drops NaNs; -inf (no element) orders lowest
+    // bitonic sort of the 512 maxima, descending, one key per thread: shuffles inside a warp, shared memory across warps
+    for (int kk = 2; kk <= 512; kk <<= 1) {
+        const bool desc = (t & kk) == 0;
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            uint32_t y;
+            if (j >= 32) {
+                __syncthreads();
+                s[t] = x;
+                __syncthreads();
+                y = s[t ^ j];
+            } else {
+                y = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+            }
+            const bool take_max = ((t & j) == 0) == desc;
+            x = take_max ? (x > y ? x : y) : (x < y ? x : y);
+        }
+    }
+    if (t == k - 1) {
+        const float mg = margin ? margin[q] : kBf16QueryMargin;
+        float tau = score_floor - mg;                              // -inf stays -inf
+        const float kth = orderable_f32(x);
+        if (kth > NINF && kth - mg > tau) tau = kth - mg;          // fewer than k maxima exist: keep the floor (admit everything)
+        tau_out[q] = tau;
+    }
+}
+
+int launch_seed_tau(const float* dense, long long dense_ld, long long n_dense, int nq, int grid_q, int k, const float* margin,
+                    float score_floor, float* tau_out, cudaStream_t stream) {
+    if (grid_q <= 0) return RVO_OK;
+    RVO_CUDA(launch_pdl(seed_tau_kernel, dim3(grid_q), dim3(512), 0, stream, dense, dense_ld, n_dense, nq, k, margin, score_floor,
+                        tau_out));
+    RVO_LAUNCHED();
+    return RVO_OK;
+}
+
 int launch_select(const SelectArgs& a, int grid_q, cudaStream_t stream) {
     if (grid_q <= 0) return RVO_OK;
     FinalArgs f;

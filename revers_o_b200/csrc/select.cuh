@@ -82,6 +82,12 @@ struct FinalArgs {
 
 int launch_chunk_topk(const ChunkTopkArgs& a, int num_chunks, int nq, cudaStream_t stream);
 int launch_select(const SelectArgs& a, int grid_q, cudaStream_t stream);
+// Seed level only (dense sample, k <= kSeedTauMaxK): tau_out[q] = max(k-th largest of the 512 per-thread maxima of the sample,
+// score_floor) - margin[q].  The per-thread maxima are distinct elements of the sample, so their k-th largest is a lower bound of
+// the sample's k-th largest (hence of the DB's): a valid threshold from ONE pass and one 512-key sort.
+constexpr int kSeedTauMaxK = 128;
+int launch_seed_tau(const float* dense, long long dense_ld, long long n_dense, int nq, int grid_q, int k, const float* margin,
+                    float score_floor, float* tau_out, cudaStream_t stream);
 // last level fused with the fp32 re-score and the final ordering: `a` selects (a.K = candidates aimed at, a.out unused),
 // `f` supplies k, score_threshold, margin, db/qn and the outputs (f.top / f.cnt / f.K2 unused)
 int launch_select_final(const SelectArgs& a, const FinalArgs& f, int nq, cudaStream_t stream);
