@@ -13,9 +13,9 @@
 //                mbarriers), with the tile's mask bytes prefetched into registers before that wait.  The first
 //                version converted a whole image between two images' MMAs (8-12 us of bubble per image).
 //   D (TMEM)   = [128 channels][slab * N + m] fp32: all D/128 slabs of an image (D/128 * N <= 512), in TWO
-//                halves with their own full/empty barriers.  MMA order is half -> patch tile -> slab, so the
-//                epilogue's sum-of-squares pass over half 0 runs under the MMAs of half 1, and half 0 is handed
-//                back (after its normalise + store pass) while half 1 is still being stored.
+//                parts with their own full/empty barriers.  MMA order is part -> patch tile -> slab, so the
+//                epilogue's sum-of-squares pass over a part runs under the MMAs of the next ones, and part 0 is
+//                handed back (after its normalise + store pass) while the later parts are still being stored.
 // Epilogue: pass 1 reduces ||e_m||^2 over channels (shuffle + smem), pass 2 writes e_m / ||e_m|| (TMEM loads
 // software-pipelined against the stores).
 // Warp roles: 0 TMA producer, 1 MMA issuer, 2-9 epilogue (two per TMEM lane quarter), 10-11 mask conversion.
@@ -32,7 +32,8 @@ constexpr int kPtCvtThreads = 64;     // mask-conversion warps 10..11
 constexpr int kPtMaxStages = 12;
 constexpr int kPtMaxPc = 16;          // patch tiles per image (P <= 1024)
 constexpr int kPtStageBytes = 16384;  // 64 patches x 128 channels bf16
-constexpr int kPtBars = 2 * kPtMaxStages + 2 * kPtMaxPc + 8;
+constexpr int kPtMaxParts = 4;        // TMEM accumulator parts with their own full/empty barriers
+constexpr int kPtBars = 2 * kPtMaxStages + 2 * kPtMaxPc + 2 * kPtMaxParts + 4;
 
 struct PoolTcParams {
     const uint8_t* masks;
@@ -98,6 +99,9 @@ __device__ __forceinline__ void mask4_to_bf16(uint32_t x, uint32_t& w0, uint32_t
     w1 = __byte_perm(f, 0u, 0x4342) * 127u;   // bytes {f2, 0, f3, 0}
 }
 
+// TO_DB: the fused-ingest variant (bf16 rows into the tiled DB, fp32 output optional); the plain variant keeps the store pass
+// free of the extra address arithmetic (it is issue-bound)
+template <bool TO_DB>
 __global__ void __launch_bounds__(kPtThreads, 1)
 mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -111,26 +115,32 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
     uint64_t* bar_empty = bars + kPtMaxStages;            // [kPtMaxStages]
     uint64_t* bar_bfull = bars + 2 * kPtMaxStages;        // [kPtMaxPc] mask tile pc of the next image converted
     uint64_t* bar_bfree = bar_bfull + kPtMaxPc;           // [kPtMaxPc] this image's MMAs on tile pc retired
-    uint64_t* bar_tfull = bar_bfree + kPtMaxPc;           // [2] accumulators of a half complete
-    uint64_t* bar_tempty = bar_tfull + 2;                 // [2] half drained
-    uint64_t* bar_mfree = bar_tempty + 2;                 // [2] epilogue done with s_outrow/s_invarea[buf]
+    uint64_t* bar_tfull = bar_bfree + kPtMaxPc;           // [kPtMaxParts] accumulators of a part complete
+    uint64_t* bar_tempty = bar_tfull + kPtMaxParts;       // [kPtMaxParts] part drained
+    uint64_t* bar_mfree = bar_tempty + kPtMaxParts;       // [2] epilogue done with s_outrow/s_invarea[buf]
     uint64_t* bar_mready = bar_mfree + 2;                 // [2] s_outrow/s_invarea[buf] of an image written
     uint32_t* s_tmem = (uint32_t*)(bars + kPtBars);
     const uint32_t kPtStages = (uint32_t)p.num_stages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pad = p.n_pad, num_pc = p.num_pc, num_slab = p.num_slab;
-    const int half_split = (num_slab + 1) >> 1;           // slabs [0, half_split) form half 0, the rest half 1
-    const int last_half = num_slab > half_split ? 1 : 0;
+    // the slabs form `parts` equal groups, each with its own TMEM full/empty barriers: between two images the MMA issuer only
+    // waits for (sum of squares of the LAST part) + (store of the FIRST part).  Two parts; four were measured SLOWER (0.086 vs
+    // 0.074 ms per configs[2] batch: the store pass restarts its TMEM-load pipeline and re-derives its scales per part).
+    const int parts = (num_slab % 2 == 0) ? 2 : 1;
+    const int spp = num_slab / parts;                     // slabs per part
+    const int last_half = parts - 1;
     const uint32_t b_tile_bytes = (uint32_t)n_pad * 128u;
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
         for (int i = 0; i < kPtMaxStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < kPtMaxPc; ++i) { mbar_init(&bar_bfull[i], 1); mbar_init(&bar_bfree[i], 1); }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kPtMaxParts; ++i) {
             mbar_init(&bar_tfull[i], 1);
             mbar_init(&bar_tempty[i], 8);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_mfree[i], 8);
             mbar_init(&bar_mready[i], 1);
         }
@@ -150,7 +160,7 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
             uint32_t stage = 0, phase = 0;
             for (int b = blockIdx.x; b < p.B; b += gridDim.x)
                 for (int h = 0; h <= last_half; ++h) {
-                    const int s0 = h ? half_split : 0, s1 = h ? num_slab : half_split;
+                    const int s0 = h * spp, s1 = s0 + spp;
                     for (int pc = 0; pc < num_pc; ++pc)
                         for (int s = s0; s < s1; ++s) {
                             mbar_wait(&bar_empty[stage], phase ^ 1);
@@ -171,7 +181,7 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
             const uint32_t sB0 = smem_u32(s_b);
             for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
                 for (int h = 0; h <= last_half; ++h) {
-                    const int s0 = h ? half_split : 0, s1 = h ? num_slab : half_split;
+                    const int s0 = h * spp, s1 = s0 + spp;
                     mbar_wait(&bar_tempty[h], (it & 1u) ^ 1u);        // this half of the previous image drained from TMEM
                     if (h == 0) trace_stamp(p, b, 1);
                     tc_fence_after();
@@ -281,10 +291,10 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
 #pragma unroll
                 for (int i = 0; i < 16; ++i) ss[gi][i] = 0.f;
             for (int h = 0; h <= last_half; ++h) {
-                const int s0 = h ? half_split : 0, s1 = h ? num_slab : half_split;
+                const int s0 = h * spp, s1 = s0 + spp;
                 mbar_wait(&bar_tfull[h], it & 1u);
                 tc_fence_after();
-                if (threadIdx.x == 64) trace_stamp(p, b, 3 + h);
+                if (threadIdx.x == 64 && (h == 0 || h == last_half)) trace_stamp(p, b, h == 0 ? 3 : 4);
 #pragma unroll
                 for (int gi = 0; gi < 2; ++gi) {
                     const int g = half_w + 2 * gi;
@@ -338,7 +348,7 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
             // immediates off one 64-bit base per region.
             float* __restrict__ gout = p.out + ch;
             for (int h = 0; h <= last_half; ++h) {
-                const int s0 = h ? half_split : 0, s1 = h ? num_slab : half_split;
+                const int s0 = h * spp, s1 = s0 + spp;
                 const int ns = s1 - s0;
 #pragma unroll
                 for (int gi = 0; gi < 2; ++gi) {
@@ -361,13 +371,13 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
                             if (j < ns) {
                                 tmem_ld_wait();
                                 if (jj < 3 && j + 1 < ns) tmem_ld_x16(taddr + (uint32_t)((s0 + j + 1) * n_pad + m0), v[(jj + 1) & 1]);
-                                if (p.out) {
+                                if (!TO_DB || p.out) {
                                     float* __restrict__ o = gout + (size_t)(s0 + j0) * 128 + jj * 128;
 #pragma unroll
                                     for (int i = 0; i < 16; ++i)
                                         if (rr[i] >= 0) __stcs(o + (size_t)rr[i] * (size_t)p.D, __uint_as_float(v[jj & 1][i]) * sc[i]);
                                 }
-                                if (p.db) {
+                                if constexpr (TO_DB) {
                                     // tiled DB storage [row/128][col/64][row%128][col%64]: the warp's 32 channels of one
                                     // region are 64 contiguous bytes
                                     const int col = (s0 + j) * 128 + ch;
@@ -558,12 +568,14 @@ int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int 
     p.b_buf_bytes = (uint32_t)b_buf;
     p.off_misc = (uint32_t)off_misc;
     p.trace = (unsigned long long*)g_pool_trace;
-    RVO_CUDA(cudaFuncSetAttribute(mask_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RVO_CUDA(cudaFuncSetAttribute(mask_pool_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RVO_CUDA(cudaFuncSetAttribute(mask_pool_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = B < sm_count ? B : sm_count;
     // ONE launch: the grid is persistent with at most one CTA per SM (all co-resident), which the in-kernel rendezvous
     // on `arrived` relies on; the launcher zeroes the counter on the same stream
     RVO_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
-    mask_pool_tc_kernel<<<grid, kPtThreads, smem, stream>>>(tm, p);
+    if (db) mask_pool_tc_kernel<true><<<grid, kPtThreads, smem, stream>>>(tm, p);
+    else mask_pool_tc_kernel<false><<<grid, kPtThreads, smem, stream>>>(tm, p);
     RVO_LAUNCHED();
     return RVO_OK;
 }
