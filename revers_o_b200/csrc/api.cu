@@ -12,6 +12,7 @@ namespace rvo {
 
 extern bool g_force_cuda_core_pool;
 extern void* g_pool_trace;
+static std::atomic<long long> opt_select_trace{0};
 size_t selfjoin_workspace_bytes(int d, long long cand_cap);
 int launch_selfjoin(const uint16_t* db, long long n_rows, int d, long long row_lo, long long row_hi, float threshold,
                     long long id_offset, long long cand_cap, long long* out_pairs, float* out_scores, long long out_cap,
@@ -294,6 +295,7 @@ int rvo_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "time_scan")) opt_time_scan = value;
     else if (!strcmp(name, "pool_path")) g_force_cuda_core_pool = value == 1;
     else if (!strcmp(name, "pdl")) g_use_pdl = value;
+    else if (!strcmp(name, "select_trace")) opt_select_trace = value;
     else if (!strcmp(name, "pool_trace")) g_pool_trace = (void*)(uintptr_t)value;
     else {
         set_error("unknown option '%s'", name);
@@ -498,6 +500,7 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
         } else {
             // last level: exact candidate selection fused with the fp32 re-score and the final ordering
             sa.K = sp.K2;
+            sa.trace = (unsigned long long*)(uintptr_t)opt_select_trace.load();
             rc = launch_select_final(sa, fa, nq, stream);
             if (rc) return rc;
         }

@@ -133,18 +133,30 @@ __device__ __forceinline__ void rescore_candidates(unsigned long long* s, int ha
         float acc = 0.f;
         if (active) {
             const uint4* r = base + ((size_t)(row >> 7) * ntk * kTileRows + (row & 127)) * 8;
-            for (int c = l8; c < nchunk; c += 8) {
-                const uint4 v = __ldg(r + (size_t)(c >> 3) * kTileRows * 8 + (c & 7));
-                const float4 q0 = __ldg((const float4*)(qv + c * 8));
-                const float4 q1 = __ldg((const float4*)(qv + c * 8 + 4));
-                acc = fmaf(__uint_as_float(v.x << 16), q0.x, acc);
-                acc = fmaf(__uint_as_float(v.x & 0xFFFF0000u), q0.y, acc);
-                acc = fmaf(__uint_as_float(v.y << 16), q0.z, acc);
-                acc = fmaf(__uint_as_float(v.y & 0xFFFF0000u), q0.w, acc);
-                acc = fmaf(__uint_as_float(v.z << 16), q1.x, acc);
-                acc = fmaf(__uint_as_float(v.z & 0xFFFF0000u), q1.y, acc);
-                acc = fmaf(__uint_as_float(v.w << 16), q1.z, acc);
-                acc = fmaf(__uint_as_float(v.w & 0xFFFF0000u), q1.w, acc);
+            // the candidate rows are random 2 KB gathers from DRAM: issue eight 16-byte loads per lane before consuming any
+            for (int c0 = l8; c0 < nchunk; c0 += 64) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = c0 + 8 * u;
+                    v[u] = c < nchunk ? __ldg(r + (size_t)(c >> 3) * kTileRows * 8 + (c & 7)) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = c0 + 8 * u;
+                    if (c < nchunk) {
+                        const float4 q0 = __ldg((const float4*)(qv + c * 8));
+                        const float4 q1 = __ldg((const float4*)(qv + c * 8 + 4));
+                        acc = fmaf(__uint_as_float(v[u].x << 16), q0.x, acc);
+                        acc = fmaf(__uint_as_float(v[u].x & 0xFFFF0000u), q0.y, acc);
+                        acc = fmaf(__uint_as_float(v[u].y << 16), q0.z, acc);
+                        acc = fmaf(__uint_as_float(v[u].y & 0xFFFF0000u), q0.w, acc);
+                        acc = fmaf(__uint_as_float(v[u].z << 16), q1.x, acc);
+                        acc = fmaf(__uint_as_float(v[u].z & 0xFFFF0000u), q1.y, acc);
+                        acc = fmaf(__uint_as_float(v[u].w << 16), q1.z, acc);
+                        acc = fmaf(__uint_as_float(v[u].w & 0xFFFF0000u), q1.w, acc);
+                    }
+                }
             }
         }
 #pragma unroll
@@ -319,22 +331,23 @@ __device__ __forceinline__ void for_each_key(const SelectArgs& a, int q, const i
     } else {
         // all sub-lists of the query as one index space: thread t takes elements t, t + blockDim, ... of each
         const int step = (int)blockDim.x * sample_every;
-        for (int sg0 = 0; sg0 < a.nseg; sg0 += 4) {
-            // four sub-lists side by side (their first blockDim elements cover most of a typical sub-list)
+        for (int sg0 = 0; sg0 < a.nseg; sg0 += 8) {
+            // eight sub-lists side by side: eight independent loads in flight per thread (the passes over the candidate
+            // lists are latency-bound: ~9k keys per query, two CTAs per SM)
             int cmax = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 8; ++u)
                 if (sg0 + u < a.nseg) cmax = s_cnt[sg0 + u] > cmax ? s_cnt[sg0 + u] : cmax;
             for (int i = (int)threadIdx.x * sample_every; i < cmax; i += step) {
-                unsigned long long k[4];
+                unsigned long long k[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const int sgm = sg0 + u;
                     k[u] = (sgm < a.nseg && i < s_cnt[sgm])
                                ? a.keys[((size_t)q * a.nseg + sgm) * (size_t)a.cap + (size_t)i] : 0ull;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 8; ++u)
                     if (k[u]) f(k[u]);
             }
         }
@@ -374,6 +387,14 @@ __device__ __forceinline__ void hist_find(const int* hist, int need, int lane, i
     }
 }
 
+__device__ __forceinline__ void sel_stamp(const SelectArgs& a, int q, int slot) {
+    if (a.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.trace[(size_t)q * 16 + slot] = t;
+    }
+}
+
 template <bool FINAL>
 __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs a, const FinalArgs f) {
     __shared__ int hist[kSelBins];
@@ -392,6 +413,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
     }
     if (tid == 0) s_over = 0;
     __syncthreads();
+    sel_stamp(a, q, 0);
     if (!a.dense && tid < a.nseg) {
         const int c = a.cnt[q * a.nseg + tid];
         s_cnt[tid] = c < a.cap ? c : a.cap;
@@ -454,6 +476,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
         __syncthreads();
         if (warp == 0) {
             // aim at ~1.5x the wanted count above the bound (plus slack for sampling noise)
+            sel_stamp(a, q, 1);   // sample histogram built
             hist_find(hist, (3 * want) / (2 * every) + 24, lane, s_res);
             __syncwarp();
             if (lane == 0) s_lo = s_res[3] ? lo0 + ((unsigned long long)s_res[0] << sh0) : 0ull;
@@ -461,8 +484,10 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
         __syncthreads();
         // one compaction pass with the proposed bound; exact whenever it kept between `want` and kSelSort keys
         const unsigned long long T0 = s_lo;
+        sel_stamp(a, q, 2);       // bound proposed
         compact(T0);
         T_used = T0;
+        sel_stamp(a, q, 3);       // compacted
         fast = s_count >= want && s_count <= kSelSort;
     }
 
@@ -531,6 +556,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
     for (int i = C + tid; i < ns; i += blockDim.x) sbuf[i] = 0ull;
     __syncthreads();
     sort_desc_u64(sbuf, ns);
+    sel_stamp(a, q, 4);           // first sort done
 
     if constexpr (FINAL) {
         // ---- fused last level: every candidate that can still reach the top-k after the fp32 re-score is one whose
@@ -562,13 +588,18 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
         if (mine) atomicAdd(&s_above, mine);
         __syncthreads();
         const int n_act = s_above;
+        sel_stamp(a, q, 5);       // cut / coverage / prefix count
         rescore_candidates(sbuf, n_act, cut, f.db, f.d_pad, f.qn + (size_t)q * (size_t)f.qn_ld);
         const int ns2 = next_pow2(n_act > 2 ? n_act : 2);
         for (int i = n_act + tid; i < ns2; i += blockDim.x) sbuf[i] = 0ull;
         if (tid == 0) s_count = 0;
         __syncthreads();
+        sel_stamp(a, q, 6);       // re-scored
         sort_desc_u64(sbuf, ns2);
+        sel_stamp(a, q, 7);       // second sort done
         emit_topk(sbuf, ns2, f, q, &s_count);
+        sel_stamp(a, q, 8);
+        if (a.trace && tid == 0) { a.trace[(size_t)q * 16 + 9] = (unsigned long long)C; a.trace[(size_t)q * 16 + 10] = (unsigned long long)n_act; a.trace[(size_t)q * 16 + 11] = (unsigned long long)nnz; }
         return;
     }
 

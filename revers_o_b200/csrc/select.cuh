@@ -46,6 +46,7 @@ struct SelectArgs {
     float score_floor;                  // the caller's score_threshold (-inf when there is none)
     int nq;                             // CTAs q >= nq only write tau_out[q] = +inf (padded query rows)
     const float* range_lo;              // optional per-query lower bound of every key's score (finer first bins)
+    unsigned long long* trace;          // option "select_trace": [nq][16] globaltimer stamps of the kernel's phases (debug)
 };
 
 // Peer-memory exchange fused into the last kernel of the sharded search: besides its own result arrays the
