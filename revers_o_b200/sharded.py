@@ -201,7 +201,9 @@ class ShardedIndex:
         return ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset)
 
     def search(self, queries: torch.Tensor, k: int, score_threshold=None):
-        """queries: f32 [Q, d] on this rank's GPU (replicated).  Returns merged (ids, scores, counts)."""
+        """queries: f32 [Q, d] on this rank's GPU (replicated).  Returns merged (ids, scores, counts) — views of buffers the
+        index reuses on its next call with the same (Q, k): copy them if they must outlive it.  Asynchronous on the current
+        stream; every rank of the group must call it (same Q, k) in the same order."""
         if self.world == 1:
             return self.search_local(queries, k, score_threshold)
         nq = queries.shape[0]
