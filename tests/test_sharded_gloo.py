@@ -53,7 +53,7 @@ def _worker(rank, world, port, ret):
 def test_two_rank_shard_gather_merge():
     world = 2
     port = _free_port()
-    with mp.Manager() as man:
+    with mp.get_context("spawn").Manager() as man:      # no fork() of the multi-threaded pytest process
         ret = man.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
