@@ -119,7 +119,9 @@ int rvo_mask_pool_to_db(const uint16_t* feats, const uint8_t* masks, int32_t B, 
  *           `limit` hits), batched over nq queries row by row.
  *   db      [dev] bf16 tiled DB storage (see "DB storage layout") of L2-normalised rows; d_pad = d
  *           rounded up to 64
- *   queries [dev] float32 [nq, d] row pitch d; NOT required to be normalised
+ *   queries [dev] float32 [nq, d] row pitch d; NOT required to be normalised.  `queries` and the three out_*
+ *           arrays may also be PINNED HOST memory (unified addressing): the first kernel then reads the queries and
+ *           the last one writes the results over PCIe, with no copy launches around the call.
  *   k       1..RVO_MAX_K  (`limit`)
  *   score_threshold   hits with score < threshold are dropped; pass -INFINITY for "None"
  *   id_offset         added to local row numbers (row-sharded DB: first global row of the shard)

@@ -386,7 +386,8 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
                 "search_topk: db must be 16-byte and workspace 1024-byte aligned");
     RVO_REQUIRE(n_rows < (1ll << 31), "search_topk: shard of %lld rows too large, shard the DB", (long long)n_rows);
     int sm = 0;
-    int rc = select_device_of(queries, &sm);
+    // the device comes from the workspace (always device memory); `queries` and the outputs may be pinned host memory
+    int rc = select_device_of(workspace, &sm);
     if (rc) return rc;
 
     if (push && (n_rows == 0 || nq <= RVO_SMALL_Q)) {

@@ -709,7 +709,7 @@ __device__ __forceinline__ bool before(float sa, long long ia, float sb, long lo
 // no sorting network, two block barriers.
 __global__ void __launch_bounds__(256) merge_kernel(const int64_t* ids, const float* scores, const int32_t* counts,
                                                     long long ids_gs, long long scores_gs, long long counts_gs,
-                                                    int G, int nq, int k, int n_pow2, int64_t* out_ids,
+                                                    int G, int k, int64_t* out_ids,
                                                     float* out_scores, int32_t* out_counts,
                                                     const unsigned long long* wait_flags, unsigned long long wait_epoch) {
     extern __shared__ unsigned char sm[];
@@ -780,8 +780,6 @@ __global__ void __launch_bounds__(256) merge_kernel(const int64_t* ids, const fl
         out_scores[(size_t)q * k + i] = -__int_as_float(0x7f800000);
     }
     if (threadIdx.x == 0) out_counts[q] = s_bad ? -1 : n_out;
-    (void)n_pow2;
-    (void)nq;
 }
 
 // ---- host wrappers ------------------------------------------------------------------------------
@@ -805,12 +803,11 @@ int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts,
         set_error("merge: at most %d lists (G=%d)", kMaxMergeLists, G);
         return RVO_E_INVALID;
     }
-    const int n_pow2 = 0;
     const size_t smem = (size_t)G * k * 12;
     if (smem > 48 * 1024)
         RVO_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_kernel<<<nq, 256, smem, stream>>>(ids, scores, counts, ids_gs, scores_gs, counts_gs, G, nq, k, n_pow2, out_ids,
-                                            out_scores, out_counts, wait_flags, wait_epoch);
+    merge_kernel<<<nq, 256, smem, stream>>>(ids, scores, counts, ids_gs, scores_gs, counts_gs, G, k, out_ids, out_scores,
+                                            out_counts, wait_flags, wait_epoch);
     RVO_LAUNCHED();
     return RVO_OK;
 }

@@ -169,14 +169,15 @@ def search_topk(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, k:
     Returns device tensors (ids int64 [nq,k], scores f32 [nq,k], counts int32 [nq]); async on the current stream.
     counts[q] == -1 marks an overflowed query (see `search_topk_exact`)."""
     require_cuda(db, "db")
-    require_cuda(queries, "queries")
+    if not (queries.is_cuda or queries.is_pinned()):
+        raise RvoError("queries must be a CUDA tensor or a pinned host tensor: the B200 library has no CPU path")
     assert db.dtype == torch.bfloat16 and db.dim() == 4 and db.is_contiguous() and db.shape[2:] == (TILE_ROWS, TILE_COLS)
     assert queries.dtype == torch.float32 and queries.dim() == 2 and queries.is_contiguous()
     nq = queries.shape[0]
     assert queries.shape[1] == d and n_rows <= db_capacity(db) and db.shape[1] * TILE_COLS == d_pad_of(d)
     if not (1 <= k <= RVO_MAX_K):
         raise RvoError(f"k={k} outside 1..{RVO_MAX_K}")
-    dev = queries.device
+    dev = db.device
     if out is None:
         ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         scores = torch.empty((nq, k), dtype=torch.float32, device=dev)

@@ -174,10 +174,10 @@ class B200VectorDB:
             if queries.shape[1] != c.dim:
                 raise RvoError(f"Wrong input: Vector dimension error: expected dim: {c.dim}, got {queries.shape[1]}")
             io = self._io_plan(queries.shape[0], c.dim, k)
-            io.q_dev.copy_(queries, non_blocking=True)
-            qd = io.q_dev
             if as_device:
-                return ops.search_topk_exact(vectors, n, c.dim, qd, k, score_threshold)
+                io.q_dev.copy_(queries, non_blocking=True)
+                return ops.search_topk_exact(vectors, n, c.dim, io.q_dev, k, score_threshold)
+            qd = queries            # the normalise kernel reads the queries straight from the caller's pinned memory
         else:
             qh = queries.detach().cpu().numpy() if isinstance(queries, torch.Tensor) else queries
             qh = np.ascontiguousarray(qh, dtype=np.float32)
@@ -188,10 +188,10 @@ class B200VectorDB:
             # host -> pinned staging -> device, all on the current stream; the views are cached per (Q, D, k) and thread
             io = self._io_plan(qh.shape[0], c.dim, k)
             np.copyto(io.q_stage_np, qh)
-            io.q_dev.copy_(io.q_stage, non_blocking=True)
-            qd = io.q_dev
             if as_device:
-                return ops.search_topk_exact(vectors, n, c.dim, qd, k, score_threshold)
+                io.q_dev.copy_(io.q_stage, non_blocking=True)
+                return ops.search_topk_exact(vectors, n, c.dim, io.q_dev, k, score_threshold)
+            qd = io.q_stage         # pinned staging: the normalise kernel reads it over PCIe, no H2D copy launch
         # the last kernel stores ids / scores / counts straight into pinned host memory (zero-copy over PCIe, 0.3 MB of posted
         # writes): no device blob, no D2H copy launch — the stream synchronise below is all that stands between the kernel and
         # the caller
@@ -200,8 +200,8 @@ class B200VectorDB:
         out_i, out_s, out_c = io.ids_np.copy(), io.scores_np.copy(), io.counts_np.copy()
         if out_c.min() < 0:  # overflow protocol of rvo_search_topk: exact fp32 scan in batches of <= RVO_SMALL_Q
             bad = np.nonzero(out_c < 0)[0]
-            a, b, cc = ops.search_topk_exact(vectors, n, c.dim, qd[torch.from_numpy(bad).to(self.device)].contiguous(), k,
-                                             score_threshold)
+            qbad = qd[torch.from_numpy(bad).to(qd.device)].to(self.device).contiguous()
+            a, b, cc = ops.search_topk_exact(vectors, n, c.dim, qbad, k, score_threshold)
             out_i[bad], out_s[bad], out_c[bad] = a.cpu().numpy(), b.cpu().numpy(), cc.cpu().numpy()
         return out_i, out_s, out_c
 
