@@ -329,23 +329,23 @@ __device__ __forceinline__ void for_each_key(const SelectArgs& a, int q, const i
                 if (v[u] != NINF) f(make_key(v[u], (uint32_t)(i0 + u * step)));  // -inf: rows past the end of the DB
         }
     } else {
-        // all sub-lists of the query as one index space: thread t takes elements t, t + blockDim, ... of each
-        const int step = (int)blockDim.x * sample_every;
+        // all sub-lists of the query as one index space: thread t takes elements t, t + blockDim, ... of each.  A SAMPLE is the
+        // first 1/sample_every of every sub-list (arrival order is unrelated to the score, and a contiguous prefix touches
+        // 1/sample_every of the cache lines — a strided sample touches them all and costs as much as the full pass).
+        const int step = (int)blockDim.x;
         for (int sg0 = 0; sg0 < a.nseg; sg0 += 8) {
-            // eight sub-lists side by side: eight independent loads in flight per thread (the passes over the candidate
-            // lists are latency-bound: ~9k keys per query, two CTAs per SM)
-            int cmax = 0;
+            // eight sub-lists side by side: eight independent loads in flight per thread
+            int lim[8], cmax = 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (sg0 + u < a.nseg) cmax = s_cnt[sg0 + u] > cmax ? s_cnt[sg0 + u] : cmax;
-            for (int i = (int)threadIdx.x * sample_every; i < cmax; i += step) {
+            for (int u = 0; u < 8; ++u) {
+                lim[u] = sg0 + u < a.nseg ? (s_cnt[sg0 + u] + sample_every - 1) / sample_every : 0;
+                cmax = lim[u] > cmax ? lim[u] : cmax;
+            }
+            for (int i = (int)threadIdx.x; i < cmax; i += step) {
                 unsigned long long k[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int sgm = sg0 + u;
-                    k[u] = (sgm < a.nseg && i < s_cnt[sgm])
-                               ? a.keys[((size_t)q * a.nseg + sgm) * (size_t)a.cap + (size_t)i] : 0ull;
-                }
+                for (int u = 0; u < 8; ++u)
+                    k[u] = i < lim[u] ? a.keys[((size_t)q * a.nseg + sg0 + u) * (size_t)a.cap + (size_t)i] : 0ull;
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
                     if (k[u]) f(k[u]);
