@@ -149,11 +149,11 @@ class ShardedIndex:
             lib.rvo_exchange_free(self._xchg["region"])
         self._xchg = None
 
-    def _search_push(self, queries: torch.Tensor, k: int, score_threshold):
+    def _search_push(self, queries: torch.Tensor, k: int, score_threshold, out=None):
         import math
         x = self._xchg
         nq = queries.shape[0]
-        dev = queries.device
+        dev = self.db.device
         lib = _lib.load()
         key = ("x", nq, k)
         if self._bufs.get("key") != key:
@@ -169,10 +169,11 @@ class ShardedIndex:
         check(lib.rvo_search_topk_push(self.db.data_ptr(), self.n_local, self.d, ops.d_pad_of(self.d), queries.data_ptr(), nq, k,
                                        thr, self.id_offset, x["table"], self.world, self.rank, x["nq_max"], x["k_max"],
                                        x["epoch"], ws.data_ptr(), nbytes, stream), "rvo_search_topk_push")
+        oi, os_, oc = out if out is not None else (b["oi"], b["os"], b["oc"])
         check(lib.rvo_merge_topk_exchange(x["region"], self.world, nq, k, x["nq_max"], x["k_max"], x["epoch"],
-                                          b["oi"].data_ptr(), b["os"].data_ptr(), b["oc"].data_ptr(), stream),
+                                          oi.data_ptr(), os_.data_ptr(), oc.data_ptr(), stream),
               "rvo_merge_topk_exchange")
-        return b["oi"], b["os"], b["oc"]
+        return oi, os_, oc
 
     @classmethod
     def from_disk(cls, path: str, collection_name: str, device, rank: int | None = None, world: int | None = None,
@@ -200,17 +201,19 @@ class ShardedIndex:
     def search_local(self, queries: torch.Tensor, k: int, score_threshold=None):
         return ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset)
 
-    def search(self, queries: torch.Tensor, k: int, score_threshold=None):
+    def search(self, queries: torch.Tensor, k: int, score_threshold=None, out=None):
         """queries: f32 [Q, d] on this rank's GPU (replicated).  Returns merged (ids, scores, counts) — views of buffers the
         index reuses on its next call with the same (Q, k): copy them if they must outlive it.  Asynchronous on the current
-        stream; every rank of the group must call it (same Q, k) in the same order."""
+        stream; every rank of the group must call it (same Q, k) in the same order.  `queries` may be a pinned host tensor and
+        `out` = (ids int64 [Q,k], scores f32 [Q,k], counts int32 [Q]) pinned host tensors: the first kernel then reads and K3
+        writes over PCIe, with no copy launches around the search."""
         if self.world == 1:
-            return self.search_local(queries, k, score_threshold)
+            return ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset, out=out)
         nq = queries.shape[0]
         x = self._xchg
         if x is not None and _lib.RVO_SMALL_Q < nq <= x["nq_max"] and k <= x["k_max"]:
-            return self._search_push(queries, k, score_threshold)
-        dev = queries.device
+            return self._search_push(queries, k, score_threshold, out)
+        dev = self.db.device
         # K2 writes straight into the packed [ids | scores | counts] blob that the all-gather ships (no pack kernels)
         key = (nq, k)
         if self._bufs.get("key") != key:
@@ -227,10 +230,11 @@ class ShardedIndex:
         counts = blob[nq * k * 12: nq * k * 12 + nq * 4].view(torch.int32)
         ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset, out=(ids, scores, counts))
         dist.all_gather_into_tensor(b["gathered"].view(-1), blob, group=self.group)   # the ONE collective of the path
+        oi, os_, oc = out if out is not None else (b["oi"], b["os"], b["oc"])
         check(_lib.load().rvo_merge_topk_packed(b["gathered"].data_ptr(), b["gathered"].stride(0), self.world, nq, k,
-                                                b["oi"].data_ptr(), b["os"].data_ptr(), b["oc"].data_ptr(),
+                                                oi.data_ptr(), os_.data_ptr(), oc.data_ptr(),
                                                 torch.cuda.current_stream(dev).cuda_stream), "rvo_merge_topk_packed")
-        return b["oi"], b["os"], b["oc"]
+        return oi, os_, oc
 
     def search_exact(self, queries: torch.Tensor, k: int, score_threshold=None):
         """`search` plus the overflow protocol of rvo_search_topk: queries whose merged count is -1 (more than 2048

@@ -177,7 +177,11 @@ class B200VectorDB:
             if as_device:
                 io.q_dev.copy_(queries, non_blocking=True)
                 return ops.search_topk_exact(vectors, n, c.dim, io.q_dev, k, score_threshold)
-            qd = queries            # the normalise kernel reads the queries straight from the caller's pinned memory
+            if os.environ.get("RVO_ZC_IN", "0") == "1":
+                qd = queries        # the normalise kernel reads the queries straight from the caller's pinned memory
+            else:
+                io.q_dev.copy_(queries, non_blocking=True)
+                qd = io.q_dev
         else:
             qh = queries.detach().cpu().numpy() if isinstance(queries, torch.Tensor) else queries
             qh = np.ascontiguousarray(qh, dtype=np.float32)
@@ -191,11 +195,18 @@ class B200VectorDB:
             if as_device:
                 io.q_dev.copy_(io.q_stage, non_blocking=True)
                 return ops.search_topk_exact(vectors, n, c.dim, io.q_dev, k, score_threshold)
-            qd = io.q_stage         # pinned staging: the normalise kernel reads it over PCIe, no H2D copy launch
-        # the last kernel stores ids / scores / counts straight into pinned host memory (zero-copy over PCIe, 0.3 MB of posted
-        # writes): no device blob, no D2H copy launch — the stream synchronise below is all that stands between the kernel and
-        # the caller
+            if os.environ.get("RVO_ZC_IN", "0") == "1":
+                qd = io.q_stage     # pinned staging: the normalise kernel reads it over PCIe, no H2D copy launch
+            else:
+                io.q_dev.copy_(io.q_stage, non_blocking=True)
+                qd = io.q_dev
+        # results land in ONE blob [ids int64 | scores f32 | counts i32]: a device blob + one D2H copy by default.  With
+        # RVO_ZC_OUT=1 the last kernel stores straight into the pinned host blob (and with RVO_ZC_IN=1 the first kernel reads
+        # the queries from pinned host memory): measured equal within noise on one GPU and 30-40 us per step WORSE with two
+        # processes on one box, so the copies stay the default
         ops.search_topk(vectors, n, c.dim, qd, k, score_threshold, out=(io.ids, io.scores, io.counts))
+        if io.res_dev is not io.res_host:
+            io.res_host.copy_(io.res_dev, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         out_i, out_s, out_c = io.ids_np.copy(), io.scores_np.copy(), io.counts_np.copy()
         if out_c.min() < 0:  # overflow protocol of rvo_search_topk: exact fp32 scan in batches of <= RVO_SMALL_Q
@@ -215,7 +226,7 @@ class B200VectorDB:
             nb = (nb_i + nb_s + nb_c + 7) // 8 * 8
             q_stage = torch.empty((nq, d), dtype=torch.float32).pin_memory()
             res_host = torch.empty(nb, dtype=torch.uint8).pin_memory()     # device-addressable (UVA): kernels write into it
-            res_dev = res_host
+            res_dev = res_host if os.environ.get("RVO_ZC_OUT", "0") == "1" else torch.empty(nb, dtype=torch.uint8, device=self.device)
             host = res_host.numpy()
             io = SimpleNamespace(
                 q_stage=q_stage, q_stage_np=q_stage.numpy(),
