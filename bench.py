@@ -1,20 +1,29 @@
 #!/usr/bin/env python
 """bench.py — the reference's headline metric on B200:  exact top-100 cosine queries/s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg1|cfg3shard|cfg0]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg1|...] [--exchange auto|push|nccl]
 
 A "step" is one pass of the hot path (rvo_search_topk: normalise queries -> threshold seeding -> fused tcgen05
 scan/select -> exact top-k -> fp32 re-score) over one synthetic query batch.
 
   N = 1   workload cfg1 = BASELINE.json configs[1]: 1M x 1024 bf16 DB, 256-query batch, top-100 (the metric's own
           100M x 1280 DB does not fit one GPU, so the largest single-GPU search configuration is used).
-  N > 1   the SAME total DB row-sharded over the N ranks (strong scaling): every rank scans its shard, ONE NCCL
-          all-gather of the packed per-shard lists, K3 merge on every rank.  Launch with torchrun (one rank per GPU).
+  N > 1   the SAME total DB row-sharded over the N ranks (strong scaling): every rank scans its shard, the per-shard
+          lists are exchanged once (peer-memory push fused into the last K2 kernel when the box allows CUDA IPC, else ONE
+          NCCL all-gather), K3 merge on every rank.  Launch with torchrun (one rank per GPU).
 
-Printed JSON (rank 0, one line): value = queries/s with inputs resident in HBM; e2e = the same through the public
-`B200VectorDB.search_batch` with HOST buffers (H2D of the queries and D2H of ids/scores/counts inside the timed
-region); roofline = the dominant kernel (full-DB scan) against MEASURED_PEAKS.json; cpu_baseline = the CPU oracle
-(numpy port of the reference's qdrant-local search) timed on this box's host cores on a bounded query sample.
+Printed JSON (rank 0, one line):
+  value         queries/s with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max over ranks)
+  e2e           the same through the public API with pinned HOST buffers (H2D of the queries and D2H of ids/scores/counts
+                inside the timed region): B200VectorDB.search_batch at N = 1, ShardedIndex.search + copies at N > 1
+  roofline      the dominant kernel (full-shard scan) timed alone by the library's own CUDA events on its stream, against
+                MEASURED_PEAKS.json; `traffic` = DRAM bytes of that kernel from the committed ncu capture (profiles/traffic.json)
+  north_star    BASELINE.json's metric layout — 12.5M x 1280 rows PER GPU (N = 8 is configs[3], 100M x 1280), Q = 4096 / 64 / 16 —
+                measured in the same run as a weak-scaling series (--no-north-star skips it)
+  mask_pool     the other half of the path (K1) on configs[2], N = 1 only
+  cpu_baseline  the CPU oracle (numpy port of the reference's qdrant-local search) timed on this box's host cores on a
+                bounded query sample, plus a labelled "fair batched" figure (one sgemm + argpartition)
+  clocks, gpu_launches, local_shard_ms_per_step (N > 1: K2 alone, max over ranks)
 
 `--impl reference` times that CPU implementation alone (numpy-only process; the reference's own dependency
 qdrant-client is not installable here, so kind="port").
@@ -276,12 +285,12 @@ def run_b200(args):
         small_ = nq_ <= _lib.RVO_SMALL_Q
         hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                "frac": hbm_ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peaks_kind,
-               "kernel": "scan_small_kernel" if small_ else "scan_tc_kernel<FILTER> (full-DB level)",
+               "kernel": "scan_small_kernel" if small_ else "scan_tc2_kernel<FILTER> / scan_tc_kernel<FILTER> (full-shard level)",
                "kernel_ms": scan_avg, "algorithmic_bytes": alg_bytes, "share_of_step": scan_avg / ms_step}
         tensor = None if small_ else {
             "bound": "tensor", "achieved": tf_ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": tf_ach / peaks["bf16_tflops"], "peak_kind": peaks_kind + " burst (kernel timed alone)",
-            "kernel": "scan_tc_kernel<FILTER> (full-DB level)", "kernel_ms": scan_avg,
+            "kernel": "scan_tc2_kernel<FILTER> / scan_tc_kernel<FILTER> (full-shard level)", "kernel_ms": scan_avg,
             "algorithmic_flops": alg_flops, "share_of_step": scan_avg / ms_step}
         return hbm, tensor
 
