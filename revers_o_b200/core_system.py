@@ -141,24 +141,38 @@ class SimpleReverso:
             return f"❌ Error deleting database: {str(e)}"
 
     def unlock_database(self, database_name):
+        """core_system.py:137-154."""
         if not database_name:
             return "❌ Please provide a database name"
-        lock = f"{self.db_root}/{database_name}/.lock"
-        if os.path.exists(lock):
-            os.remove(lock)
-            return f"✅ Unlocked database: {database_name}"
-        return f"ℹ️ Database was not locked: {database_name}"
+        db_path = f"{self.db_root}/{database_name}"
+        if not os.path.exists(db_path):
+            return f"❌ Database not found: {database_name}"
+        lock_file = os.path.join(db_path, ".lock")
+        if os.path.exists(lock_file):
+            try:
+                os.remove(lock_file)
+                return f"✅ Removed lock file from database: {database_name}"
+            except Exception as e:
+                return f"❌ Error removing lock file: {str(e)}"
+        return f"ℹ️ No lock file found for database: {database_name}"
 
     # ---- detection (third-party; injected) -------------------------------------------------------
-    def detect_regions(self, image, text_prompt):
-        """core_system.py:226-318.  Returns the number of regions; the detector only PRODUCES masks."""
+    def detect_regions(self, image, text_prompt=None):
+        """core_system.py:237-318.  Returns the number of regions; the detector only PRODUCES masks.  Like the reference it
+        falls back to the generic prompt "object" and clears the previous detections / embeddings first (:239-246)."""
+        if text_prompt is None:
+            text_prompt = "object"
+        print(f"🔍 Detecting regions with prompt: '{text_prompt}'")
+        self.detected_regions = []
+        self.region_embeddings = None
+        self.query_embedding_for_search = None
         try:
             if self._detector is None:
                 return 0 if self._fail("GroundedSAM detector not available in this environment") else 0
             pil = self._to_pil(image)
             self.detected_regions = self._detector(pil, text_prompt)
             n = len(self.detected_regions) if self.detected_regions is not None else 0
-            print(f"✅ Detected {n} regions")
+            print(f"✅ Found {n} regions")
             return n
         except Exception as e:
             print(f"❌ Detection error: {e}")
@@ -282,88 +296,107 @@ class SimpleReverso:
         self._stop_requested = True
 
     # ---- ingest ------------------------------------------------------------------------------------
-    def create_database(self, folder_path, database_name, text_prompt="person . car . building .", use_direct_pe=False,
-                        resume_from_checkpoint=True, include_subfolders=False, progress_callback=None):
-        """core_system.py:461-648.  Orchestration is unchanged in meaning; the checkpoint feature is dead code in
-        the reference and is not reproduced."""
+    def create_database(self, folder_path, database_name, text_prompt="person . car . building", use_direct_pe=False,
+                        progress_callback=None, resume_from_checkpoint=False, include_subfolders=False):
+        """core_system.py:461-648: same signature, defaults, status lines and return text.  The checkpoint feature is dead
+        code in the reference (json/datetime never imported) and is not reproduced: `resume_from_checkpoint`
+        is accepted and ignored."""
         status_messages = []
 
-        def log_status(msg, progress=None):
-            print(msg)
-            status_messages.append(msg)
+        def log_status(message, progress_value=None):
+            print(message)
+            status_messages.append(message)
             if progress_callback:
                 try:
-                    progress_callback(msg, progress)
+                    progress_callback(message, progress_value)
                 except Exception:
                     pass
-            return msg
+            return "\n".join(status_messages)
 
         try:
             if not os.path.exists(folder_path):
                 return log_status(f"❌ Folder not found: {folder_path}")
             if not database_name:
                 return log_status("❌ Please provide a database name")
-            exts = (".jpg", ".jpeg", ".png", ".bmp", ".tiff", ".webp")
-            files = []
+            os.makedirs(self.db_root, exist_ok=True)
+            db_path = os.path.join(self.db_root, database_name)
+            log_status(f"📁 Creating database '{database_name}' from {folder_path}")
+            image_extensions = (".jpg", ".jpeg", ".png", ".bmp", ".tiff", ".webp")
+            image_files = []
             if include_subfolders:
                 for root, _, fs in os.walk(folder_path):
-                    files += [os.path.join(root, f) for f in fs if f.lower().endswith(exts)]
+                    image_files += [os.path.join(root, f) for f in fs if f.lower().endswith(image_extensions)]
             else:
-                files = [os.path.join(folder_path, f) for f in os.listdir(folder_path) if f.lower().endswith(exts)]
-            files.sort()
-            if not files:
+                image_files = [os.path.join(folder_path, f) for f in os.listdir(folder_path) if f.lower().endswith(image_extensions)]
+            image_files.sort()                      # the reference keeps os.listdir order (arbitrary); sorted is one such order
+            if not image_files:
                 return log_status(f"❌ No images found in {folder_path}")
-            log_status(f"📁 Found {len(files)} images", 0.0)
+            log_status(f"📊 Found {len(image_files)} images to process", 0.1)
+            if include_subfolders:
+                log_status("📂 Including images from subfolders")
+            log_status(f"🔧 Processing mode: {'Direct PE' if use_direct_pe else 'GroundedSAM + PE'}")
+            log_status(f"📂 Database will be stored at: {db_path}")
 
-            db_path = f"{self.db_root}/{database_name}"
             os.makedirs(db_path, exist_ok=True)
             client = B200VectorDB(path=None, device=self.device)
             processed = failed = 0
-            for n, path in enumerate(files):
+            for i, image_path in enumerate(image_files):
                 if self._stop_requested:
-                    log_status("🛑 Stop requested. Progress saved.")
+                    log_status("🛑 Stop requested. Saving progress...")
                     return "\n".join(status_messages) + "\n\n⏸️ Processing stopped. You can resume later."
+                filename = os.path.basename(image_path)
+                log_status(f"🔄 Processing {i + 1}/{len(image_files)}: {filename}", 0.1 + (0.7 * (i / len(image_files))))
                 try:
                     from PIL import Image
-                    image = Image.open(path).convert("RGB")
+                    image = Image.open(image_path).convert("RGB")
                     if use_direct_pe:
-                        embs, metas = self.process_image_direct_pe(image)
+                        embeddings, metadata_list = self.process_image_direct_pe(image)
+                        log_status(f"✅ Extracted global embedding for {filename}")
                     else:
-                        if self.detect_regions(image, text_prompt) == 0:
+                        num_regions = self.detect_regions(image, text_prompt)
+                        if num_regions > 0:
+                            embeddings, metadata_list = self.extract_embeddings(image)
+                            log_status(f"✅ Found {num_regions} regions, extracted {len(embeddings)} embeddings in {filename}")
+                        else:
+                            log_status(f"⚠️ No regions found in {filename}, skipping")
                             failed += 1
                             continue
-                        embs, metas = self.extract_embeddings(image)
-                    for m in metas:
-                        m["image_source"] = path
-                        m["filename"] = os.path.basename(path)
-                        m.setdefault("original_region_id", m["region_id"])
-                    self._partial_embeddings += embs
-                    self._partial_metadata += metas
+                    for meta_item in metadata_list:
+                        meta_item["image_source"] = image_path
+                        meta_item["filename"] = filename
+                        # a new UUID per point; the extraction-time id is kept in the payload (core_system.py:571-574)
+                        meta_item["original_region_id"] = meta_item.get("region_id", str(uuid.uuid4()))
+                        meta_item["region_id"] = str(uuid.uuid4())
+                    self._partial_embeddings.extend(embeddings)
+                    self._partial_metadata.extend(metadata_list)
                     processed += 1
-                    self._last_processed_file = path
-                    log_status(f"✅ {os.path.basename(path)}: {len(embs)} regions", 0.8 * (n + 1) / len(files))
+                    self._last_processed_file = image_path
                 except Exception as e:
+                    log_status(f"❌ Error processing {filename}: {str(e)}")
                     failed += 1
-                    log_status(f"❌ Error processing {os.path.basename(path)}: {e}")
+                    continue
             if not self._partial_embeddings:
                 return log_status("❌ No embeddings extracted from any images")
 
             vector_dim = self._partial_embeddings[0].shape[0]
             collection_name = f"{COLLECTION_PREFIX}{database_name}"
-            client.recreate_collection(collection_name=collection_name,
-                                       vectors_config=models.VectorParams(size=vector_dim, distance=models.Distance.COSINE))
-            log_status(f"📦 Recreated collection: {collection_name}", 0.8)
+            try:
+                client.recreate_collection(collection_name=collection_name,
+                                           vectors_config=models.VectorParams(size=vector_dim, distance=models.Distance.COSINE))
+                log_status(f"📦 Recreated collection: {collection_name}", 0.8)
+            except Exception as e:
+                log_status(f"ℹ️ Note: Collection {collection_name} might already exist or error: {e}")
             points = [models.PointStruct(id=meta["region_id"], vector=emb.cpu().numpy(), payload=meta)
                       for emb, meta in zip(self._partial_embeddings, self._partial_metadata)]
             for j in range(0, len(points), UPSERT_BATCH):
                 if self._stop_requested:
                     log_status("🛑 Stop requested during database storage. Progress saved.")
                     return "\n".join(status_messages) + "\n\n⏸️ Processing stopped. You can resume later."
-                batch = points[j:j + UPSERT_BATCH]
-                client.upsert(collection_name=collection_name, points=batch)
+                batch_points = points[j:j + UPSERT_BATCH]
+                client.upsert(collection_name=collection_name, points=batch_points)
                 log_status(f"💾 Stored batch {j // UPSERT_BATCH + 1}/{(len(points) + UPSERT_BATCH - 1) // UPSERT_BATCH} "
-                           f"({len(batch)} points)", 0.8 + 0.1 * j / len(points))
-            client.save(db_path)
+                           f"({len(batch_points)} points)", 0.8 + (0.1 * (j / len(points))))
+            client.save(db_path)                    # qdrant's local mode persisted implicitly; this store is explicit
             client.path = db_path
             self.vector_db = client
             self.current_database = collection_name
@@ -373,7 +406,7 @@ class SimpleReverso:
                 log_status(f"⚠️ Failed to process: {failed} images")
             log_status(f"🔍 Total embeddings stored: {len(self._partial_embeddings)}")
             log_status(f"🎯 Database '{database_name}' ready for searching!", 1.0)
-        except Exception as e:
+        except Exception as e:                      # the UI shows the text; nothing raises into Gradio (ui.py:102-104)
             log_status(f"❌ Error creating database: {e}")
         finally:
             self._stop_requested = False

@@ -77,8 +77,12 @@ def test_ui_call_pattern(dev, tmp_path, mode):
         make_image(i).save(folder / f"img{i}.png")
     # ui.py:86-94 build_database_ui
     msgs = []
-    status = r.create_database(str(folder), "t", "object .", False, True, False, lambda m, p=None: msgs.append(m))
+    status = r.create_database(folder_path=str(folder), database_name="t", text_prompt="object .", use_direct_pe=False,
+                               resume_from_checkpoint=True, include_subfolders=False,
+                               progress_callback=lambda m, p=None: msgs.append(m))            # keywords, as ui.py:86-94
     assert "ready for searching" in status and r.vector_db and r.current_database == "simple_reverso_t"
+    assert any(m.startswith("🔄 Processing 1/6: img0.png") for m in msgs) and any("Stored batch 1/1 (18 points)" in m for m in msgs)
+    assert "✅ Found 4 regions, extracted 3 embeddings in img0.png" in msgs and "✅ Successfully processed: 6 images" in msgs
     assert r.vector_db.count(r.current_database) == 6 * 3                 # one region of four is empty
     assert r.list_databases() == ["t"]
     # ui.py:47-53 detect_and_extract_ui on a query image that is in the DB
