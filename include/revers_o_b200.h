@@ -69,7 +69,8 @@ size_t rvo_db_bytes(int64_t n_rows, int32_t d);
  *            tiled_row0 <  0: plain row-major [n, dst_ld] (dst_ld % 8 == 0, >= d), pad columns zeroed.
  *   dst_f32  [dev] float32 [n, d] row pitch d: the normalised rows in float32.  May be NULL.
  * A zero row stays zero (qdrant divides by eps; the reference never stores one, see
- * core_system.py:402-404).
+ * core_system.py:402-404).  A row with a NaN / Inf component is stored as the zero vector too (the reference
+ * would store NaNs, which then score NaN against every query and sort to the top of every result).
  * ---------------------------------------------------------------------------------------------- */
 int rvo_normalize_rows(const float* src, int64_t n, int32_t d, int64_t src_ld,
                        uint16_t* dst_bf16, int64_t dst_ld, int64_t tiled_row0, float* dst_f32, void* stream);

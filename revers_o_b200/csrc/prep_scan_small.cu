@@ -28,13 +28,16 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
     const float nrm = sqrtf(ss);
-    const float inv = nrm != 0.f ? 1.0f / nrm : 0.f;  // zero rows stay zero
+    // zero rows stay zero; a row with a NaN / Inf component (norm not finite) is stored as the zero vector as well, so that one
+    // bad vector cannot poison every search of the collection with NaN scores (it then scores 0 against everything)
+    const bool usable = nrm != 0.f && isfinite(nrm);
+    const float inv = usable ? 1.0f / nrm : 0.f;
     if (dst_bf16) {
         if (tiled_row0 < 0) {
             uint16_t* o = dst_bf16 + (size_t)row * (size_t)dst_ld;
             float e2 = 0.f;  // ||bf16(q_hat) - q_hat||^2: the exact rounding error of THIS query operand
             for (long long i = lane; i < dst_ld; i += 32) {
-                const float v = i < d ? s[i] * inv : 0.f;
+                const float v = (usable && i < d) ? s[i] * inv : 0.f;
                 const __nv_bfloat16 b = __float2bfloat16_rn(v);
                 const float e = __bfloat162float(b) - v;
                 e2 = fmaf(e, e, e2);
@@ -48,14 +51,14 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
         } else {
             const int nk = (int)(dst_ld / kTileCols);
             for (int i = lane; i < (int)dst_ld; i += 32) {
-                const float v = i < d ? s[i] * inv : 0.f;
+                const float v = (usable && i < d) ? s[i] * inv : 0.f;
                 dst_bf16[tiled_offset(tiled_row0 + row, i, nk)] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
             }
         }
     }
     if (dst_f32) {
         float* o = dst_f32 + (size_t)row * (size_t)f32_ld;
-        for (long long i = lane; i < f32_ld; i += 32) o[i] = i < d ? s[i] * inv : 0.f;
+        for (long long i = lane; i < f32_ld; i += 32) o[i] = (usable && i < d) ? s[i] * inv : 0.f;
     }
 }
 

@@ -401,3 +401,29 @@ def test_degenerate_queries_and_shapes(dev, nq):
     assert cnt[1] == 50 and np.all(sc[1, :50] == 0.0)
     keep = [i for i in range(nq) if i != 1]
     assert_topk_match(ids[keep], sc[keep], cnt[keep], [ref[i] for i in keep], 50, TOL, "degenerate")
+
+
+def test_non_finite_vectors_are_stored_as_zero_vectors(dev):
+    """A NaN / Inf component would turn every score against that row into NaN and float it to the top of every search (the
+    reference's numpy argsort does the same).  The ingest kernel stores such a row as the zero vector instead, and a
+    non-finite query scores 0 against everything."""
+    from revers_o_b200 import ops
+    rs = np.random.RandomState(5)
+    n, d, k = 5000, 128, 5
+    x = rs.randn(n, d).astype(np.float32)
+    x[7, 3] = np.nan
+    x[9, 0] = np.inf
+    db, _ = ops.normalize_rows(torch.from_numpy(x).to(dev), db=ops.db_alloc(n, d, dev))
+    rows = ops.untile_rows(db, n, d).float()
+    assert torch.isfinite(rows).all() and float(rows[7].abs().sum()) == 0.0 and float(rows[9].abs().sum()) == 0.0
+    q = rs.randn(6, d).astype(np.float32)
+    q[2, 5] = np.nan
+    # the sanitised query ties with all 5000 rows at score 0: beyond the fused path's capacity, answered by the exact protocol
+    a, b, c = ops.search_topk_exact(db, n, d, torch.from_numpy(q).to(dev), k)
+    torch.cuda.synchronize()
+    ids, sc, cnt = a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()
+    assert np.isfinite(sc).all() and np.all(cnt == k) and np.all(sc[2] == 0.0)
+    good = [0, 1, 3, 4, 5]
+    xf = x.copy(); xf[7] = 0; xf[9] = 0
+    ref = O.search_batch(O.round_to_bf16(O._cosine_prepare(xf)), q[good], k, None, db_is_normalized=True)
+    assert_topk_match(ids[good], sc[good], cnt[good], ref, k, TOL, "nonfinite")
