@@ -29,7 +29,7 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static std::atomic<long long> opt_force_path{0}, opt_m_sub{0}, opt_cand_cap{32768}, opt_final_ratio{48}, opt_time_scan{0};
+static std::atomic<long long> opt_force_path{0}, opt_m_sub{0}, opt_cand_cap{32768}, opt_final_ratio{48}, opt_time_scan{0}, opt_hot{1};
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static bool g_ev_valid = false;
 
@@ -162,13 +162,15 @@ struct SearchPlan {
     float* qn;
     uint16_t* qb;
     float* tau;       // [n_levels+1][nq_pad]
+    float* tau_hot;   // [nq_pad] hot threshold of the LAST level (scan_tc.cuh kHotSplit)
+    int hot_rank;     // rank (in the sample the last threshold comes from) whose score becomes tau_hot
     float* margin;    // [nq_pad] per-query admission margin (common.cuh query_margin)
     int* cnt;         // [n_levels+1][nq_pad]
     unsigned long long* cand;
     float* dense;
     long long dense_ld;
     unsigned long long *bufA, *bufB;
-    size_t zero_off, zero_bytes;  // region cleared with one memset at the start of a call
+    size_t cnt_bytes;             // candidate counters (multiple of 16 bytes), cleared by the normalise launch
     size_t bytes;
 };
 
@@ -185,9 +187,7 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
     if (sp->small) {
         sp->K2 = next_pow2_host(k);
         const long long ld = (n_rows + 63) / 64 * 64;
-        sp->zero_off = ar.off;
         sp->qn = ar.take<float>((size_t)RVO_SMALL_Q * sp->d_pad, 1024);
-        sp->zero_bytes = ar.off - sp->zero_off;
         sp->dense = ar.take<float>((size_t)RVO_SMALL_Q * (size_t)(ld > 0 ? ld : 64));
         sp->dense_ld = ld > 0 ? ld : 64;
         const size_t e1 = reduce_buf_elems(n_rows > 0 ? n_rows : 1, k > sp->K2 ? k : sp->K2);
@@ -231,16 +231,32 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
             sp->n_levels = L + 1;
         }
         sp->seed_cols = scan_tc_sample_rows(n_rows, sp->tc, sp->seed_stride);
-        sp->zero_off = ar.off;
         sp->qb = ar.take<uint16_t>((size_t)nq_pad * sp->d_pad, 1024);
-        sp->cnt = ar.take<int>((size_t)(sp->n_levels + 1) * nq_pad * kCandSplit);
-        sp->zero_bytes = ar.off - sp->zero_off;
-        sp->qn = ar.take<float>((size_t)nq * sp->d_pad, 1024);
+        sp->cnt_bytes = align_up((size_t)(sp->n_levels + 1) * nq_pad * kCandSegs * sizeof(int), 16);
+        sp->cnt = (int*)ar.take<char>(sp->cnt_bytes, 256);
+        sp->qn = ar.take<float>((size_t)nq_pad * sp->d_pad, 1024);
         sp->tau = ar.take<float>((size_t)(sp->n_levels + 1) * nq_pad);
         sp->margin = ar.take<float>((size_t)nq_pad);
+        sp->tau_hot = ar.take<float>((size_t)nq_pad);
+        {
+            // hot threshold: aim at ~kHotTarget rows of the shard above it.  The last threshold level sees `prev` rows (the seed
+            // sample, or the previous FILTER level's tile sample): the r-th best of that sample has about r * n_rows / prev rows of
+            // the shard above it; r >= 10 keeps the relative spread of that count (1/sqrt(r)) small enough that fewer than k hot
+            // rows (-> general path) stays a < 1e-3 event per query.
+            constexpr double kHotTarget = 600.0;
+            long long prev = sp->seed_cols;
+            if (sp->n_levels >= 2) {
+                const long long st = sp->level_stride[sp->n_levels - 2];
+                prev = (supers + st - 1) / st * T;
+            }
+            long long r = (long long)(kHotTarget * (double)prev / (double)(n_rows > 0 ? n_rows : 1) + 0.999);
+            if (r < 10) r = 10;
+            if (r > k) r = k;
+            sp->hot_rank = (int)r;
+        }
         sp->dense_ld = (sp->seed_cols + 63) / 64 * 64;
         sp->dense = ar.take<float>((size_t)nq_pad * (size_t)sp->dense_ld);
-        if (sp->n_levels > 0) sp->cand = ar.take<unsigned long long>((size_t)nq_pad * kCandSplit * (size_t)sp->cap);
+        if (sp->n_levels > 0) sp->cand = ar.take<unsigned long long>((size_t)nq_pad * kCandSegs * (size_t)sp->cap);
         sp->bufA = ar.take<unsigned long long>((size_t)nq * sp->K2);
         sp->bufB = nullptr;
     }
@@ -253,9 +269,11 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
 }
 
 static int prep_queries(const SearchPlan& sp, const float* queries, int nq, int d, void* ws, cudaStream_t stream) {
-    RVO_CUDA(cudaMemsetAsync((char*)ws + sp.zero_off, 0, sp.zero_bytes, stream));
+    // one launch: normalise, zero the padding rows of the query operand, clear the candidate counters (no memset node)
+    (void)ws;
     return launch_normalize_rows(queries, nq, d, d, sp.small ? nullptr : sp.qb, sp.d_pad, -1, sp.qn, sp.d_pad, stream,
-                                 sp.small ? nullptr : sp.margin);
+                                 sp.small ? nullptr : sp.margin, sp.small ? RVO_SMALL_Q : sp.tc.nq_pad,
+                                 sp.small ? nullptr : (void*)sp.cnt, sp.small ? 0 : sp.cnt_bytes);
 }
 
 }  // namespace rvo
@@ -293,6 +311,7 @@ int rvo_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "cand_cap")) opt_cand_cap = value;
     else if (!strcmp(name, "final_ratio")) opt_final_ratio = value;
     else if (!strcmp(name, "time_scan")) opt_time_scan = value;
+    else if (!strcmp(name, "hot")) opt_hot = value;
     else if (!strcmp(name, "pool_path")) g_force_cuda_core_pool = value == 1;
     else if (!strcmp(name, "pdl")) g_use_pdl = value;
     else if (!strcmp(name, "select_trace")) opt_select_trace = value;
@@ -466,20 +485,26 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
     }
     sa.K = k;
     sa.tau_out = sp.tau;
+    const bool seed_is_last = sp.n_levels == 1;    // the seed threshold feeds the full scan directly: it also proposes tau_hot
     if (k <= kSeedTauMaxK)   // one pass + one 512-key sort: k-th largest of the per-thread maxima (select.cuh)
-        rc = launch_seed_tau(sp.dense, sp.dense_ld, sp.seed_cols, nq, nq_pad, k, sp.margin, score_threshold, sp.tau, stream);
-    else
+        rc = launch_seed_tau(sp.dense, sp.dense_ld, sp.seed_cols, nq, nq_pad, k, sp.margin, score_threshold, sp.tau, stream,
+                             sp.hot_rank, seed_is_last ? sp.tau_hot : nullptr);
+    else {
+        sa.hot_rank = sp.hot_rank;
+        sa.tau_hot_out = seed_is_last ? sp.tau_hot : nullptr;
         rc = launch_select(sa, nq_pad, stream);
+    }
     if (rc) return rc;
 
     // FILTER levels: each tightens tau on a larger tile sample; the last one scans every row
+    const bool use_hot = opt_hot.load() != 0;
     for (int L = 0; L < sp.n_levels; ++L) {
         const bool last = L == sp.n_levels - 1;
-        int* cnt = sp.cnt + (size_t)L * nq_pad * kCandSplit;
+        int* cnt = sp.cnt + (size_t)L * nq_pad * kCandSegs;
         const float* tau_in = sp.tau + (size_t)L * nq_pad;
         if (last && (rc = scan_timer(true, stream))) return rc;
         rc = launch_scan_tc(kModeFilter, db, n_rows, sp.level_stride[L], sp.d_pad, sp.qb, sp.tc, tau_in, sp.cand, cnt, sp.cap,
-                            nullptr, 0, sm, stream);
+                            nullptr, 0, sm, stream, last && use_hot ? sp.tau_hot : nullptr, kCandSegs);
         if (rc) return rc;
         if (last && (rc = scan_timer(false, stream))) return rc;
         memset(&sa, 0, sizeof(sa));
@@ -487,7 +512,7 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
         sa.keys = sp.cand;
         sa.range_lo = tau_in;
         sa.cnt = cnt;
-        sa.nseg = kCandSplit;
+        sa.nseg = kCandSegs;
         sa.cap = sp.cap;
         sa.margin = sp.margin;
         sa.score_floor = score_threshold;
@@ -496,12 +521,21 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
             sa.tau_out = sp.tau + (size_t)(L + 1) * nq_pad;
             sa.tau_prev = tau_in;
             sa.tau_k = k;
+            if (L == sp.n_levels - 2) {   // this level's threshold feeds the full scan: propose tau_hot as well
+                sa.hot_rank = sp.hot_rank;
+                sa.tau_hot_out = sp.tau_hot;
+            }
             rc = launch_select(sa, nq_pad, stream);
             if (rc) return rc;
         } else {
             // last level: exact candidate selection fused with the fp32 re-score and the final ordering
             sa.K = sp.K2;
             sa.trace = (unsigned long long*)(uintptr_t)opt_select_trace.load();
+            if (use_hot) {
+                sa.tau_hot = sp.tau_hot;
+                sa.hot_seg0 = kCandSplit;
+                sa.hot_nseg = kHotSplit;
+            }
             rc = launch_select_final(sa, fa, nq, stream);
             if (rc) return rc;
         }

@@ -14,15 +14,37 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
                                                              long long src_ld, uint16_t* __restrict__ dst_bf16,
                                                              long long dst_ld, long long tiled_row0,
                                                              float* __restrict__ dst_f32, long long f32_ld,
-                                                             float* __restrict__ margin_out) {
+                                                             float* __restrict__ margin_out, long long n_pad_rows,
+                                                             uint4* __restrict__ zero_base, long long zero_u4) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the seed scan may pre-launch (it waits for this grid)
-    if (row >= n) return;
+    // scratch the search driver needs cleared (candidate counters): folded into this launch instead of a separate memset node
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < zero_u4; i += (long long)gridDim.x * blockDim.x)
+        zero_base[i] = make_uint4(0, 0, 0, 0);
+    if (row >= n) {
+        // padding rows of the query operand (row-major outputs only): all-zero, margin 0
+        if (row < n_pad_rows && tiled_row0 < 0) {
+            if (dst_bf16)
+                for (long long i = lane; i < dst_ld; i += 32) dst_bf16[(size_t)row * (size_t)dst_ld + i] = 0;
+            if (dst_f32)
+                for (long long i = lane; i < f32_ld; i += 32) dst_f32[(size_t)row * (size_t)f32_ld + i] = 0.f;
+            if (margin_out && lane == 0) margin_out[row] = 0.f;
+        }
+        return;
+    }
     const float* s = src + (size_t)row * (size_t)src_ld;
+    // sum of squares, scaled by the row's largest magnitude so that rows with huge (but finite) components do not overflow
+    // to inf and silently become the zero vector
+    float amax = 0.f;
+    for (int i = lane; i < d; i += 32) amax = fmaxf(amax, fabsf(s[i]));   // fmaxf drops NaNs: caught below through ss
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+    const bool rescale = amax > 1e18f || (amax < 1e-18f && amax > 0.f);
+    const float pre = rescale ? 1.0f / amax : 1.0f;
     float ss = 0.f;
     for (int i = lane; i < d; i += 32) {
-        const float v = s[i];
+        const float v = s[i] * pre;
         ss = fmaf(v, v, ss);
     }
 #pragma unroll
@@ -31,7 +53,7 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
     // zero rows stay zero; a row with a NaN / Inf component (norm not finite) is stored as the zero vector as well, so that one
     // bad vector cannot poison every search of the collection with NaN scores (it then scores 0 against everything)
     const bool usable = nrm != 0.f && isfinite(nrm);
-    const float inv = usable ? 1.0f / nrm : 0.f;
+    const float inv = usable ? pre / nrm : 0.f;
     if (dst_bf16) {
         if (tiled_row0 < 0) {
             uint16_t* o = dst_bf16 + (size_t)row * (size_t)dst_ld;
@@ -64,11 +86,14 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
 
 int launch_normalize_rows(const float* src, long long n, int d, long long src_ld, uint16_t* dst_bf16, long long dst_ld,
                           long long tiled_row0, float* dst_f32, long long f32_ld, cudaStream_t stream,
-                          float* margin_out) {
-    if (n <= 0) return RVO_OK;
-    const long long blocks = (n + 7) / 8;
+                          float* margin_out, long long n_pad_rows, void* zero_base, size_t zero_bytes) {
+    if (n_pad_rows < n) n_pad_rows = n;
+    if (n_pad_rows <= 0 && zero_bytes == 0) return RVO_OK;
+    long long blocks = (n_pad_rows + 7) / 8;
+    if (blocks < 1) blocks = 1;
     normalize_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, n, d, src_ld, dst_bf16, dst_ld, tiled_row0, dst_f32,
-                                                                f32_ld, margin_out);
+                                                                f32_ld, margin_out, n_pad_rows, (uint4*)zero_base,
+                                                                (long long)(zero_bytes / 16));
     RVO_LAUNCHED();
     return RVO_OK;
 }

@@ -175,7 +175,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
         uint32_t wcount = 0;
         int cur_qb = -1;
         // candidate appends in flight from the previous TMEM slot (FILTER mode)
-        int pend_n = 0, pend_q0 = 0, pend_seg = 0;
+        int pend_n = 0, pend_q0 = 0;
         uint32_t pend_row = 0;
         int pend_pos[4] = {0, 0, 0, 0};
         unsigned long long pend_ent[4] = {0ull, 0ull, 0ull, 0ull};
@@ -192,12 +192,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
             const int seg = (int)(st % kCandSplit);
             const uint32_t tbuf = p.num_qblk > 1 ? (wcount & 1u) : 0u;
             const float* tau_s = s_tau + tbuf * 256;
+            const float* tauh_s = s_tau + 512 + tbuf * 256;
+            const int hot_seg = kCandSplit + (int)(st % kHotSplit);   // hot sub-list of this super-tile (search path only)
 
             if (MODE == kModeFilter && qb != cur_qb) {
                 // double-buffered by work item; the barrier also orders "everyone left work w-1" before
                 // anyone overwrites that buffer at work w+1
                 const int i = ew * 32 + lane;
-                if (i < nq_blk) s_tau[tbuf * 256 + i] = p.tau[q0 + i];
+                if (i < nq_blk) {
+                    s_tau[tbuf * 256 + i] = p.tau[q0 + i];
+                    s_tau[512 + tbuf * 256 + i] = p.tau_hot ? p.tau_hot[q0 + i] : __int_as_float(0x7f800000);
+                }
                 epi_bar_sync();
                 cur_qb = p.num_qblk > 1 ? -1 : qb;       // several query blocks: reload every work item
             }
@@ -239,14 +244,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                             for (int u = 0; u < 4; ++u)
                                 if (e + u < cnt) {
                                     ent[u] = s_queue[(e + u) * kEpiThreads + qt];
-                                    slot_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(ent[u] & 0xFFFFu)) * kCandSplit + seg, 1);
+                                    slot_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(ent[u] & 0xFFFFu)) * p.nseg + (int)((ent[u] >> 16) & 0xFFu), 1);
                                 }
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
                                 if (e + u < cnt && slot_pos[u] < p.cap) {
                                     const int q = q0 + (int)(ent[u] & 0xFFFFu);
                                     const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(ent[u] >> 32)));
-                                    p.cand[((size_t)q * kCandSplit + seg) * (size_t)p.cap + (size_t)slot_pos[u]] =
+                                    p.cand[((size_t)q * p.nseg + ((ent[u] >> 16) & 0xFFu)) * (size_t)p.cap + (size_t)slot_pos[u]] =
                                         ((unsigned long long)ob << 32) | (unsigned long long)key_row_bits;
                                 }
                         }
@@ -275,8 +280,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
 #pragma unroll
                                     for (int i = 0; i < 8; ++i) {
                                         if (__uint_as_float(v[g][h * 8 + i]) >= tt[i]) {
+                                            const int col = cc * 16 + h * 8 + i;
+                                            const int sg = __uint_as_float(v[g][h * 8 + i]) >= tauh_s[col] ? hot_seg : seg;
                                             s_queue[n * kEpiThreads + qt] = ((unsigned long long)v[g][h * 8 + i] << 32) |
-                                                                            (unsigned)(cc * 16 + h * 8 + i);
+                                                                            (unsigned)((sg << 16) | col);
                                             ++n;
                                         }
                                     }
@@ -297,18 +304,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                         if (u < pend_n && pend_pos[u] < p.cap) {
                             const int q = pend_q0 + (int)(pend_ent[u] & 0xFFFFu);
                             const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(pend_ent[u] >> 32)));
-                            p.cand[((size_t)q * kCandSplit + pend_seg) * (size_t)p.cap + (size_t)pend_pos[u]] =
+                            p.cand[((size_t)q * p.nseg + ((pend_ent[u] >> 16) & 0xFFu)) * (size_t)p.cap + (size_t)pend_pos[u]] =
                                 ((unsigned long long)ob << 32) | (unsigned long long)pend_row;
                         }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (u < n) {
                             pend_ent[u] = s_queue[u * kEpiThreads + qt];
-                            pend_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(pend_ent[u] & 0xFFFFu)) * kCandSplit + seg, 1);
+                            pend_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(pend_ent[u] & 0xFFFFu)) * p.nseg + (int)((pend_ent[u] >> 16) & 0xFFu), 1);
                         }
                     pend_n = n < 4 ? n : 4;
                     pend_q0 = q0;
-                    pend_seg = seg;
                     pend_row = key_row_bits;
                     if (n > 4) flush_sync(4, n);
                 }
@@ -321,7 +327,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                 if (u < pend_n && pend_pos[u] < p.cap) {
                     const int q = pend_q0 + (int)(pend_ent[u] & 0xFFFFu);
                     const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(pend_ent[u] >> 32)));
-                    p.cand[((size_t)q * kCandSplit + pend_seg) * (size_t)p.cap + (size_t)pend_pos[u]] =
+                    p.cand[((size_t)q * p.nseg + ((pend_ent[u] >> 16) & 0xFFu)) * (size_t)p.cap + (size_t)pend_pos[u]] =
                         ((unsigned long long)ob << 32) | (unsigned long long)pend_row;
                 }
         }
@@ -400,7 +406,7 @@ int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl) {
     pl->num_slots = 512 / pl->slot_w;
     if (pl->num_slots > kMaxSlots) pl->num_slots = kMaxSlots;
 
-    const size_t fixed = (size_t)kQueueCap * kEpiThreads * 8 + 2 * 256 * 4 + 512;
+    const size_t fixed = (size_t)kQueueCap * kEpiThreads * 8 + kTauSmemBytes + 512;
     const size_t budget = (size_t)kSmemLimit - fixed;
     const size_t res_bytes = (size_t)pl->nq_blk * d_pad * 2;
 
@@ -425,7 +431,7 @@ int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl) {
     pl->off_stages = res;  // multiple of 1024: nq_blk % 16 == 0 and d_pad % 64 == 0
     pl->off_queue = pl->off_stages + stages * pl->stage_bytes;
     pl->off_tau = pl->off_queue + (size_t)kQueueCap * kEpiThreads * 8;
-    pl->off_bars = pl->off_tau + 2 * 256 * 4;
+    pl->off_bars = pl->off_tau + kTauSmemBytes;
     pl->smem_bytes = pl->off_bars + 512;
     pl->pair = 0;
     // query block too large to stay resident: CTA pairs halve the query operand's L2->SM traffic (scan_tc2.cu)
@@ -446,11 +452,12 @@ long long scan_tc_sample_rows(long long n_rows, const TcPlan& pl, long long supe
 
 int launch_scan_tc(int mode, const uint16_t* db, long long n_rows, long long super_stride, int d_pad,
                    const uint16_t* q_bf16, const TcPlan& pl, const float* tau, unsigned long long* cand,
-                   int* cand_cnt, int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream) {
+                   int* cand_cnt, int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream,
+                   const float* tau_hot, int nseg) {
     if (n_rows <= 0) return RVO_OK;
     if (pl.pair)
         return launch_scan_tc2(mode, db, n_rows, super_stride, d_pad, q_bf16, pl, tau, cand, cand_cnt, cap, dense, dense_ld,
-                               sm_count, stream);
+                               sm_count, stream, tau_hot, nseg);
     if (n_rows >= (1ll << 31)) {
         set_error("launch_scan_tc: shard too large (%lld rows); shard the DB", n_rows);
         return RVO_E_INVALID;
@@ -489,8 +496,10 @@ int launch_scan_tc(int mode, const uint16_t* db, long long n_rows, long long sup
     p.off_bars = (uint32_t)pl.off_bars;
     p.num_super = ((n_rows + T - 1) / T + super_stride - 1) / super_stride;
     p.tau = tau;
+    p.tau_hot = tau_hot;
     p.cand = cand;
     p.cand_cnt = cand_cnt;
+    p.nseg = nseg;
     p.cap = cap;
     p.dense = dense;
     p.dense_ld = dense_ld;

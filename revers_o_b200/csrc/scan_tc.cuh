@@ -18,6 +18,11 @@ constexpr int kQueueCap = 12;                             // smem survivor queue
 constexpr int kSmemLimit = 232448;                        // 227 KiB opt-in dynamic smem per CTA
 constexpr int kCandSplit = 16;                            // sub-lists per query: spreads the append atomics over
                                                           // 16x more L2 addresses (same-address atomics serialise)
+constexpr int kHotSplit = 4;                              // extra "hot" sub-lists per query (search only): survivors whose score
+                                                          // also reaches tau_hot (a proposal for "the few hundred best") go here,
+                                                          // so the final select reads ~600 keys instead of every survivor
+constexpr int kCandSegs = kCandSplit + kHotSplit;         // sub-lists per query of the search path ([safe 0..15 | hot 16..19])
+constexpr int kTauSmemBytes = 4 * 256 * 4;                // [2][256] tau + [2][256] tau_hot, double-buffered by work item
 constexpr int kModeDense = 0;
 constexpr int kModeFilter = 1;
 
@@ -29,8 +34,10 @@ struct ScanParams {
     uint32_t stage_bytes, off_stages, off_queue, off_tau, off_bars;
     // FILTER
     const float* tau;              // [nq_pad] per-query admission thresholds
-    unsigned long long* cand;      // [nq_pad][kCandSplit][cap] candidate ordering keys
-    int* cand_cnt;                 // [nq_pad][kCandSplit]; CTA b appends to sub-list b % kCandSplit
+    const float* tau_hot;          // [nq_pad] or nullptr: survivors with score >= tau_hot[q] go to a hot sub-list
+    unsigned long long* cand;      // [nq_pad][nseg][cap] candidate ordering keys
+    int* cand_cnt;                 // [nq_pad][nseg]; super-tile st appends to sub-list st % kCandSplit (hot: kCandSplit + st % kHotSplit)
+    int nseg;                      // sub-lists per query in cand / cand_cnt (kCandSplit, or kCandSegs with hot lists)
     int cap;                       // capacity of ONE sub-list
     // DENSE
     float* dense;                  // [nq_pad][dense_ld]
@@ -47,11 +54,14 @@ int plan_scan_tc(int nq, int d_pad, int force_m_sub, TcPlan* pl);   // force_m_s
 int plan_scan_tc2(const TcPlan& base, int d_pad, TcPlan* pl);
 int launch_scan_tc2(int mode, const uint16_t* db, long long n_rows, long long super_stride, int d_pad,
                     const uint16_t* q_bf16, const TcPlan& pl, const float* tau, unsigned long long* cand, int* cand_cnt,
-                    int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream);
+                    int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream, const float* tau_hot,
+                    int nseg);
 // columns of the DENSE output / rows visited when only every super_stride-th super-tile is scanned
 long long scan_tc_sample_rows(long long n_rows, const TcPlan& pl, long long super_stride);
+// tau_hot / nseg: see ScanParams (defaults: no hot lists, kCandSplit sub-lists per query)
 int launch_scan_tc(int mode, const uint16_t* db, long long n_rows, long long super_stride, int d_pad,
                    const uint16_t* q_bf16, const TcPlan& pl, const float* tau, unsigned long long* cand,
-                   int* cand_cnt, int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream);
+                   int* cand_cnt, int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream,
+                   const float* tau_hot = nullptr, int nseg = kCandSplit);
 
 }  // namespace rvo

@@ -136,7 +136,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
         const int nchunks = nq_blk / 16;
         uint32_t acc = 0;
         int cur_qb = -1;
-        int pend_n = 0, pend_q0 = 0, pend_seg = 0;
+        int pend_n = 0, pend_q0 = 0;
         uint32_t pend_row = 0;
         int pend_pos[4] = {0, 0, 0, 0};
         unsigned long long pend_ent[4] = {0ull, 0ull, 0ull, 0ull};
@@ -149,10 +149,15 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
             const int seg = (int)(st % kCandSplit);
             const uint32_t tbuf = p.num_qblk > 1 ? (acc & 1u) : 0u;
             const float* tau_s = s_tau + tbuf * 256;
+            const float* tauh_s = s_tau + 512 + tbuf * 256;
+            const int hot_seg = kCandSplit + (int)(st % kHotSplit);   // hot sub-list of this super-tile (search path only)
 
             if (MODE == kModeFilter && qb != cur_qb) {
                 const int i = ew * 32 + lane;
-                if (i < nq_blk) s_tau[tbuf * 256 + i] = p.tau[q0 + i];
+                if (i < nq_blk) {
+                    s_tau[tbuf * 256 + i] = p.tau[q0 + i];
+                    s_tau[512 + tbuf * 256 + i] = p.tau_hot ? p.tau_hot[q0 + i] : __int_as_float(0x7f800000);
+                }
                 epi_bar_sync2();
                 cur_qb = p.num_qblk > 1 ? -1 : qb;
             }
@@ -189,14 +194,14 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
                         for (int u = 0; u < 4; ++u)
                             if (e + u < cnt) {
                                 ent[u] = s_queue[(e + u) * kEpiThreads + qt];
-                                slot_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(ent[u] & 0xFFFFu)) * kCandSplit + seg, 1);
+                                slot_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(ent[u] & 0xFFFFu)) * p.nseg + (int)((ent[u] >> 16) & 0xFFu), 1);
                             }
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                             if (e + u < cnt && slot_pos[u] < p.cap) {
                                 const int q = q0 + (int)(ent[u] & 0xFFFFu);
                                 const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(ent[u] >> 32)));
-                                p.cand[((size_t)q * kCandSplit + seg) * (size_t)p.cap + (size_t)slot_pos[u]] =
+                                p.cand[((size_t)q * p.nseg + ((ent[u] >> 16) & 0xFFu)) * (size_t)p.cap + (size_t)slot_pos[u]] =
                                     ((unsigned long long)ob << 32) | (unsigned long long)key_row_bits;
                             }
                     }
@@ -224,8 +229,10 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     if (__uint_as_float(v[g][h * 8 + i]) >= tt[i]) {
+                                        const int col = cc * 16 + h * 8 + i;
+                                        const int sg = __uint_as_float(v[g][h * 8 + i]) >= tauh_s[col] ? hot_seg : seg;
                                         s_queue[n * kEpiThreads + qt] = ((unsigned long long)v[g][h * 8 + i] << 32) |
-                                                                        (unsigned)(cc * 16 + h * 8 + i);
+                                                                        (unsigned)((sg << 16) | col);
                                         ++n;
                                     }
                                 }
@@ -243,18 +250,17 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
                     if (u < pend_n && pend_pos[u] < p.cap) {
                         const int q = pend_q0 + (int)(pend_ent[u] & 0xFFFFu);
                         const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(pend_ent[u] >> 32)));
-                        p.cand[((size_t)q * kCandSplit + pend_seg) * (size_t)p.cap + (size_t)pend_pos[u]] =
+                        p.cand[((size_t)q * p.nseg + ((pend_ent[u] >> 16) & 0xFFu)) * (size_t)p.cap + (size_t)pend_pos[u]] =
                             ((unsigned long long)ob << 32) | (unsigned long long)pend_row;
                     }
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (u < n) {
                         pend_ent[u] = s_queue[u * kEpiThreads + qt];
-                        pend_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(pend_ent[u] & 0xFFFFu)) * kCandSplit + seg, 1);
+                        pend_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(pend_ent[u] & 0xFFFFu)) * p.nseg + (int)((pend_ent[u] >> 16) & 0xFFu), 1);
                     }
                 pend_n = n < 4 ? n : 4;
                 pend_q0 = q0;
-                pend_seg = seg;
                 pend_row = key_row_bits;
                 if (n > 4) flush_sync(4, n);
             }
@@ -265,7 +271,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
                 if (u < pend_n && pend_pos[u] < p.cap) {
                     const int q = pend_q0 + (int)(pend_ent[u] & 0xFFFFu);
                     const uint32_t ob = f32_orderable(__uint_as_float((uint32_t)(pend_ent[u] >> 32)));
-                    p.cand[((size_t)q * kCandSplit + pend_seg) * (size_t)p.cap + (size_t)pend_pos[u]] =
+                    p.cand[((size_t)q * p.nseg + ((pend_ent[u] >> 16) & 0xFFu)) * (size_t)p.cap + (size_t)pend_pos[u]] =
                         ((unsigned long long)ob << 32) | (unsigned long long)pend_row;
                 }
         }
@@ -285,21 +291,22 @@ int plan_scan_tc2(const TcPlan& base, int d_pad, TcPlan* pl) {
     pl->resident = 0;
     pl->m_sub = 2;                                   // a pair covers 2 x 128 rows
     pl->stage_bytes = (size_t)kSubTileBytes + (size_t)base.nq_blk * 64;
-    const size_t fixed = (size_t)kQueueCap * kEpiThreads * 8 + 2 * 256 * 4 + 512;
+    const size_t fixed = (size_t)kQueueCap * kEpiThreads * 8 + kTauSmemBytes + 512;
     size_t stages = ((size_t)kSmemLimit - fixed) / pl->stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     pl->num_stages = (int)stages;
     pl->off_stages = 0;
     pl->off_queue = stages * pl->stage_bytes;
     pl->off_tau = pl->off_queue + (size_t)kQueueCap * kEpiThreads * 8;
-    pl->off_bars = pl->off_tau + 2 * 256 * 4;
+    pl->off_bars = pl->off_tau + kTauSmemBytes;
     pl->smem_bytes = pl->off_bars + 512;
     return RVO_OK;
 }
 
 int launch_scan_tc2(int mode, const uint16_t* db, long long n_rows, long long super_stride, int d_pad,
                     const uint16_t* q_bf16, const TcPlan& pl, const float* tau, unsigned long long* cand, int* cand_cnt,
-                    int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream) {
+                    int cap, float* dense, long long dense_ld, int sm_count, cudaStream_t stream, const float* tau_hot,
+                    int nseg) {
     if (n_rows <= 0) return RVO_OK;
     if (super_stride < 1) super_stride = 1;
     const long long row_blocks = (n_rows + kBlockM - 1) / kBlockM;
@@ -334,8 +341,10 @@ int launch_scan_tc2(int mode, const uint16_t* db, long long n_rows, long long su
     p.off_bars = (uint32_t)pl.off_bars;
     p.num_super = ((n_rows + T - 1) / T + super_stride - 1) / super_stride;
     p.tau = tau;
+    p.tau_hot = tau_hot;
     p.cand = cand;
     p.cand_cnt = cand_cnt;
+    p.nseg = nseg;
     p.cap = cap;
     p.dense = dense;
     p.dense_ld = dense_ld;

@@ -46,6 +46,14 @@ struct SelectArgs {
     float score_floor;                  // the caller's score_threshold (-inf when there is none)
     int nq;                             // CTAs q >= nq only write tau_out[q] = +inf (padded query rows)
     const float* range_lo;              // optional per-query lower bound of every key's score (finer first bins)
+    // hot lists (scan_tc.cuh kHotSplit).  Threshold levels (select_kernel<false>, seed_tau) also emit
+    //   tau_hot_out[q] = max(score of the hot_rank-th best key of the sample, tau_out[q])     (no margin: a proposal only)
+    // and the final level (select_kernel<true>) first tries the sub-lists [hot_seg0, hot_seg0 + hot_nseg) alone: they hold
+    // every candidate with tensor score >= tau_hot[q], which covers the top-k whenever (k-th best hot score) - margin >= tau_hot.
+    float* tau_hot_out;
+    int hot_rank;
+    const float* tau_hot;
+    int hot_seg0, hot_nseg;
     unsigned long long* trace;          // option "select_trace": [nq][16] globaltimer stamps of the kernel's phases (debug)
 };
 
@@ -88,7 +96,7 @@ int launch_select(const SelectArgs& a, int grid_q, cudaStream_t stream);
 // the sample's k-th largest (hence of the DB's): a valid threshold from ONE pass and one 512-key sort.
 constexpr int kSeedTauMaxK = 128;
 int launch_seed_tau(const float* dense, long long dense_ld, long long n_dense, int nq, int grid_q, int k, const float* margin,
-                    float score_floor, float* tau_out, cudaStream_t stream);
+                    float score_floor, float* tau_out, cudaStream_t stream, int hot_rank = 0, float* tau_hot_out = nullptr);
 // last level fused with the fp32 re-score and the final ordering: `a` selects (a.K = candidates aimed at, a.out unused),
 // `f` supplies k, score_threshold, margin, db/qn and the outputs (f.top / f.cnt / f.K2 unused)
 int launch_select_final(const SelectArgs& a, const FinalArgs& f, int nq, cudaStream_t stream);
