@@ -38,6 +38,10 @@ extern "C" {
 #define RVO_MAX_K          512   /* largest `limit` served by rvo_search_topk                        */
 #define RVO_SMALL_Q        4     /* batches of <= RVO_SMALL_Q queries take the exact fp32 scan       */
 
+/* 16-bit feature types accepted by K1. */
+#define RVO_DTYPE_BF16     0
+#define RVO_DTYPE_F16      1
+
 /* Library / ABI version (major*10000 + minor*100 + patch). */
 int rvo_version(void);
 
@@ -68,6 +72,7 @@ size_t rvo_db_bytes(int64_t n_rows, int32_t d);
  *                             written at DB rows tiled_row0 .. tiled_row0 + n - 1 (append / overwrite);
  *            tiled_row0 <  0: plain row-major [n, dst_ld] (dst_ld % 8 == 0, >= d), pad columns zeroed.
  *   dst_f32  [dev] float32 [n, d] row pitch d: the normalised rows in float32.  May be NULL.
+ * (K1 applies the same rule to a region whose mean is zero or non-finite: its embedding is the zero vector.)
  * A zero row stays zero (qdrant divides by eps; the reference never stores one, see
  * core_system.py:402-404).  A row with a NaN / Inf component is stored as the zero vector too (the reference
  * would store NaNs, which then score NaN against every query and sort to the top of every result).
@@ -80,7 +85,9 @@ int rvo_normalize_rows(const float* src, int64_t n, int32_t d, int64_t src_ld,
  * Replaces: the per-region python loop of core_system.py:363-408 (binarise :398-400, skip empty
  *           :402-404, region embedding + normalise :406-408) with the mask-pooled definition the
  *           reference states (main.py:8-9): e_m = mean of patch features under mask m, then L2.
- *   feats   [dev] bf16  [B, P, D]   patch-feature map, D contiguous (D % 8 == 0)
+ *   feats   [dev] 16-bit float [B, P, D]  patch-feature map, D contiguous (D % 8 == 0)
+ *   feat_dtype          RVO_DTYPE_BF16 or RVO_DTYPE_F16 (what the reference's `.half()` encoder emits on CUDA,
+ *                       core_system.py:195-196): consumed as is, products accumulate in fp32
  *   masks   [dev] uint8 [B, M, P]   nonzero = patch p belongs to region m
  *   max_regions          only the first min(M, max_regions) regions of an image are visited
  *                        (core_system.py:363 uses 50); <=0 means M
@@ -91,7 +98,7 @@ int rvo_normalize_rows(const float* src, int64_t n, int32_t d, int64_t src_ld,
  *   workspace [dev]                 rvo_mask_pool_workspace_bytes(B, M, P, D) bytes, 256-B aligned
  * ---------------------------------------------------------------------------------------------- */
 size_t rvo_mask_pool_workspace_bytes(int32_t B, int32_t M, int32_t P, int32_t D);
-int rvo_mask_pool(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
+int rvo_mask_pool(const uint16_t* feats, int32_t feat_dtype, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
                   int32_t max_regions, float* out, int32_t* out_counts, int32_t* out_src, int32_t* out_total,
                   void* workspace, size_t workspace_bytes, void* stream);
 
@@ -108,7 +115,7 @@ int rvo_mask_pool(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_
  * Returns RVO_E_UNSUPPORTED for shapes outside the tensor-core kernel (D % 128 != 0, more than 64 regions
  * per image, D/128 * M_pad > 512, more than 1024 patches): call rvo_mask_pool + rvo_normalize_rows instead.
  * ---------------------------------------------------------------------------------------------- */
-int rvo_mask_pool_to_db(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
+int rvo_mask_pool_to_db(const uint16_t* feats, int32_t feat_dtype, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
                         int32_t max_regions, uint16_t* db, int64_t db_row0, float* out_f32, int32_t* out_counts,
                         int32_t* out_src, int32_t* out_total, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -191,7 +198,9 @@ int rvo_merge_topk_packed(const void* gathered, int64_t rank_stride_bytes, int32
  *           order); parity selects one of two slot sets, so a rank may run one search ahead of its peers.
  * rvo_search_topk_push = rvo_search_topk with the result written to this rank's slot of every region; returns
  * RVO_E_UNSUPPORTED for nq <= RVO_SMALL_Q or an empty shard (take the all-gather path on ALL ranks then).
- * rvo_merge_topk_exchange = rvo_merge_topk over the local region once all `world` flags show `epoch`.
+ * rvo_merge_topk_exchange = rvo_merge_topk over the local region once all `world` flags show `epoch`.  It waits like a
+ * collective would; after option "exchange_timeout_ms" (default 60000) without the peers' flags it gives up WITHOUT
+ * trapping: every out_counts[q] of the batch is -2 and the caller raises or falls back to the all-gather path.
  * ---------------------------------------------------------------------------------------------- */
 size_t rvo_exchange_bytes(int32_t world, int32_t nq_max, int32_t k_max);
 int rvo_exchange_alloc(size_t bytes, void** out_region);
@@ -224,6 +233,15 @@ int rvo_selfjoin_threshold(const uint16_t* db, int64_t n_rows, int32_t d, int64_
                            uint64_t* out_count, int32_t* out_overflowed, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* Same join with an explicit candidate capacity per query row (instead of option "cand_cap", default 32768): the host raises
+ * it and re-runs when out_overflowed > 0 — a row with more near-duplicates than the lists hold (a static video scene) is
+ * then joined exactly instead of failing.  cand_cap >= n_rows + 4096 can never overflow. */
+size_t rvo_selfjoin_workspace_bytes_ex(int32_t d, int64_t cand_cap);
+int rvo_selfjoin_threshold_ex(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad, int64_t row_lo, int64_t row_hi,
+                              float threshold, int64_t id_offset, int64_t cand_cap, int64_t* out_pairs, float* out_scores,
+                              int64_t out_cap, uint64_t* out_count, int32_t* out_overflowed, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Counters for bench.py's `gpu_launches` claim: number of kernels THIS library has launched on the
  * calling process since load (monotonic).
@@ -240,7 +258,8 @@ float rvo_last_scan_ms(void);
  *   name: "force_path" (0 auto, 1 small-q scan, 2 tcgen05 scan), "m_sub" (0 auto,1,2),
  *         "cand_cap" (candidates per query, default 32768), "final_ratio" (default 48),
  *         "time_scan" (0/1, see rvo_last_scan_ms), "pool_path" (0 auto: tensor-core mask pooling when the
- *         shape fits TMEM, 1: CUDA-core kernels)                                                */
+ *         shape fits TMEM, 1: CUDA-core kernels), "hot" (1 default: hot candidate sub-lists + one-pass final select,
+ *         0: general select only), "exchange_timeout_ms" (peer-exchange wait limit, default 60000)            */
 int rvo_set_option(const char* name, int64_t value);
 
 #ifdef __cplusplus

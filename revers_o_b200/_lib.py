@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librevers_o_b200.so")
 RVO_E_UNSUPPORTED = -5
 RVO_MAX_K = 512
 RVO_SMALL_Q = 4
+RVO_DTYPE_BF16, RVO_DTYPE_F16 = 0, 1
 
 # name -> (restype, argtypes); mirrors include/revers_o_b200.h one to one
 PROTOTYPES = {
@@ -24,9 +25,9 @@ PROTOTYPES = {
     "rvo_normalize_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                      C.c_void_p, C.c_void_p]),
     "rvo_mask_pool_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
-    "rvo_mask_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+    "rvo_mask_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "rvo_mask_pool_to_db": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+    "rvo_mask_pool_to_db": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_size_t, C.c_void_p]),
     "rvo_exchange_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
@@ -57,6 +58,10 @@ PROTOTYPES = {
     "rvo_selfjoin_threshold": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_float,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_size_t, C.c_void_p]),
+    "rvo_selfjoin_workspace_bytes_ex": (C.c_size_t, [C.c_int32, C.c_int64]),
+    "rvo_selfjoin_threshold_ex": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_float,
+                                            C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_size_t, C.c_void_p]),
     "rvo_kernel_launch_count": (C.c_int64, []),
     "rvo_last_scan_ms": (C.c_float, []),
     "rvo_set_option": (C.c_int, [C.c_char_p, C.c_int64]),

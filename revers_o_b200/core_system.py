@@ -11,15 +11,21 @@ Same class name, method names, argument meaning, return shapes and status-string
   search_similar query head                     (core_system.py:650-666)
         -> `B200VectorDB.search` (K2 scan + exact select + fp32 re-score)
 
-Out of scope and therefore injected, not re-implemented: the PE encoder
-(`encoder(image_tensor) -> [1,N,D] | [1,D]`, `preprocess(pil) -> tensor`) and the GroundedSAM detector
-(`detector(pil, prompt) -> object with .mask [n,H,W], .confidence, .class_id, .xyxy`).  With no
-argument the constructor tries the reference's own imports lazily and reports a ❌ status if they are
-absent; nothing on the similarity path depends on them.
+Out of scope and therefore not re-implemented: the PE encoder and the GroundedSAM detector.  They can be
+injected (`encoder(image_tensor) -> [1,N,D] | [1,D]`, `preprocess(pil) -> tensor`, `detector(pil, prompt) -> object with
+.mask [n,H,W], .confidence, .class_id, .xyxy`); with the no-argument constructor the UI uses (ui.py:20) they are loaded
+LAZILY through the reference's own imports and calls (`setup_device` / `load_pe_model`, core_system.py:156-203;
+`init_grounded_sam`, :205-224) the first time an image has to be embedded or detected, and a ❌ status is reported if those
+third-party packages are absent; nothing on the similarity path depends on them.
+
+Several GPUs: `SimpleReverso(devices=[0, 1, ...])`, or the environment variable RVO_DEVICES ("0,1,2,3" or "all") for the
+no-argument constructor — `create_database` / `load_database` then row-shard the collection over those GPUs inside this one
+process and `search_similar` scans all shards (vector_db.py).
 
 `parity_mode`:
-  "reference"  every non-empty region gets the normalised GLOBAL embedding, exactly what
-               core_system.py:406-407 computes today (SURVEY.md F4) — bit-for-bit UI parity;
+  "reference"  every non-empty region gets the normalised GLOBAL embedding, what core_system.py:406-407 computes today
+               (SURVEY.md F4); bf16 / fp16 tokens are consumed as they are, fp32 tokens are rounded to bf16 for the pooling
+               kernel (values then agree with the reference's to bf16 rounding of the tokens, ~1e-3 relative);
   "pooled"     the reference's stated design (main.py:8-9): patch features averaged under each mask.
 """
 from __future__ import annotations
@@ -76,15 +82,18 @@ class SimpleReverso:
     """Simplified visual investigation system (B200-native hot path)."""
 
     def __init__(self, encoder=None, preprocess=None, detector=None, parity_mode: str = "reference",
-                 db_root: str = DB_ROOT, device=None):
+                 db_root: str = DB_ROOT, device=None, devices=None):
         print("🚀 Initializing Simple Revers-o (B200-native similarity path)...")
         if parity_mode not in ("reference", "pooled"):
             raise ValueError("parity_mode must be 'reference' or 'pooled'")
         self.parity_mode = parity_mode
         self.db_root = db_root
-        self.device = torch.device(device) if device is not None else (
-            torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu"))
-        self.pe_model, self.preprocess = encoder, preprocess
+        self.device = torch.device(device) if device is not None else self.setup_device()
+        if devices is None and os.environ.get("RVO_DEVICES"):
+            spec = os.environ["RVO_DEVICES"].strip().lower()
+            devices = list(range(torch.cuda.device_count())) if spec == "all" else [int(x) for x in spec.split(",") if x.strip()]
+        self.devices = list(devices) if devices else None      # None: the vector DB lives on self.device only
+        self.pe_model, self.preprocess = encoder, preprocess   # None: loaded lazily (load_pe_model) on first use
         self._detector = detector
         self.grounded_sam = None
         self.vector_db = None
@@ -97,6 +106,87 @@ class SimpleReverso:
         self._partial_embeddings = []
         self._partial_metadata = []
         print("✅ Simple Revers-o ready!")
+
+    # ---- device / encoder / detector boundary (core_system.py:156-224; third-party, loaded lazily) ---------------
+    def setup_device(self):
+        """core_system.py:156-167, minus MPS: the similarity path is CUDA (sm_100) only."""
+        if torch.cuda.is_available():
+            device = torch.device("cuda")
+            print(f"🔥 Using CUDA: {device}")
+        else:
+            device = torch.device("cpu")
+            print(f"💻 Using CPU: {device} (embedding only: the vector search needs a B200)")
+        return device
+
+    def load_pe_model(self):
+        """core_system.py:169-203 through the reference's own imports: PE-Core-L14-336 if available, `.half()` on CUDA
+        (mixed precision, :195-196), 336-px transform (:200).  Raises ImportError when perception_models is not installed."""
+        import sys
+        if "./perception_models" not in sys.path:
+            sys.path.append("./perception_models")          # core_system.py:5
+        import core.vision_encoder.pe as pe                  # noqa: E402  (third-party, not vendored)
+        import core.vision_encoder.transforms as transforms  # noqa: E402
+        print("📚 Loading PE-Core-L14-336 (optimal for investigation)...")
+        available_configs = pe.CLIP.available_configs()
+        target_model = "PE-Core-L14-336"
+        name = target_model if target_model in available_configs else available_configs[0]
+        try:
+            pe_model = pe.CLIP.from_config(name, pretrained=True)
+            print(f"✅ Loaded {name}")
+        except Exception as e:
+            print(f"❌ Failed to load {name}: {e}")
+            pe_model = pe.CLIP.from_config(available_configs[0], pretrained=True)
+            print(f"🔄 Using fallback: {available_configs[0]}")
+        pe_model = pe_model.to(self.device)
+        if self.device.type == "cuda":
+            pe_model = pe_model.half()
+            print("⚡ Mixed precision enabled")
+        preprocess = transforms.get_image_transform(336)
+        print("🎯 PE model ready - using layer 24 (research optimal)")
+        return pe_model, preprocess
+
+    def init_grounded_sam(self, text_prompt):
+        """core_system.py:205-224 through the reference's own imports (re-created per call, thresholds 0.35 / 0.25)."""
+        from autodistill_grounded_sam import GroundedSAM     # third-party, not vendored
+        from autodistill.detection import CaptionOntology
+        prompts = [p.strip() for p in text_prompt.split(".") if p.strip()] if text_prompt else []
+        if not prompts:
+            prompts = ["object"]
+        self.grounded_sam = GroundedSAM(ontology=CaptionOntology({p: p for p in prompts}), box_threshold=0.35,
+                                        text_threshold=0.25)
+        print(f"🎯 GroundedSAM ready with prompts: {prompts}")
+
+    def _detect_with_grounded_sam(self, pil, text_prompt):
+        """core_system.py:248-308: temp JPEG round trip, predict, masks to numpy."""
+        import tempfile
+        self.init_grounded_sam(text_prompt)
+        temp_path = os.path.join(tempfile.gettempdir(), f"temp_image_{uuid.uuid4().hex[:8]}.jpg")
+        pil.convert("RGB").save(temp_path)
+        try:
+            det = self.grounded_sam.predict(temp_path)
+        finally:
+            if os.path.exists(temp_path):
+                os.remove(temp_path)
+        masks = getattr(det, "mask", None)
+        if masks is None:
+            masks = getattr(det, "masks", None)
+        if isinstance(masks, torch.Tensor):
+            masks = masks.detach().cpu().numpy()
+        if len(det.xyxy) == 0:
+            masks = np.zeros((0, pil.height, pil.width), dtype=np.uint8)
+        try:
+            from supervision.detection.core import Detections
+            return Detections(xyxy=det.xyxy, mask=masks, confidence=det.confidence, class_id=det.class_id)
+        except ImportError:
+            from types import SimpleNamespace
+
+            class _Det(SimpleNamespace):
+                def __len__(self):
+                    return len(self.xyxy)
+            return _Det(xyxy=det.xyxy, mask=masks, confidence=det.confidence, class_id=det.class_id)
+
+    def _new_client(self, db_path):
+        return B200VectorDB(path=db_path, device=self.device if self.device.type == "cuda" else None, devices=self.devices)
 
     # ---- database housekeeping (core_system.py:74-154) ------------------------------------------
     def list_databases(self):
@@ -111,7 +201,7 @@ class SimpleReverso:
         if not os.path.exists(db_path):
             return f"❌ Database not found: {database_name}"
         try:
-            client = B200VectorDB(path=db_path, device=self.device)
+            client = self._new_client(db_path)
             collection_name = f"{COLLECTION_PREFIX}{database_name}"
             names = [c.name for c in client.get_collections().collections]
             if collection_name not in names:
@@ -167,10 +257,14 @@ class SimpleReverso:
         self.region_embeddings = None
         self.query_embedding_for_search = None
         try:
-            if self._detector is None:
-                return 0 if self._fail("GroundedSAM detector not available in this environment") else 0
             pil = self._to_pil(image)
-            self.detected_regions = self._detector(pil, text_prompt)
+            if self._detector is None:
+                try:
+                    self.detected_regions = self._detect_with_grounded_sam(pil, text_prompt)
+                except ImportError as e:
+                    return 0 if self._fail(f"GroundedSAM detector not available in this environment ({e})") else 0
+            else:
+                self.detected_regions = self._detector(pil, text_prompt)
             n = len(self.detected_regions) if self.detected_regions is not None else 0
             print(f"✅ Found {n} regions")
             return n
@@ -182,7 +276,11 @@ class SimpleReverso:
     # ---- embedding half --------------------------------------------------------------------------
     def _encode(self, image):
         if self.pe_model is None or self.preprocess is None:
-            raise RvoError("PE encoder not available: pass encoder= and preprocess= (perception_models is not vendored)")
+            try:        # the no-argument constructor of ui.py:20: load the reference's own encoder on first use
+                self.pe_model, self.preprocess = self.load_pe_model()
+            except ImportError as e:
+                raise RvoError("PE encoder not available: perception_models is not installed "
+                               f"({e}); pass encoder= and preprocess=") from None
         pil = self._to_pil(image)
         x = self.preprocess(pil.convert("RGB")).unsqueeze(0).to(self.device)
         with torch.no_grad():
@@ -194,7 +292,7 @@ class SimpleReverso:
         Both run in the CUDA library: the token mean is K1 with an all-ones mask."""
         if features.dim() == 3:
             _, N, D = features.shape
-            feats = features[:1].to(torch.bfloat16).contiguous()  # encoder-side cast; K1 consumes bf16 features
+            feats = self._k1_features(features[:1])               # bf16 / fp16 as they are; fp32 rounded to bf16
             ones = torch.ones((1, 1, N), dtype=torch.uint8, device=feats.device)
             out, _, _, _ = ops.mask_pool(feats, ones)
             return out[0]
@@ -202,6 +300,13 @@ class SimpleReverso:
             _, f32 = ops.normalize_rows(features[:1].float().contiguous(), want_f32=True)
             return f32[0]
         raise ValueError(f"Unexpected feature shape: {tuple(features.shape)}")
+
+    @staticmethod
+    def _k1_features(tokens: torch.Tensor) -> torch.Tensor:
+        """K1 consumes 16-bit features: bf16, or the fp16 a `.half()` encoder emits (core_system.py:195-196), unchanged."""
+        if tokens.dtype in (torch.bfloat16, torch.float16):
+            return tokens.contiguous()
+        return tokens.to(torch.bfloat16).contiguous()
 
     def extract_embeddings(self, image):
         """core_system.py:320-429.  Returns (list[Tensor[D]] on CPU, list[dict])."""
@@ -275,7 +380,7 @@ class SimpleReverso:
         for j, m in enumerate(masks_hw):
             if m is not None:
                 pm[0, j] = mask_to_patch_grid(m, g)
-        feats = tokens.to(torch.bfloat16).contiguous().unsqueeze(0)
+        feats = self._k1_features(tokens).unsqueeze(0)
         out, counts, src, total = ops.mask_pool(feats, torch.from_numpy(pm).to(feats.device))
         out = out[:M].cpu()  # every mask is non-empty here, so total == M
         return [out[j].clone() for j in range(M)]
@@ -338,7 +443,7 @@ class SimpleReverso:
             log_status(f"📂 Database will be stored at: {db_path}")
 
             os.makedirs(db_path, exist_ok=True)
-            client = B200VectorDB(path=None, device=self.device)
+            client = self._new_client(db_path)          # persists implicitly on every upsert, like QdrantClient(path=...)
             processed = failed = 0
             for i, image_path in enumerate(image_files):
                 if self._stop_requested:
@@ -396,8 +501,6 @@ class SimpleReverso:
                 client.upsert(collection_name=collection_name, points=batch_points)
                 log_status(f"💾 Stored batch {j // UPSERT_BATCH + 1}/{(len(points) + UPSERT_BATCH - 1) // UPSERT_BATCH} "
                            f"({len(batch_points)} points)", 0.8 + (0.1 * (j / len(points))))
-            client.save(db_path)                    # qdrant's local mode persisted implicitly; this store is explicit
-            client.path = db_path
             self.vector_db = client
             self.current_database = collection_name
             log_status("\n📊 Final Summary:", 0.9)

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <math.h>
+#include <mutex>
 
 #include "common.cuh"
 #include "scan_tc.cuh"
@@ -11,6 +12,7 @@
 namespace rvo {
 
 extern bool g_force_cuda_core_pool;
+extern std::atomic<long long> g_exchange_timeout_ms;
 extern void* g_pool_trace;
 static std::atomic<long long> opt_select_trace{0};
 size_t selfjoin_workspace_bytes(int d, long long cand_cap);
@@ -44,6 +46,28 @@ static int scan_timer(bool start, cudaStream_t stream) {
     return RVO_OK;
 }
 
+// Every exported entry point makes the device that owns its pointers current for the duration of the call and restores the
+// caller's device on return (a single process may drive several GPUs, B200VectorDB(devices=[...]); torch tracks its own
+// current device per thread and must not find it changed).
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            prev = -1;
+            cudaGetLastError();
+        }
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// per-device properties, filled once per device (Gradio worker threads may race here: std::call_once)
+constexpr int kMaxDevices = 64;
+static std::once_flag g_prop_once[kMaxDevices];
+static int g_prop_sm[kMaxDevices], g_prop_major[kMaxDevices];
+
 int select_device_of(const void* dev_ptr, int* sm_count) {
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, dev_ptr);
@@ -56,20 +80,28 @@ int select_device_of(const void* dev_ptr, int* sm_count) {
         set_error("pointer %p is not device memory (type %d)", dev_ptr, (int)at.type);
         return RVO_E_INVALID;
     }
-    RVO_CUDA(cudaSetDevice(at.device));
-    static int cached_dev = -1, cached_sm = 0, cached_major = 0;
-    if (cached_dev != at.device) {
-        cudaDeviceProp pr;
-        RVO_CUDA(cudaGetDeviceProperties(&pr, at.device));
-        cached_dev = at.device;
-        cached_sm = pr.multiProcessorCount;
-        cached_major = pr.major;
-    }
-    if (cached_major != 10) {
-        set_error("device %d is sm_%d0, this library is built for sm_100a (B200) only", at.device, cached_major);
+    if (at.device < 0 || at.device >= kMaxDevices) {
+        set_error("device ordinal %d out of range", at.device);
         return RVO_E_NO_DEVICE;
     }
-    if (sm_count) *sm_count = cached_sm;
+    RVO_CUDA(cudaSetDevice(at.device));
+    const int dev = at.device;
+    std::call_once(g_prop_once[dev], [dev]() {
+        int sm = 0, major = 0;
+        if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+            cudaGetLastError();
+            sm = 0;
+            major = 0;
+        }
+        g_prop_sm[dev] = sm;
+        g_prop_major[dev] = major;
+    });
+    if (g_prop_major[dev] != 10) {
+        set_error("device %d is sm_%d0, this library is built for sm_100a (B200) only", dev, g_prop_major[dev]);
+        return RVO_E_NO_DEVICE;
+    }
+    if (sm_count) *sm_count = g_prop_sm[dev];
     return RVO_OK;
 }
 
@@ -299,6 +331,7 @@ float rvo_last_scan_ms(void) {
 }
 
 int rvo_device_sm_count(const void* dev_ptr) {
+    DeviceGuard device_guard;
     int sm = 0;
     int rc = select_device_of(dev_ptr, &sm);
     return rc ? rc : sm;
@@ -312,6 +345,7 @@ int rvo_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "final_ratio")) opt_final_ratio = value;
     else if (!strcmp(name, "time_scan")) opt_time_scan = value;
     else if (!strcmp(name, "hot")) opt_hot = value;
+    else if (!strcmp(name, "exchange_timeout_ms")) g_exchange_timeout_ms = value > 0 ? value : 1;
     else if (!strcmp(name, "pool_path")) g_force_cuda_core_pool = value == 1;
     else if (!strcmp(name, "pdl")) g_use_pdl = value;
     else if (!strcmp(name, "select_trace")) opt_select_trace = value;
@@ -331,6 +365,7 @@ size_t rvo_db_bytes(int64_t n_rows, int32_t d) {
 
 int rvo_normalize_rows(const float* src, int64_t n, int32_t d, int64_t src_ld, uint16_t* dst_bf16, int64_t dst_ld,
                        int64_t tiled_row0, float* dst_f32, void* stream) {
+    DeviceGuard device_guard;
     RVO_REQUIRE(src && (dst_bf16 || dst_f32), "normalize_rows: null pointer");
     RVO_REQUIRE(n >= 0 && d > 0 && src_ld >= d, "normalize_rows: bad shape n=%lld d=%d ld=%lld", (long long)n, d,
                 (long long)src_ld);
@@ -346,10 +381,12 @@ size_t rvo_mask_pool_workspace_bytes(int32_t B, int32_t M, int32_t P, int32_t D)
     return mask_pool_workspace_bytes(B, M, P, D);
 }
 
-int rvo_mask_pool(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
+int rvo_mask_pool(const uint16_t* feats, int32_t feat_dtype, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
                   int32_t max_regions, float* out, int32_t* out_counts, int32_t* out_src, int32_t* out_total,
                   void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceGuard device_guard;
     RVO_REQUIRE(feats && masks && out && out_counts && out_total && workspace, "mask_pool: null pointer");
+    RVO_REQUIRE(feat_dtype == RVO_DTYPE_BF16 || feat_dtype == RVO_DTYPE_F16, "mask_pool: feat_dtype %d (bf16 = 0, fp16 = 1)", feat_dtype);
     RVO_REQUIRE(B > 0 && M > 0 && P > 0 && D > 0, "mask_pool: bad shape B=%d M=%d P=%d D=%d", B, M, P, D);
     RVO_REQUIRE(((uintptr_t)feats & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)masks & 3) == 0,
                 "mask_pool: feats/out must be 16-byte aligned, masks 4-byte aligned");
@@ -357,13 +394,15 @@ int rvo_mask_pool(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_
     int rc = select_device_of(feats, &sm);
     if (rc) return rc;
     return launch_mask_pool(feats, masks, B, M, P, D, max_regions, out, out_counts, out_src, out_total, workspace,
-                            workspace_bytes, sm, (cudaStream_t)stream);
+                            workspace_bytes, sm, (cudaStream_t)stream, nullptr, 0, feat_dtype == RVO_DTYPE_F16);
 }
 
-int rvo_mask_pool_to_db(const uint16_t* feats, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
+int rvo_mask_pool_to_db(const uint16_t* feats, int32_t feat_dtype, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
                         int32_t max_regions, uint16_t* db, int64_t db_row0, float* out_f32, int32_t* out_counts,
                         int32_t* out_src, int32_t* out_total, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceGuard device_guard;
     RVO_REQUIRE(feats && masks && db && out_counts && out_total && workspace, "mask_pool_to_db: null pointer");
+    RVO_REQUIRE(feat_dtype == RVO_DTYPE_BF16 || feat_dtype == RVO_DTYPE_F16, "mask_pool_to_db: feat_dtype %d (bf16 = 0, fp16 = 1)", feat_dtype);
     RVO_REQUIRE(B > 0 && M > 0 && P > 0 && D > 0 && db_row0 >= 0, "mask_pool_to_db: bad shape B=%d M=%d P=%d D=%d row0=%lld", B,
                 M, P, D, (long long)db_row0);
     RVO_REQUIRE(((uintptr_t)feats & 15) == 0 && ((uintptr_t)db & 15) == 0 && ((uintptr_t)masks & 3) == 0 &&
@@ -377,7 +416,7 @@ int rvo_mask_pool_to_db(const uint16_t* feats, const uint8_t* masks, int32_t B, 
         return RVO_E_UNSUPPORTED;
     }
     rc = launch_mask_pool(feats, masks, B, M, P, D, max_regions, out_f32, out_counts, out_src, out_total, workspace,
-                          workspace_bytes, sm, (cudaStream_t)stream, db, db_row0);
+                          workspace_bytes, sm, (cudaStream_t)stream, db, db_row0, feat_dtype == RVO_DTYPE_F16);
     if (rc == RVO_E_UNSUPPORTED)
         set_error("mask_pool_to_db: shape B=%d M=%d P=%d D=%d is outside the fused kernel: use rvo_mask_pool + rvo_normalize_rows",
                   B, M, P, D);
@@ -394,6 +433,7 @@ size_t rvo_search_workspace_bytes(int64_t n_rows, int32_t d, int32_t nq, int32_t
 static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad_in, const float* queries, int32_t nq,
                        int32_t k, float score_threshold, int64_t id_offset, int64_t* out_ids, float* out_scores,
                        int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream_, const PushArgs* push) {
+    DeviceGuard device_guard;
     cudaStream_t stream = (cudaStream_t)stream_;
     RVO_REQUIRE(queries && out_ids && out_scores && out_counts && workspace, "search_topk: null pointer");
     RVO_REQUIRE(n_rows >= 0 && d > 0 && nq > 0, "search_topk: bad shape n_rows=%lld d=%d nq=%d", (long long)n_rows, d, nq);
@@ -642,6 +682,7 @@ int rvo_search_topk_push(const uint16_t* db, int64_t n_rows, int32_t d, int64_t 
 
 int rvo_merge_topk_exchange(const void* local_region, int32_t world, int32_t nq, int32_t k, int32_t nq_max, int32_t k_max,
                             uint64_t epoch, int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream) {
+    DeviceGuard device_guard;
     RVO_REQUIRE(local_region && out_ids && out_scores && out_counts, "merge_topk_exchange: null pointer");
     RVO_REQUIRE(world >= 2 && world <= kMaxPeers && nq > 0 && nq <= nq_max && k > 0 && k <= k_max && (long long)world * k <= 4096,
                 "merge_topk_exchange: bad shape");
@@ -673,6 +714,7 @@ int rvo_scan_tile_rows(int32_t nq, int32_t d) {
 int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad_in, const float* queries, int32_t nq,
                      int64_t tile_stride, float* out, int64_t out_ld, void* workspace, size_t workspace_bytes,
                      void* stream_) {
+    DeviceGuard device_guard;
     cudaStream_t stream = (cudaStream_t)stream_;
     RVO_REQUIRE(db && queries && out && workspace, "scores_dense: null pointer");
     RVO_REQUIRE(n_rows > 0 && d > 0 && nq > 0 && tile_stride >= 1, "scores_dense: bad shape");
@@ -700,17 +742,28 @@ int rvo_scores_dense(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pa
                           stream);
 }
 
-size_t rvo_selfjoin_workspace_bytes(int32_t d) {
-    if (d <= 0) return 0;
-    return selfjoin_workspace_bytes(d, opt_cand_cap.load());
+size_t rvo_selfjoin_workspace_bytes(int32_t d) { return rvo_selfjoin_workspace_bytes_ex(d, opt_cand_cap.load()); }
+
+size_t rvo_selfjoin_workspace_bytes_ex(int32_t d, int64_t cand_cap) {
+    if (d <= 0 || cand_cap <= 0) return 0;
+    return selfjoin_workspace_bytes(d, cand_cap);
 }
 
 int rvo_selfjoin_threshold(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad_in, int64_t row_lo, int64_t row_hi,
                            float threshold, int64_t id_offset, int64_t* out_pairs, float* out_scores, int64_t out_cap,
                            uint64_t* out_count, int32_t* out_overflowed, void* workspace, size_t workspace_bytes,
                            void* stream) {
+    return rvo_selfjoin_threshold_ex(db, n_rows, d, d_pad_in, row_lo, row_hi, threshold, id_offset, opt_cand_cap.load(), out_pairs,
+                                     out_scores, out_cap, out_count, out_overflowed, workspace, workspace_bytes, stream);
+}
+
+int rvo_selfjoin_threshold_ex(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad_in, int64_t row_lo, int64_t row_hi,
+                              float threshold, int64_t id_offset, int64_t cand_cap, int64_t* out_pairs, float* out_scores,
+                              int64_t out_cap, uint64_t* out_count, int32_t* out_overflowed, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    DeviceGuard device_guard;
     RVO_REQUIRE(db && out_pairs && out_scores && out_count && workspace, "selfjoin: null pointer");
-    RVO_REQUIRE(n_rows > 0 && d > 0 && row_lo >= 0 && row_lo <= row_hi && row_hi <= n_rows && out_cap >= 0,
+    RVO_REQUIRE(n_rows > 0 && d > 0 && row_lo >= 0 && row_lo <= row_hi && row_hi <= n_rows && out_cap >= 0 && cand_cap > 0,
                 "selfjoin: bad shape n_rows=%lld rows [%lld,%lld)", (long long)n_rows, (long long)row_lo, (long long)row_hi);
     RVO_REQUIRE(d_pad_in == (d + kBlockK - 1) / kBlockK * kBlockK, "selfjoin: d_pad must be d rounded up to 64");
     RVO_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)db & 15) == 0, "selfjoin: alignment");
@@ -718,13 +771,14 @@ int rvo_selfjoin_threshold(const uint16_t* db, int64_t n_rows, int32_t d, int64_
     int sm = 0;
     int rc = select_device_of(db, &sm);
     if (rc) return rc;
-    return launch_selfjoin(db, n_rows, d, row_lo, row_hi, threshold, id_offset, opt_cand_cap.load(), (long long*)out_pairs,
+    return launch_selfjoin(db, n_rows, d, row_lo, row_hi, threshold, id_offset, cand_cap, (long long*)out_pairs,
                            out_scores, out_cap, (unsigned long long*)out_count, out_overflowed, workspace, workspace_bytes, sm,
                            (cudaStream_t)stream);
 }
 
 int rvo_merge_topk(const int64_t* ids, const float* scores, const int32_t* counts, int32_t G, int32_t nq, int32_t k,
                    int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream) {
+    DeviceGuard device_guard;
     RVO_REQUIRE(ids && scores && counts && out_ids && out_scores && out_counts, "merge_topk: null pointer");
     RVO_REQUIRE(G >= 1 && nq >= 1 && k >= 1 && (long long)G * k <= 4096, "merge_topk: need G*k <= 4096 (G=%d k=%d)", G, k);
     int rc = select_device_of(ids, nullptr);
@@ -740,6 +794,7 @@ size_t rvo_packed_result_bytes(int32_t nq, int32_t k) {
 
 int rvo_merge_topk_packed(const void* gathered, int64_t rank_stride_bytes, int32_t G, int32_t nq, int32_t k,
                           int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream) {
+    DeviceGuard device_guard;
     RVO_REQUIRE(gathered && out_ids && out_scores && out_counts, "merge_topk_packed: null pointer");
     RVO_REQUIRE(G >= 1 && nq >= 1 && k >= 1 && (long long)G * k <= 4096, "merge_topk_packed: need G*k <= 4096 (G=%d k=%d)",
                 G, k);

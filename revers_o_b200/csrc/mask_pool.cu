@@ -13,6 +13,8 @@
 //                        warp-shuffle reduction; writes the un-normalised mean and accumulates ||e||^2
 //   mask_scale_kernel    e /= sqrt(||e||^2)   (rows just written are L2-resident)
 // Work is proportional to sum of mask areas (segmented), not to M*P.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "prep_scan_small.cuh"
 
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(1024) mask_offsets_kernel(const int* __restric
     if (threadIdx.x == 1023) *out_total = s_scan[1023];
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kPoolThreads) mask_pool_kernel(const uint16_t* __restrict__ feats, int M, int P, int D, int lim,
                                                                  int p_pad, const uint16_t* __restrict__ idx,
                                                                  const int* __restrict__ area, const int* __restrict__ out_row,
@@ -120,10 +123,17 @@ __global__ void __launch_bounds__(kPoolThreads) mask_pool_kernel(const uint16_t*
         for (int r = threadIdx.x >> 2; r < P; r += kPoolThreads / 4) {
             const uint4 v = __ldcs((const uint4*)(base + (size_t)r * D));
             float4 lo4, hi4;
-            lo4.x = __uint_as_float(v.x << 16); lo4.y = __uint_as_float(v.x & 0xFFFF0000u);
-            lo4.z = __uint_as_float(v.y << 16); lo4.w = __uint_as_float(v.y & 0xFFFF0000u);
-            hi4.x = __uint_as_float(v.z << 16); hi4.y = __uint_as_float(v.z & 0xFFFF0000u);
-            hi4.z = __uint_as_float(v.w << 16); hi4.w = __uint_as_float(v.w & 0xFFFF0000u);
+            if constexpr (F16) {
+                const float2 a = __half22float2(*(const __half2*)&v.x), b2 = __half22float2(*(const __half2*)&v.y);
+                const float2 c2 = __half22float2(*(const __half2*)&v.z), d2 = __half22float2(*(const __half2*)&v.w);
+                lo4 = make_float4(a.x, a.y, b2.x, b2.y);
+                hi4 = make_float4(c2.x, c2.y, d2.x, d2.y);
+            } else {
+                lo4.x = __uint_as_float(v.x << 16); lo4.y = __uint_as_float(v.x & 0xFFFF0000u);
+                lo4.z = __uint_as_float(v.y << 16); lo4.w = __uint_as_float(v.y & 0xFFFF0000u);
+                hi4.x = __uint_as_float(v.z << 16); hi4.y = __uint_as_float(v.z & 0xFFFF0000u);
+                hi4.z = __uint_as_float(v.w << 16); hi4.w = __uint_as_float(v.w & 0xFFFF0000u);
+            }
             float4* d4 = (float4*)(sf + (size_t)r * kSlab + seg * 8);
             d4[0] = lo4;
             d4[1] = hi4;
@@ -181,18 +191,22 @@ __global__ void __launch_bounds__(256) mask_scale_kernel(float* __restrict__ out
                                                          const int* __restrict__ src_of_row, const int* __restrict__ total) {
     const int row = blockIdx.x;
     if (row >= *total) return;
-    const float inv = 1.0f / sqrtf(sumsq[src_of_row[row]]);  // no epsilon (core_system.py:407)
+    // no epsilon (core_system.py:407) — but a region whose mean is the zero vector, or whose features hold NaN / Inf, becomes
+    // the zero vector instead of a NaN row (same rule as rvo_normalize_rows: one bad row must not poison every search)
+    const float ssq = sumsq[src_of_row[row]];
+    const float inv = (ssq != 0.f && isfinite(ssq)) ? 1.0f / sqrtf(ssq) : 0.f;
     float4* o = (float4*)(out + (size_t)row * D);
     for (int i = threadIdx.x; i < (D >> 2); i += blockDim.x) {
         float4 v = o[i];
-        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        if (inv == 0.f) v = make_float4(0.f, 0.f, 0.f, 0.f);   // 0 * NaN would stay NaN
+        else { v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv; }
         o[i] = v;
     }
 }
 
 int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int lim, float* out,
                         int32_t* out_counts, int32_t* out_src, int32_t* out_total, int* img_base, int* area,
-                        unsigned int* ticket, int sm_count, cudaStream_t stream, uint16_t* db, long long db_row0);
+                        unsigned int* ticket, int sm_count, cudaStream_t stream, uint16_t* db, long long db_row0, int feat_f16);
 
 size_t mask_pool_workspace_bytes(int B, int M, int P, int D) {
     (void)D;
@@ -207,7 +221,7 @@ size_t mask_pool_workspace_bytes(int B, int M, int P, int D) {
 
 int launch_mask_pool(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int max_regions, float* out,
                      int32_t* out_counts, int32_t* out_src, int32_t* out_total, void* workspace, size_t workspace_bytes,
-                     int sm_count, cudaStream_t stream, uint16_t* db, long long db_row0) {
+                     int sm_count, cudaStream_t stream, uint16_t* db, long long db_row0, int feat_f16) {
     if (D % kSlab != 0) {
         set_error("mask_pool: D=%d must be a multiple of %d", D, kSlab);
         return RVO_E_INVALID;
@@ -233,7 +247,7 @@ int launch_mask_pool(const uint16_t* feats, const uint8_t* masks, int B, int M, 
     if (!g_force_cuda_core_pool) {
         // tensor-core path (mask_pool_tc.cu) whenever the image's whole output fits TMEM
         const int rc = launch_mask_pool_tc(feats, masks, B, M, P, D, lim, out, out_counts, out_src, out_total, img_base,
-                                           area, ticket, sm_count, stream, db, db_row0);
+                                           area, ticket, sm_count, stream, db, db_row0, feat_f16);
         if (rc <= 0) return rc;
     }
     if (db) return RVO_E_UNSUPPORTED;   // the fused ingest exists on the tensor-core kernel only
@@ -247,9 +261,15 @@ int launch_mask_pool(const uint16_t* feats, const uint8_t* masks, int B, int M, 
     RVO_LAUNCHED();
     mask_offsets_kernel<<<1, 1024, 0, stream>>>(area, B, M, out_row, out_counts, src_of_row, out_total, sumsq);
     RVO_LAUNCHED();
-    RVO_CUDA(cudaFuncSetAttribute(mask_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mask_pool_kernel<<<dim3(D / kSlab, B), kPoolThreads, smem, stream>>>(feats, M, P, D, lim, p_pad, idx, area, out_row, out,
-                                                                         sumsq);
+    if (feat_f16) {
+        RVO_CUDA(cudaFuncSetAttribute(mask_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mask_pool_kernel<true><<<dim3(D / kSlab, B), kPoolThreads, smem, stream>>>(feats, M, P, D, lim, p_pad, idx, area, out_row,
+                                                                                   out, sumsq);
+    } else {
+        RVO_CUDA(cudaFuncSetAttribute(mask_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mask_pool_kernel<false><<<dim3(D / kSlab, B), kPoolThreads, smem, stream>>>(feats, M, P, D, lim, p_pad, idx, area, out_row,
+                                                                                    out, sumsq);
+    }
     RVO_LAUNCHED();
     mask_scale_kernel<<<bm, 256, 0, stream>>>(out, D, sumsq, src_of_row, out_total);
     RVO_LAUNCHED();

@@ -47,6 +47,8 @@ struct PoolTcParams {
     int* out_src;
     int B, M, P, D, lim, n_pad, num_pc, num_slab, num_stages;
     uint32_t off_b, b_buf_bytes, off_misc;
+    uint32_t one_mul;      // 0x80 * one_mul = the 16-bit pattern of 1.0 in the feature dtype: 127 (bf16 0x3F80), 120 (fp16 0x3C00)
+    uint32_t f16;          // features (and therefore the converted masks) are fp16 instead of bf16
     unsigned long long* trace;     // option "pool_trace": [B][8] globaltimer stamps of the per-image pipeline events (or null)
 };
 
@@ -92,11 +94,11 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 
 // four mask bytes (any non-zero value = set) -> four bf16 0/1 in two words.  Non-zero bytes are flagged 0x80
 // (SWAR), spread into 16-bit lanes and multiplied by 127: 0x80 * 127 = 0x3F80 = bf16(1.0).
-__device__ __forceinline__ void mask4_to_bf16(uint32_t x, uint32_t& w0, uint32_t& w1, int& cnt) {
+__device__ __forceinline__ void mask4_to_bf16(uint32_t x, uint32_t& w0, uint32_t& w1, int& cnt, uint32_t one_mul) {
     const uint32_t f = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
     cnt += __popc(f);
-    w0 = __byte_perm(f, 0u, 0x4140) * 127u;   // bytes {f0, 0, f1, 0}
-    w1 = __byte_perm(f, 0u, 0x4342) * 127u;   // bytes {f2, 0, f3, 0}
+    w0 = __byte_perm(f, 0u, 0x4140) * one_mul;   // bytes {f0, 0, f1, 0}; one_mul = 127: bf16 1.0, 120: fp16 1.0
+    w1 = __byte_perm(f, 0u, 0x4342) * one_mul;   // bytes {f2, 0, f3, 0}
 }
 
 // TO_DB: the fused-ingest variant (bf16 rows into the tiled DB, fp32 output optional); the plain variant keeps the store pass
@@ -176,7 +178,8 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
         // ===================== MMA issuer =====================
         if (elect_one()) {
             // A: MN-major (bit 15), B: K-major, bf16 x bf16 -> fp32, M = 128, N = n_pad
-            const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_pad) | (1u << 15);
+            // fp16 features: a_format = b_format = F16 (0) instead of BF16 (1); the masks are converted to the same type
+            const uint32_t idesc = (make_idesc_bf16(128, (uint32_t)n_pad) & (p.f16 ? ~((1u << 7) | (1u << 10)) : ~0u)) | (1u << 15);
             uint32_t stage = 0, phase = 0, it = 0;
             const uint32_t sB0 = smem_u32(s_b);
             for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
@@ -359,7 +362,10 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
                     int rr[16];                     // output row of the region, < 0: empty region (dropped)
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        sc[i] = invarea[m0 + i] * rsqrtf(s_ss[m0 + i]);
+                        // a region whose mean is the zero vector, or whose features hold NaN / Inf, is stored as the zero
+                        // vector (sc = 0), never as a NaN row: same rule as rvo_normalize_rows
+                        const float ssq = s_ss[m0 + i];
+                        sc[i] = (ssq != 0.f && isfinite(ssq)) ? invarea[m0 + i] * rsqrtf(ssq) : 0.f;
                         rr[i] = outrow[m0 + i];
                     }
                     for (int j0 = 0; j0 < ns; j0 += 4) {
@@ -375,7 +381,9 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
                                     float* __restrict__ o = gout + (size_t)(s0 + j0) * 128 + jj * 128;
 #pragma unroll
                                     for (int i = 0; i < 16; ++i)
-                                        if (rr[i] >= 0) __stcs(o + (size_t)rr[i] * (size_t)p.D, __uint_as_float(v[jj & 1][i]) * sc[i]);
+                                        if (rr[i] >= 0)
+                                            __stcs(o + (size_t)rr[i] * (size_t)p.D,
+                                                   sc[i] != 0.f ? __uint_as_float(v[jj & 1][i]) * sc[i] : 0.f);
                                 }
                                 if constexpr (TO_DB) {
                                     // tiled DB storage [row/128][col/64][row%128][col%64]: the warp's 32 channels of one
@@ -388,7 +396,8 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
                                         if (rr[i] >= 0) {
                                             const long long row = p.db_row0 + rr[i];
                                             t0[((size_t)(row >> 7) * nk) * (kTileRows * kTileCols) + (size_t)(row & 127) * kTileCols] =
-                                                __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(v[jj & 1][i]) * sc[i]));
+                                                __bfloat16_as_ushort(__float2bfloat16_rn(
+                                                    sc[i] != 0.f ? __uint_as_float(v[jj & 1][i]) * sc[i] : 0.f));
                                         }
                                 }
                             }
@@ -451,8 +460,8 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
                     if (m < n_pad) {
                         uint32_t w0, w1, w2, w3;
                         int unused = 0;
-                        mask4_to_bf16((uint32_t)cur[j], w0, w1, unused);
-                        mask4_to_bf16((uint32_t)(cur[j] >> 32), w2, w3, unused);
+                        mask4_to_bf16((uint32_t)cur[j], w0, w1, unused, p.one_mul);
+                        mask4_to_bf16((uint32_t)(cur[j] >> 32), w2, w3, unused, p.one_mul);
                         *(uint4*)(tile + (size_t)m * 128 + (size_t)((cin ^ (m & 7)) << 4)) = make_uint4(w0, w1, w2, w3);
                     }
                 }
@@ -515,7 +524,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 // CUDA-core kernel — same results), <0 on error.
 int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int lim, float* out,
                         int32_t* out_counts, int32_t* out_src, int32_t* out_total, int* img_base, int* area,
-                        unsigned int* ticket, int sm_count, cudaStream_t stream, uint16_t* db, long long db_row0) {
+                        unsigned int* ticket, int sm_count, cudaStream_t stream, uint16_t* db, long long db_row0, int feat_f16) {
     const int n_pad = (M + 15) / 16 * 16;
     const int num_pc = (P + 63) / 64, num_slab = D / 128;
     if (D % 128 != 0 || n_pad > 64 || num_slab * n_pad > 512) return 1;
@@ -545,7 +554,7 @@ int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int 
     cuuint64_t gstr[2] = {(cuuint64_t)D * 2ull, (cuuint64_t)P * D * 2ull};
     cuuint32_t box[3] = {64, 64, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(feats), gdim, gstr, box, estr,
+    CUresult r = enc(&tm, feat_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(feats), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -567,6 +576,8 @@ int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int 
     p.off_b = (uint32_t)off_b;
     p.b_buf_bytes = (uint32_t)b_buf;
     p.off_misc = (uint32_t)off_misc;
+    p.one_mul = feat_f16 ? 120u : 127u;
+    p.f16 = feat_f16 ? 1u : 0u;
     p.trace = (unsigned long long*)g_pool_trace;
     RVO_CUDA(cudaFuncSetAttribute(mask_pool_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RVO_CUDA(cudaFuncSetAttribute(mask_pool_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -18,6 +18,6 @@ int launch_scan_small(const uint16_t* db, long long n_rows, int d_pad, const flo
 size_t mask_pool_workspace_bytes(int B, int M, int P, int D);
 int launch_mask_pool(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int max_regions, float* out,
                      int32_t* out_counts, int32_t* out_src, int32_t* out_total, void* workspace, size_t workspace_bytes,
-                     int sm_count, cudaStream_t stream, uint16_t* db = nullptr, long long db_row0 = 0);
+                     int sm_count, cudaStream_t stream, uint16_t* db = nullptr, long long db_row0 = 0, int feat_f16 = 0);
 
 }  // namespace rvo

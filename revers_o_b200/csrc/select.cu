@@ -890,6 +890,7 @@ int launch_select_final(const SelectArgs& a, const FinalArgs& f, int nq, cudaStr
 
 // ---- K3: merge of per-shard lists -------------------------------------------------------------
 constexpr int kMaxMergeLists = 64;
+std::atomic<long long> g_exchange_timeout_ms{60000};   // option "exchange_timeout_ms"
 __device__ __forceinline__ bool before(float sa, long long ia, float sb, long long ib) {
     return sa > sb || (sa == sb && ia < ib);
 }
@@ -902,21 +903,38 @@ __global__ void __launch_bounds__(256) merge_kernel(const int64_t* ids, const fl
                                                     long long ids_gs, long long scores_gs, long long counts_gs,
                                                     int G, int k, int64_t* out_ids,
                                                     float* out_scores, int32_t* out_counts,
-                                                    const unsigned long long* wait_flags, unsigned long long wait_epoch) {
+                                                    const unsigned long long* wait_flags, unsigned long long wait_epoch,
+                                                    unsigned long long wait_timeout_ns) {
     extern __shared__ unsigned char sm[];
+    __shared__ int s_timeout;
     if (wait_flags) {
         // peer-memory exchange: rank g's push of this search has landed in the local region once its flag shows the epoch
+        // A late peer (host-side GC, lazy module load, ingest) only delays this rank, as a collective would.  After
+        // `wait_timeout_ns` (option "exchange_timeout_ms", default 60 s) the kernel gives up WITHOUT trapping: every query
+        // of the batch reports count -2 and the host raises / falls back to the all-gather path; the context stays usable.
+        if (threadIdx.x == 0) s_timeout = 0;
+        __syncthreads();
         if (threadIdx.x < G) {
-            unsigned int spins = 0;
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
             while (ld_acquire_sys_u64(wait_flags + threadIdx.x) < wait_epoch) {
-                __nanosleep(100);
-                if (++spins == (1u << 25)) {
-                    printf("rvo: merge wait for rank %d timed out (epoch %llu)\n", (int)threadIdx.x, wait_epoch);
-                    __trap();
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                if (t1 - t0 > wait_timeout_ns) {
+                    s_timeout = 1;
+                    break;
                 }
             }
         }
         __syncthreads();
+        if (s_timeout) {
+            for (int i = threadIdx.x; i < k; i += blockDim.x) {
+                out_ids[(size_t)blockIdx.x * k + i] = -1;
+                out_scores[(size_t)blockIdx.x * k + i] = -__int_as_float(0x7f800000);
+            }
+            if (threadIdx.x == 0) out_counts[blockIdx.x] = -2;
+            return;
+        }
     }
     long long* sid = (long long*)sm;                 // [G][k]
     float* ssc = (float*)(sid + (size_t)G * k);      // [G][k]
@@ -998,7 +1016,8 @@ int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts,
     if (smem > 48 * 1024)
         RVO_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_kernel<<<nq, 256, smem, stream>>>(ids, scores, counts, ids_gs, scores_gs, counts_gs, G, k, out_ids, out_scores,
-                                            out_counts, wait_flags, wait_epoch);
+                                            out_counts, wait_flags, wait_epoch,
+                                            (unsigned long long)g_exchange_timeout_ms.load() * 1000000ull);
     RVO_LAUNCHED();
     return RVO_OK;
 }

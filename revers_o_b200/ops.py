@@ -36,6 +36,10 @@ def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     return buf[off:off + nbytes]
 
 
+def _feat_dtype(t: torch.Tensor) -> int:
+    return _lib.RVO_DTYPE_F16 if t.dtype == torch.float16 else _lib.RVO_DTYPE_BF16
+
+
 def require_cuda(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise RvoError(f"{name} must be a CUDA tensor: the B200 library has no CPU path")
@@ -103,11 +107,11 @@ def normalize_rows(src: torch.Tensor, dst_bf16: torch.Tensor | None = None, want
 
 
 def mask_pool(feats: torch.Tensor, masks: torch.Tensor, max_regions: int = 0):
-    """K1.  feats bf16 [B,P,D], masks uint8 [B,M,P] -> (out f32 [B*M, D] (first `total` rows valid),
+    """K1.  feats bf16 or fp16 [B,P,D], masks uint8 [B,M,P] -> (out f32 [B*M, D] (first `total` rows valid),
     counts int32 [B], src int32 [B*M], total int32 [1]) — all device tensors, no host sync."""
     require_cuda(feats, "feats")
     require_cuda(masks, "masks")
-    assert feats.dtype == torch.bfloat16 and feats.is_contiguous() and feats.dim() == 3
+    assert feats.dtype in (torch.bfloat16, torch.float16) and feats.is_contiguous() and feats.dim() == 3
     assert masks.dtype == torch.uint8 and masks.is_contiguous() and masks.dim() == 3
     B, P, D = feats.shape
     M = masks.shape[1]
@@ -120,7 +124,7 @@ def mask_pool(feats: torch.Tensor, masks: torch.Tensor, max_regions: int = 0):
     lib = _lib.load()
     nbytes = lib.rvo_mask_pool_workspace_bytes(B, M, P, D)
     ws = workspace(dev, nbytes)
-    check(lib.rvo_mask_pool(_ptr(feats), _ptr(masks), B, M, P, D, int(max_regions), _ptr(out), _ptr(counts), _ptr(src),
+    check(lib.rvo_mask_pool(_ptr(feats), _feat_dtype(feats), _ptr(masks), B, M, P, D, int(max_regions), _ptr(out), _ptr(counts), _ptr(src),
                             _ptr(total), _ptr(ws), nbytes, _stream(dev)), "rvo_mask_pool")
     return out, counts, src, total
 
@@ -134,7 +138,7 @@ def mask_pool_to_db(feats: torch.Tensor, masks: torch.Tensor, db: torch.Tensor, 
     require_cuda(feats, "feats")
     require_cuda(masks, "masks")
     require_cuda(db, "db")
-    assert feats.dtype == torch.bfloat16 and feats.is_contiguous() and feats.dim() == 3
+    assert feats.dtype in (torch.bfloat16, torch.float16) and feats.is_contiguous() and feats.dim() == 3
     assert masks.dtype == torch.uint8 and masks.is_contiguous() and masks.dim() == 3
     assert db.dtype == torch.bfloat16 and db.is_contiguous() and db.dim() == 4
     B, P, D = feats.shape
@@ -151,7 +155,7 @@ def mask_pool_to_db(feats: torch.Tensor, masks: torch.Tensor, db: torch.Tensor, 
     lib = _lib.load()
     nbytes = lib.rvo_mask_pool_workspace_bytes(B, M, P, D)
     ws = workspace(dev, nbytes)
-    rc = lib.rvo_mask_pool_to_db(_ptr(feats), _ptr(masks), B, M, P, D, int(max_regions), _ptr(db), int(row0), _ptr(f32),
+    rc = lib.rvo_mask_pool_to_db(_ptr(feats), _feat_dtype(feats), _ptr(masks), B, M, P, D, int(max_regions), _ptr(db), int(row0), _ptr(f32),
                                  _ptr(counts), _ptr(src), _ptr(total), _ptr(ws), nbytes, _stream(dev))
     if rc == _lib.RVO_E_UNSUPPORTED:
         out, counts, src, total = mask_pool(feats, masks, max_regions)
@@ -269,6 +273,39 @@ def selfjoin_threshold(db: torch.Tensor, n_rows: int, d: int, threshold: float, 
                                      int(id_offset), _ptr(pairs), _ptr(scores), out_cap, _ptr(count), _ptr(over), _ptr(ws),
                                      nbytes, _stream(dev)), "rvo_selfjoin_threshold")
     return pairs, scores, count, over
+
+
+def selfjoin_exact(db: torch.Tensor, n_rows: int, d: int, threshold: float, row_lo: int = 0, row_hi: int | None = None,
+                   max_pairs: int = 1 << 22, id_offset: int = 0, cand_cap: int = 32768):
+    """`selfjoin_threshold` that cannot lose pairs: when a query row's candidate sub-list overflows (more near-duplicates
+    than `cand_cap` holds — a static video scene) the join is re-run with 8x the capacity (exact once
+    cand_cap >= n_rows + 4096), and when more than `max_pairs` pairs exist the output buffers grow to the reported count.
+    Returns host arrays (pairs int64 [m, 2], scores f32 [m]).  Synchronises."""
+    require_cuda(db, "db")
+    row_hi = n_rows if row_hi is None else row_hi
+    dev = db.device
+    lib = _lib.load()
+    cap, out_cap = int(cand_cap), int(max_pairs)
+    while True:
+        pairs = torch.empty((out_cap, 2), dtype=torch.int64, device=dev)
+        scores = torch.empty((out_cap,), dtype=torch.float32, device=dev)
+        count = torch.zeros((1,), dtype=torch.int64, device=dev)
+        over = torch.zeros((1,), dtype=torch.int32, device=dev)
+        nbytes = lib.rvo_selfjoin_workspace_bytes_ex(d, cap)
+        ws = workspace(dev, nbytes)
+        check(lib.rvo_selfjoin_threshold_ex(_ptr(db), n_rows, d, d_pad_of(d), int(row_lo), int(row_hi), float(threshold),
+                                            int(id_offset), cap, _ptr(pairs), _ptr(scores), out_cap, _ptr(count), _ptr(over),
+                                            _ptr(ws), nbytes, _stream(dev)), "rvo_selfjoin_threshold_ex")
+        m, ov = int(count.item()), int(over.item())
+        if ov > 0 and cap < n_rows + 4096:
+            cap = min(cap * 8, n_rows + 4096 + TILE_ROWS * 16)
+            continue
+        if m > out_cap:
+            out_cap = m
+            continue
+        if ov > 0:
+            raise RvoError(f"self-join candidate lists overflowed at capacity {cap} for {n_rows} rows")
+        return pairs[:m].cpu().numpy(), scores[:m].cpu().numpy()
 
 
 def merge_topk(ids: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor, k: int):

@@ -161,18 +161,19 @@ class ShardedIndex:
                           "os": torch.empty((nq, k), dtype=torch.float32, device=dev),
                           "oc": torch.empty((nq,), dtype=torch.int32, device=dev)}
         b = self._bufs
-        x["epoch"] += 1
+        epoch = x["epoch"] + 1      # committed only after BOTH launches succeeded: a failed call must not desynchronise the ranks
         nbytes = lib.rvo_search_workspace_bytes(self.n_local, self.d, nq, k)
         ws = ops.workspace(dev, nbytes)
         thr = -math.inf if score_threshold is None else float(score_threshold)
         stream = torch.cuda.current_stream(dev).cuda_stream
         check(lib.rvo_search_topk_push(self.db.data_ptr(), self.n_local, self.d, ops.d_pad_of(self.d), queries.data_ptr(), nq, k,
                                        thr, self.id_offset, x["table"], self.world, self.rank, x["nq_max"], x["k_max"],
-                                       x["epoch"], ws.data_ptr(), nbytes, stream), "rvo_search_topk_push")
+                                       epoch, ws.data_ptr(), nbytes, stream), "rvo_search_topk_push")
         oi, os_, oc = out if out is not None else (b["oi"], b["os"], b["oc"])
-        check(lib.rvo_merge_topk_exchange(x["region"], self.world, nq, k, x["nq_max"], x["k_max"], x["epoch"],
+        check(lib.rvo_merge_topk_exchange(x["region"], self.world, nq, k, x["nq_max"], x["k_max"], epoch,
                                           oi.data_ptr(), os_.data_ptr(), oc.data_ptr(), stream),
               "rvo_merge_topk_exchange")
+        x["epoch"] = epoch
         return oi, os_, oc
 
     @classmethod

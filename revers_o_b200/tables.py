@@ -191,12 +191,13 @@ class IdTable:
         """Roll back to the first n rows (a failed write must not leave ids without vectors)."""
         if n >= self.n:
             return
-        if self.kind == self.KIND_OBJ or self._tail:
-            self._tail = {k: r for k, r in self._tail.items() if r < n}
-        if self._sorted_n > n:
+        self._tail = {k: r for k, r in self._tail.items() if r < n}
+        if self._sorted_n > n:                  # the sorted index mentions dropped rows: rebuild lazily
             self._sorted, self._sorted_n = None, 0
-            self._tail_complete_from = max(self._tail_complete_from, n)
-        self._tail_complete_from = min(self._tail_complete_from, n) if self._sorted_n == 0 and not self._tail else self._tail_complete_from
+            if self.kind != self.KIND_OBJ:
+                self._tail = {}
+                self._tail_complete_from = n
+        self._tail_complete_from = min(self._tail_complete_from, n)
         self.n = n
 
     # ---- row -> id --------------------------------------------------------------------------------------------------

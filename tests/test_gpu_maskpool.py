@@ -152,3 +152,29 @@ def test_ingest_regions_then_search(dev):
     b, m = divmod(int(src[j]), M)
     expect_id = f"img{b}-r{m}" if j >= n1 else None
     assert hit.payload == {"image": b, "region": m} and (expect_id is None or hit.id == expect_id)
+
+
+@pytest.mark.parametrize("path", [0, 1])
+def test_fp16_features_are_consumed_natively(dev, path):
+    """SURVEY §8 H5 "bf16 or fp16": the reference's encoder is `.half()` on CUDA (core_system.py:195-196).  fp16 features go
+    into the kernels unchanged (no lossy cast to bf16): parity against the oracle fed the same fp16 values, 1e-3 relative."""
+    from revers_o_b200 import _lib, ops
+    g = torch.Generator().manual_seed(3)
+    B, M, P, D = 5, 20, 576, 1024
+    feats = torch.randn((B, P, D), generator=g).to(dev).to(torch.float16)
+    masks = (torch.rand((B, M, P), generator=g) < 0.2).to(torch.uint8).to(dev)
+    masks[2, 7] = 0
+    _lib.set_option("pool_path", path)
+    try:
+        out, counts, src, total = ops.mask_pool(feats, masks)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option("pool_path", 0)
+    emb, rc, _ = O.mask_pool(feats.float().cpu().numpy(), masks.cpu().numpy())
+    t = int(total.item())
+    assert t == emb.shape[0] and np.array_equal(counts.cpu().numpy(), rc)
+    got = out[:t].cpu().numpy()
+    assert np.max(np.abs(got - emb)) <= 1e-3 * np.max(np.abs(emb))
+    # and they are NOT the bf16-rounded features' embeddings (the cast the round-1 drop-in applied)
+    emb_bf16, _, _ = O.mask_pool(feats.to(torch.bfloat16).float().cpu().numpy(), masks.cpu().numpy())
+    assert np.max(np.abs(got - emb)) < 0.2 * np.max(np.abs(emb_bf16 - emb))

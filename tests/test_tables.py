@@ -1,0 +1,68 @@
+"""CPU: host-side id / payload tables (revers_o_b200/tables.py) — array-backed ids with qdrant's upsert-overwrite semantics,
+append-only payload log with lazy reads."""
+import uuid
+
+import numpy as np
+
+from revers_o_b200.tables import IdTable, PayloadStore
+
+
+def test_id_table_uuid_strings_append_lookup_overwrite():
+    t = IdTable()
+    ids = [str(uuid.uuid4()) for _ in range(1000)]              # core_system.py:574: one uuid4 string per point
+    assert (t.append(ids[:500]) == np.arange(500)).all()
+    assert (t.append(ids[400:600]) == np.arange(400, 600)).all()   # known ids keep their row (overwrite), new ones append
+    assert t[123] == ids[123] and len(t) == 600 and t.kind == "str" and t.array().dtype == np.dtype("S36")
+    assert (t.append(ids[600:], assume_new=True) == np.arange(600, 1000)).all()
+    assert (t.lookup([ids[5], ids[999], "nope"]) == np.array([5, 999, -1])).all()
+    assert list(t)[:3] == ids[:3] and t[-1] == ids[-1]
+    t2 = IdTable.from_array(t.array().copy())                    # what a load from <collection>.ids produces: index built lazily
+    assert (t2.lookup([ids[7], ids[998]]) == [7, 998]).all()
+    assert list(t2.append([ids[3], "new-one", "new-one"])) == [3, 1000, 1000]   # duplicate inside a batch: one row
+    t.truncate(700)                                              # roll-back of a failed write
+    assert len(t) == 700 and t.lookup([ids[800]])[0] == -1 and t.lookup([ids[650]])[0] == 650
+    assert list(t.append([ids[800]])) == [700]
+
+
+def test_id_table_longer_strings_ints_and_mixed():
+    t = IdTable()
+    t.append(["a" * 36])
+    t.append(["b" * 50])                                         # wider than the column: widened, old ids intact
+    assert t[0] == "a" * 36 and t[1] == "b" * 50 and t.lookup(["b" * 50])[0] == 1 and t.lookup(["b" * 49])[0] == -1
+    ti = IdTable()
+    assert list(ti.append([5, 9, 5])) == [0, 1, 0] and ti[1] == 9 and ti.kind == "int" and ti.disk_dtype() == "<i8"
+    assert ti.lookup(["5"])[0] == -1                             # a string is not the integer id
+    ti.append(["x"])                                             # mixed types: python-object fallback keeps everything
+    assert ti.kind == "obj" and ti[2] == "x" and ti.lookup([9])[0] == 1 and ti.disk_dtype() is None
+
+
+def test_id_table_large_sorted_index():
+    t = IdTable()
+    n = 200_000
+    t.append(list(range(0, 2 * n, 2)), assume_new=True)
+    got = t.lookup([0, 2 * n - 2, 7, 123456])
+    assert list(got) == [0, n - 1, -1, 61728]
+    assert list(t.append([123456, 1])) == [61728, n]
+
+
+def test_payload_store_log_is_append_only_and_lazy(tmp_path):
+    log, idx = str(tmp_path / "l"), str(tmp_path / "i")
+    p = PayloadStore()
+    p.append_or_set(np.arange(3), [{"a": 1}, None, {"b": [1, 2]}])
+    lb, ib = p.flush(log, idx, 0, 0)
+    size1 = (tmp_path / "l").stat().st_size
+    p.append_or_set(np.array([1, 3]), [{"c": 3}, {"d": 4}])      # overwrite row 1, append row 3
+    lb2, ib2 = p.flush(log, idx, lb, ib)
+    assert (tmp_path / "l").read_bytes()[:size1] == (tmp_path / "l").read_bytes()[:size1] and lb2 > lb and ib2 == ib + 32
+    q = PayloadStore.open(log, idx, 4, ib2)                      # only the (row, offset) index is read
+    assert not q._ram and [q[i] for i in range(4)] == [{"a": 1}, {"c": 3}, {"b": [1, 2]}, {"d": 4}]
+    # a torn write after the last meta.json (bytes beyond what it vouches for) is cut off by the next flush
+    with open(log, "ab") as f:
+        f.write(b'{"row": 9, "payl')
+    q.append_or_set(np.array([4]), [{"e": 5}])
+    lb3, ib3 = q.flush(log, idx, lb2, ib2)
+    r = PayloadStore.open(log, idx, 5, ib3)
+    assert r[4] == {"e": 5} and r[1] == {"c": 3} and len(r) == 5
+    # the state meta.json vouched for BEFORE the second flush is still readable (crash between flush and meta replace)
+    old = PayloadStore.open(log, idx, 3, ib)
+    assert [old[i] for i in range(3)] == [{"a": 1}, None, {"b": [1, 2]}]
