@@ -135,15 +135,16 @@ class IdTable:
         enc = self._encode(ids) if kind != self.KIND_STR else np.array([s.encode("utf-8") for s in ids])
         if self._sorted_n:
             keys = self._arr[: self._sorted_n]
-            if kind == self.KIND_STR and enc.dtype.itemsize > keys.dtype.itemsize:
-                pass          # longer than every stored id: cannot match the sorted part
+            if kind == self.KIND_STR:
+                fits = np.char.str_len(enc) <= keys.dtype.itemsize     # a longer string cannot equal a stored id
+                e = enc.astype(keys.dtype)                             # (the cast truncates: masked out by `fits`)
             else:
-                e = enc.astype(keys.dtype) if kind == self.KIND_STR else enc
-                pos = np.searchsorted(keys, e, sorter=self._sorted)
-                pos = np.minimum(pos, self._sorted_n - 1)
-                rows = self._sorted[pos]
-                hit = keys[rows] == e
-                out[hit] = rows[hit]
+                fits, e = True, enc
+            pos = np.searchsorted(keys, e, sorter=self._sorted)
+            pos = np.minimum(pos, self._sorted_n - 1)
+            rows = self._sorted[pos]
+            hit = (keys[rows] == e) & fits
+            out[hit] = rows[hit]
         if self._tail:
             for j, i in enumerate(ids):
                 r = self._tail.get(i)

@@ -14,7 +14,7 @@ third-party modules in `sys.modules` and then loads the reference modules withou
 
 Where the reference comes from:
   * `/root/reference/*.py`                    in the authoring container (source, loaded in place, never copied);
-  * `oracle/_ref/*.pyc`                       on the GPU box: bytecode compiled from those sources by `oracle/build_ref.py`
+  * `oracle/_ref/*.rvoc`                       on the GPU box: bytecode compiled from those sources by `oracle/build_ref.py`
                                               (`__graft_entry__.build()`), git-ignored, travels with the gpurun snapshot.
 TEST INFRASTRUCTURE ONLY: nothing under revers_o_b200/ imports this.
 """
@@ -42,7 +42,7 @@ def reference_location():
     """('source', dir) | ('pyc', dir) | (None, None)."""
     if os.path.exists(os.path.join(REFERENCE_DIR, "core_system.py")):
         return "source", REFERENCE_DIR
-    if os.path.exists(os.path.join(REF_PYC_DIR, "core_system.pyc")):
+    if os.path.exists(os.path.join(REF_PYC_DIR, "core_system.rvoc")):
         return "pyc", REF_PYC_DIR
     return None, None
 
@@ -89,7 +89,7 @@ class FakePE:
     def encode_image(self, x):
         import torch
         p = torch.nn.functional.adaptive_avg_pool2d(x.float(), 24).flatten(2).transpose(1, 2)   # [1,576,3]
-        t = torch.tanh(p @ self.w + torch.linspace(-1, 1, 1024, device=x.device))
+        t = torch.tanh(((p - 0.5) * 4.0) @ self.w + 0.1 * torch.linspace(-1, 1, 1024, device=x.device))
         out = torch.cat([t.mean(1, keepdim=True), t], 1)
         return out.half() if self.is_half else out
 
@@ -306,7 +306,7 @@ def _load(name, kind, where):
     if kind == "source":
         spec = importlib.util.spec_from_file_location(name, os.path.join(where, name + ".py"))
     else:
-        path = os.path.join(where, name + ".pyc")
+        path = os.path.join(where, name + ".rvoc")
         spec = importlib.util.spec_from_loader(name, importlib.machinery.SourcelessFileLoader(name, path))
     mod = importlib.util.module_from_spec(spec)
     sys.modules[name] = mod

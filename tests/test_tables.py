@@ -19,6 +19,9 @@ def test_id_table_uuid_strings_append_lookup_overwrite():
     t2 = IdTable.from_array(t.array().copy())                    # what a load from <collection>.ids produces: index built lazily
     assert (t2.lookup([ids[7], ids[998]]) == [7, 998]).all()
     assert list(t2.append([ids[3], "new-one", "new-one"])) == [3, 1000, 1000]   # duplicate inside a batch: one row
+    t3 = IdTable.from_array(t.array().copy())
+    longer = ids[4] + "-suffix-beyond-36-characters"             # shares a 36-character prefix with a stored id: NOT that id
+    assert list(t3.append([ids[4], longer])) == [4, 1000] and t3[1000] == longer and t3[4] == ids[4]
     t.truncate(700)                                              # roll-back of a failed write
     assert len(t) == 700 and t.lookup([ids[800]])[0] == -1 and t.lookup([ids[650]])[0] == 650
     assert list(t.append([ids[800]])) == [700]
