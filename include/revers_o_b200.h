@@ -138,9 +138,10 @@ int rvo_mask_pool_to_db(const uint16_t* feats, int32_t feat_dtype, const uint8_t
  *   out_counts [dev] int32   [nq]     hits per query (0..k), or -1 if the query OVERFLOWED the
  *                                     candidate buffers of the fused path (pathological tie mass);
  *                                     the caller must re-run such queries in batches of
- *                                     <= RVO_SMALL_Q, which never overflow.
+ *                                     <= RVO_SMALL_Q (fp32 scan) and, should one of those report -1 as well,
+ *                                     with rvo_search_topk_ex(path = RVO_PATH_DENSE), which cannot overflow.
  *   workspace  [dev] rvo_search_workspace_bytes(...) bytes, 1024-B aligned.  Contents are scratch.
- * nq <= RVO_SMALL_Q: exact fp32 CUDA-core scan (HBM-bound).  nq > RVO_SMALL_Q: bf16 tcgen05 scan
+ * nq <= RVO_SMALL_Q (and d <= 2048): exact fp32 CUDA-core scan (HBM-bound).  nq > RVO_SMALL_Q: bf16 tcgen05 scan
  * with the threshold-select fused in its epilogue, candidates re-scored in fp32.
  * ---------------------------------------------------------------------------------------------- */
 size_t rvo_search_workspace_bytes(int64_t n_rows, int32_t d, int32_t nq, int32_t k);
@@ -148,6 +149,25 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
                     const float* queries, int32_t nq, int32_t k, float score_threshold, int64_t id_offset,
                     int64_t* out_ids, float* out_scores, int32_t* out_counts,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same search with the kernel path chosen by the caller instead of by nq:
+ *   RVO_PATH_AUTO    nq <= RVO_SMALL_Q -> fp32 scan, else tcgen05 (what rvo_search_topk does)
+ *   RVO_PATH_SMALL   fp32 CUDA-core scan (nq <= RVO_SMALL_Q).  Shards up to 131072 rows: [scan + every score] -> [exact top-k],
+ *                    two launches, the reference's own operating point (Q = 1, core_system.py:657).  Larger shards: a row
+ *                    sample's k-th best key filters the full scan, so scores never reach HBM; a survivor list that overflows
+ *                    (adversarial row order) flags the query with count -1
+ *   RVO_PATH_TENSOR  tcgen05 scan + fused select + fp32 re-score, any nq
+ *   RVO_PATH_DENSE   fp32 scan keeping every score of the shard (nq <= RVO_SMALL_Q): cannot overflow, whatever the data — the
+ *                    last resort of the overflow protocol (workspace: 4 bytes per row per query) */
+#define RVO_PATH_AUTO   0
+#define RVO_PATH_SMALL  1
+#define RVO_PATH_TENSOR 2
+#define RVO_PATH_DENSE  3
+size_t rvo_search_workspace_bytes_ex(int64_t n_rows, int32_t d, int32_t nq, int32_t k, int32_t path);
+int rvo_search_topk_ex(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad,
+                       const float* queries, int32_t nq, int32_t k, float score_threshold, int64_t id_offset, int32_t path,
+                       int64_t* out_ids, float* out_scores, int32_t* out_counts,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Rows the tcgen05 path pads a batch of nq queries to (query blocks of <=256, multiples of 16). */
 int rvo_padded_queries(int32_t nq, int32_t d);

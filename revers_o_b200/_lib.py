@@ -15,6 +15,7 @@ RVO_E_UNSUPPORTED = -5
 RVO_MAX_K = 512
 RVO_SMALL_Q = 4
 RVO_DTYPE_BF16, RVO_DTYPE_F16 = 0, 1
+RVO_PATH_AUTO, RVO_PATH_SMALL, RVO_PATH_TENSOR, RVO_PATH_DENSE = 0, 1, 2, 3
 
 # name -> (restype, argtypes); mirrors include/revers_o_b200.h one to one
 PROTOTYPES = {
@@ -45,6 +46,10 @@ PROTOTYPES = {
     "rvo_search_topk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                   C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p]),
+    "rvo_search_workspace_bytes_ex": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "rvo_search_topk_ex": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_float, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                     C.c_void_p]),
     "rvo_padded_queries": (C.c_int, [C.c_int32, C.c_int32]),
     "rvo_scan_tile_rows": (C.c_int, [C.c_int32, C.c_int32]),
     "rvo_scores_dense": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,

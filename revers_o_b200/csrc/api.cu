@@ -126,66 +126,16 @@ static int next_pow2_host(int x) {
     return p;
 }
 
-// ---- chunked top-K reduction: repeat chunk_topk until one chunk per query remains ---------------
-struct TopkSrc {
-    const float* dense;
-    long long dense_ld;
-    const unsigned long long* keys;
-    long long keys_ld;
-    const int* cnt;
-    int cap;
-    long long n;
-};
-
-static size_t reduce_buf_elems(long long n, int K) { return (size_t)((n + kChunk - 1) / kChunk) * (size_t)K; }
-
-static int reduce_topk(TopkSrc src, int nq, int K_mid, int K_final, unsigned long long* bufA, unsigned long long* bufB,
-                       float* tau_out, const float* tau_prev, int tau_k, float tau_margin, float tau_floor,
-                       const unsigned long long** result, long long* result_ld, cudaStream_t stream) {
-    unsigned long long* bufs[2] = {bufA, bufB};
-    int tog = 0;
-    for (;;) {
-        const long long n = src.n;
-        const int chunks = (int)((n + kChunk - 1) / kChunk);
-        const bool last = chunks <= 1;
-        ChunkTopkArgs a;
-        a.dense = src.dense;
-        a.dense_ld = src.dense_ld;
-        a.keys = src.keys;
-        a.keys_ld = src.keys_ld;
-        a.cnt = src.cnt;
-        a.cap = src.cap;
-        a.n_fixed = n;
-        a.K = last ? K_final : K_mid;
-        a.out = bufs[tog];
-        a.out_ld = (long long)(chunks > 0 ? chunks : 1) * a.K;
-        a.tau_out = last ? tau_out : nullptr;
-        a.tau_prev = tau_prev;
-        a.tau_k = tau_k;
-        a.tau_margin = tau_margin;
-        a.tau_floor = tau_floor;
-        int rc = launch_chunk_topk(a, chunks > 0 ? chunks : 1, nq, stream);
-        if (rc) return rc;
-        if (last) {
-            *result = a.out;
-            *result_ld = a.out_ld;
-            return RVO_OK;
-        }
-        src.dense = nullptr;
-        src.keys = a.out;
-        src.keys_ld = a.out_ld;
-        src.cnt = nullptr;
-        src.n = a.out_ld;
-        tog ^= 1;
-    }
-}
-
-
 // ---- search plan (shared by the workspace query and the driver) --------------------------------
 constexpr long long kSeedRows = 16384;  // rows of the DENSE threshold-seeding sample
 
+constexpr long long kSmallDenseRows = 131072;   // Q <= 4: shards up to this many rows keep EVERY score (<= 512 KB per query, L2)
+constexpr int kSmallSegCap = 4096;              // Q <= 4, larger shards: capacity of one of the 16 survivor sub-lists per query
+
 struct SearchPlan {
     bool small;
+    long long pair_stride, n_cols;   // small path: row pairs visited by the DENSE pass (1 = every row) and its columns
+    unsigned long long* tau_key;     // small path, sampled: k-th best ordering key of the sample per query
     int d_pad, K2, cap, n_levels;
     long long level_stride[8];       // super-tile stride of each FILTER level (last one is 1)
     long long seed_stride, seed_cols;
@@ -201,30 +151,53 @@ struct SearchPlan {
     unsigned long long* cand;
     float* dense;
     long long dense_ld;
-    unsigned long long *bufA, *bufB;
     size_t cnt_bytes;             // candidate counters (multiple of 16 bytes), cleared by the normalise launch
     size_t bytes;
 };
 
-static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws_bytes, SearchPlan* sp) {
+static int make_plan(long long n_rows, int d, int nq, int k, int path, void* ws, size_t ws_bytes, SearchPlan* sp) {
     memset(sp, 0, sizeof(*sp));
     sp->d_pad = (d + kBlockK - 1) / kBlockK * kBlockK;
-    const long long force = opt_force_path.load();
-    sp->small = (force == 1) || (force != 2 && nq <= RVO_SMALL_Q);
+    const long long force = path != RVO_PATH_AUTO ? (long long)path : opt_force_path.load();
+    sp->small = (force == RVO_PATH_SMALL || force == RVO_PATH_DENSE) ||
+                (force != RVO_PATH_TENSOR && nq <= RVO_SMALL_Q && scan_small_supports(sp->d_pad));
     if (sp->small && nq > RVO_SMALL_Q) {
-        set_error("force_path=1 needs nq <= %d", RVO_SMALL_Q);
+        set_error("the fp32 scan (path %lld) needs nq <= %d", force, RVO_SMALL_Q);
         return RVO_E_INVALID;
+    }
+    if (sp->small && !scan_small_supports(sp->d_pad)) {
+        set_error("the fp32 scan (path %lld) does not cover d = %d", force, d);
+        return RVO_E_UNSUPPORTED;
     }
     Arena ar(ws, ws_bytes);
     if (sp->small) {
-        sp->K2 = next_pow2_host(k);
-        const long long ld = (n_rows + 63) / 64 * 64;
+        // DENSE pass over every row (small shard, or path DENSE: the unconditional exact route) or over a strided sample whose
+        // k-th best key then filters the full scan: expected survivors = k * n / sample <= ~8k per query
+        sp->K2 = next_pow2_host((2 * k > k + 64) ? 2 * k : k + 64);
+        if (sp->K2 > 1024) sp->K2 = 1024;
+        const long long npairs = (n_rows + 1) / 2;
+        sp->pair_stride = 1;
+        if (n_rows > kSmallDenseRows && force != RVO_PATH_DENSE) {
+            long long sample = n_rows / 96;
+            if (sample < 16384) sample = 16384;       // <= 16k columns: the selection kernel keeps them in registers
+            const long long by_k = (long long)k * (n_rows / 8192 + 1);
+            if (sample < by_k) sample = by_k;
+            const long long sample_pairs = (sample + 1) / 2;
+            sp->pair_stride = (npairs + sample_pairs - 1) / sample_pairs;     // rounded up: at most `sample` columns
+            if (sp->pair_stride < 1) sp->pair_stride = 1;
+        }
+        sp->n_cols = 2 * ((npairs + sp->pair_stride - 1) / sp->pair_stride);
+        sp->dense_ld = (sp->n_cols + 63) / 64 * 64;
+        if (sp->dense_ld < 64) sp->dense_ld = 64;
         sp->qn = ar.take<float>((size_t)RVO_SMALL_Q * sp->d_pad, 1024);
-        sp->dense = ar.take<float>((size_t)RVO_SMALL_Q * (size_t)(ld > 0 ? ld : 64));
-        sp->dense_ld = ld > 0 ? ld : 64;
-        const size_t e1 = reduce_buf_elems(n_rows > 0 ? n_rows : 1, k > sp->K2 ? k : sp->K2);
-        sp->bufA = ar.take<unsigned long long>((size_t)nq * e1);
-        sp->bufB = ar.take<unsigned long long>((size_t)nq * reduce_buf_elems((long long)e1, sp->K2));
+        sp->dense = ar.take<float>((size_t)nq * (size_t)sp->dense_ld);
+        if (sp->pair_stride > 1) {
+            sp->cap = kSmallSegCap;
+            sp->tau_key = ar.take<unsigned long long>(RVO_SMALL_Q);
+            sp->cnt_bytes = align_up((size_t)RVO_SMALL_Q * kCandSplit * sizeof(int), 16);
+            sp->cnt = (int*)ar.take<char>(sp->cnt_bytes, 256);
+            sp->cand = ar.take<unsigned long long>((size_t)nq * kCandSplit * (size_t)sp->cap);
+        }
     } else {
         int rc = plan_scan_tc(nq, sp->d_pad, (int)opt_m_sub.load(), &sp->tc);
         if (rc) return rc;
@@ -289,8 +262,6 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
         sp->dense_ld = (sp->seed_cols + 63) / 64 * 64;
         sp->dense = ar.take<float>((size_t)nq_pad * (size_t)sp->dense_ld);
         if (sp->n_levels > 0) sp->cand = ar.take<unsigned long long>((size_t)nq_pad * kCandSegs * (size_t)sp->cap);
-        sp->bufA = ar.take<unsigned long long>((size_t)nq * sp->K2);
-        sp->bufB = nullptr;
     }
     sp->bytes = ar.off + 1024;
     if (ws && !ar.ok()) {
@@ -300,12 +271,10 @@ static int make_plan(long long n_rows, int d, int nq, int k, void* ws, size_t ws
     return RVO_OK;
 }
 
-static int prep_queries(const SearchPlan& sp, const float* queries, int nq, int d, void* ws, cudaStream_t stream) {
+static int prep_queries(const SearchPlan& sp, const float* queries, int nq, int d, cudaStream_t stream) {
     // one launch: normalise, zero the padding rows of the query operand, clear the candidate counters (no memset node)
-    (void)ws;
-    return launch_normalize_rows(queries, nq, d, d, sp.small ? nullptr : sp.qb, sp.d_pad, -1, sp.qn, sp.d_pad, stream,
-                                 sp.small ? nullptr : sp.margin, sp.small ? RVO_SMALL_Q : sp.tc.nq_pad,
-                                 sp.small ? nullptr : (void*)sp.cnt, sp.small ? 0 : sp.cnt_bytes);
+    return launch_normalize_rows(queries, nq, d, d, sp.qb, sp.d_pad, -1, sp.qn, sp.d_pad, stream, sp.margin, sp.tc.nq_pad,
+                                 (void*)sp.cnt, sp.cnt_bytes);
 }
 
 }  // namespace rvo
@@ -424,16 +393,22 @@ int rvo_mask_pool_to_db(const uint16_t* feats, int32_t feat_dtype, const uint8_t
 }
 
 size_t rvo_search_workspace_bytes(int64_t n_rows, int32_t d, int32_t nq, int32_t k) {
-    if (n_rows < 0 || d <= 0 || nq <= 0 || k <= 0 || k > RVO_MAX_K) return 0;
+    return rvo_search_workspace_bytes_ex(n_rows, d, nq, k, RVO_PATH_AUTO);
+}
+
+size_t rvo_search_workspace_bytes_ex(int64_t n_rows, int32_t d, int32_t nq, int32_t k, int32_t path) {
+    if (n_rows < 0 || d <= 0 || nq <= 0 || k <= 0 || k > RVO_MAX_K || path < RVO_PATH_AUTO || path > RVO_PATH_DENSE) return 0;
     SearchPlan sp;
-    if (make_plan(n_rows, d, nq, k, nullptr, 0, &sp)) return 0;
+    if (make_plan(n_rows, d, nq, k, path, nullptr, 0, &sp)) return 0;
     return sp.bytes;
 }
 
 static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad_in, const float* queries, int32_t nq,
                        int32_t k, float score_threshold, int64_t id_offset, int64_t* out_ids, float* out_scores,
-                       int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream_, const PushArgs* push) {
+                       int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream_, const PushArgs* push,
+                       int path = RVO_PATH_AUTO) {
     DeviceGuard device_guard;
+    RVO_REQUIRE(path >= RVO_PATH_AUTO && path <= RVO_PATH_DENSE, "search_topk: path %d (0 auto, 1 fp32 scan, 2 tcgen05, 3 dense fp32)", path);
     cudaStream_t stream = (cudaStream_t)stream_;
     RVO_REQUIRE(queries && out_ids && out_scores && out_counts && workspace, "search_topk: null pointer");
     RVO_REQUIRE(n_rows >= 0 && d > 0 && nq > 0, "search_topk: bad shape n_rows=%lld d=%d nq=%d", (long long)n_rows, d, nq);
@@ -449,9 +424,8 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
     int rc = select_device_of(workspace, &sm);
     if (rc) return rc;
 
-    if (push && (n_rows == 0 || nq <= RVO_SMALL_Q)) {
-        set_error("search_topk_push: the fused exchange needs a non-empty shard and nq > %d (use the all-gather path)",
-                  RVO_SMALL_Q);
+    if (push && n_rows == 0) {
+        set_error("search_topk_push: the fused exchange needs a non-empty shard (use the all-gather path)");
         return RVO_E_UNSUPPORTED;
     }
     if (n_rows == 0) {
@@ -462,10 +436,12 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
     }
 
     SearchPlan sp;
-    rc = make_plan(n_rows, d, nq, k, workspace, workspace_bytes, &sp);
+    rc = make_plan(n_rows, d, nq, k, path, workspace, workspace_bytes, &sp);
     if (rc) return rc;
-    rc = prep_queries(sp, queries, nq, d, workspace, stream);
-    if (rc) return rc;
+    if (push && sp.small) {
+        set_error("search_topk_push: the fused exchange serves the tcgen05 path only");
+        return RVO_E_UNSUPPORTED;
+    }
 
     FinalArgs fa;
     memset(&fa, 0, sizeof(fa));
@@ -483,22 +459,72 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
     if (push) fa.push = *push;
 
     if (sp.small) {
-        // exact fp32 scan -> dense scores -> chunked exact top-k (never overflows)
-        const unsigned long long* top = nullptr;
-        long long top_ld = 0;
-        if ((rc = scan_timer(true, stream))) return rc;
-        rc = launch_scan_small(db, n_rows, sp.d_pad, sp.qn, sp.d_pad, nq, sp.dense, sp.dense_ld, sm, stream);
+        // The reference's own operating point (Q = 1, core_system.py:657): exact fp32 scores on CUDA cores.
+        //   small shard (or path DENSE): [scan: normalise + every score] -> [exact top-k of the dense row]          2 launches
+        //   large shard: [scan of a row sample] -> [k-th best key of the sample] -> [full scan, survivors only] -> [exact top-k]
+        // Scores are final (no re-score); the dense scores of a large shard never reach HBM.
+        SmallScanArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.db = (const uint4*)db;
+        sa.n_rows = n_rows;
+        sa.nk = sp.d_pad / kTileCols;
+        sa.nchunks = sp.d_pad / 8;
+        sa.nq = nq;
+        sa.d = d;
+        sa.q = queries;
+        sa.q_ld = d;
+        sa.qn_out = sp.qn;
+        sa.qn_ld = sp.d_pad;
+        sa.out = sp.dense;
+        sa.out_ld = sp.dense_ld;
+        sa.pair_stride = sp.pair_stride;
+        const bool sampled = sp.pair_stride > 1;
+        if (sampled) {
+            sa.zero_base = (uint4*)sp.cnt;
+            sa.zero_u4 = (long long)(sp.cnt_bytes / 16);
+        }
+        if (!sampled && (rc = scan_timer(true, stream))) return rc;
+        rc = launch_scan_small(sa, true, true, sm, stream);
         if (rc) return rc;
-        if ((rc = scan_timer(false, stream))) return rc;
-        TopkSrc src = {sp.dense, sp.dense_ld, nullptr, 0, nullptr, 0, n_rows};
-        rc = reduce_topk(src, nq, k, sp.K2, sp.bufA, sp.bufB, nullptr, nullptr, 0, 0.f, 0.f, &top, &top_ld, stream);
-        if (rc) return rc;
-        fa.top = top;
-        fa.top_ld = top_ld;
+        if (!sampled && (rc = scan_timer(false, stream))) return rc;
+        DenseTopkArgs da;
+        memset(&da, 0, sizeof(da));
+        da.dense = sp.dense;
+        da.dense_ld = sp.dense_ld;
+        da.n_cols = sp.n_cols;
+        da.n_rows = n_rows;
+        da.pair_stride = sp.pair_stride;
+        da.k = k;
         fa.rescore = 0;
         fa.margin = nullptr;
-        return launch_final(fa, nq, stream);
+        if (!sampled) return launch_dense_topk(da, &fa, nq, stream);
+        da.tau_key_out = sp.tau_key;
+        rc = launch_dense_topk(da, nullptr, nq, stream);
+        if (rc) return rc;
+        sa.q = sp.qn;                    // normalised by the first pass
+        sa.q_ld = sp.d_pad;
+        sa.tau_key = sp.tau_key;
+        sa.cand = sp.cand;
+        sa.cnt = sp.cnt;
+        sa.nseg = kCandSplit;
+        sa.cap = sp.cap;
+        if ((rc = scan_timer(true, stream))) return rc;
+        rc = launch_scan_small(sa, false, false, sm, stream);
+        if (rc) return rc;
+        if ((rc = scan_timer(false, stream))) return rc;
+        SelectArgs sl;
+        memset(&sl, 0, sizeof(sl));
+        sl.nq = nq;
+        sl.keys = sp.cand;
+        sl.cnt = sp.cnt;
+        sl.nseg = kCandSplit;
+        sl.cap = sp.cap;
+        sl.K = sp.K2;
+        sl.score_floor = score_threshold;
+        return launch_select_final(sl, fa, nq, stream);     // a sub-list that overflowed flags the query (-1): path DENSE serves it
     }
+    rc = prep_queries(sp, queries, nq, d, stream);
+    if (rc) return rc;
 
     const int nq_pad = sp.tc.nq_pad;
     fa.rescore = 1;
@@ -588,6 +614,13 @@ int rvo_search_topk(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad
                     int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream) {
     return search_impl(db, n_rows, d, d_pad, queries, nq, k, score_threshold, id_offset, out_ids, out_scores, out_counts,
                        workspace, workspace_bytes, stream, nullptr);
+}
+
+int rvo_search_topk_ex(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad, const float* queries, int32_t nq,
+                       int32_t k, float score_threshold, int64_t id_offset, int32_t path, int64_t* out_ids, float* out_scores,
+                       int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    return search_impl(db, n_rows, d, d_pad, queries, nq, k, score_threshold, id_offset, out_ids, out_scores, out_counts,
+                       workspace, workspace_bytes, stream, nullptr, path);
 }
 
 // ---- peer-memory exchange ------------------------------------------------------------------------------

@@ -101,20 +101,62 @@ int launch_normalize_rows(const float* src, long long n, int d, long long src_ld
 // ---- small-Q scan --------------------------------------------------------------------------------
 // One warp per pair of DB rows; lane l owns the 16-byte chunks l, l+32, ... of a row, and keeps the
 // matching slices of all NQ queries in registers (no shared-memory traffic in the loop).
+//   NORM    the kernel normalises the raw queries itself (every CTA redundantly: NQ <= 4 rows of L2-resident floats; block 0
+//           also publishes them for the kernels that follow) — no separate normalise launch on the reference's Q = 1 path
+//   DENSE   scores of every `pair_stride`-th row pair go to out[q][2*j + {0,1}] (pair_stride = 1: every row)
+//   FILTER  rows whose ordering key (score, row) reaches tau_key[q] — the k-th best key of a row sample, a lower bound of the
+//           k-th best key of the shard — are appended to cand[q][seg][cap]; scores never reach HBM
+// The arithmetic of a row's score is identical in both modes (same lanes, same order), so a sampled row passes its own filter.
 // uint4 index of the 16-byte chunk `idx` (0 .. d_pad/8) of row `r` in the tiled DB storage
 __device__ __forceinline__ size_t tiled_u4(long long r, int idx, int nk) {
     return (((size_t)(r >> 7) * (size_t)nk + (size_t)(idx >> 3)) * kTileRows + (size_t)(r & 127)) * 8 + (size_t)(idx & 7);
 }
 
-template <int NQ, int CPL>
-__global__ void __launch_bounds__(256) scan_small_kernel(const uint4* __restrict__ db, long long n_rows,
-                                                         int nk, int nchunks, const float* __restrict__ qn,
-                                                         long long qn_ld, float* __restrict__ out, long long out_ld) {
-    const int lane = threadIdx.x & 31;
+template <int NQ, int CPL, bool DENSE, bool NORM>
+__global__ void __launch_bounds__(256) scan_small_kernel(const SmallScanArgs a) {
+    __shared__ float s_inv[RVO_SMALL_Q];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-    asm volatile("griddepcontrol.wait;" ::: "memory");               // the normalised queries come from the previous kernel
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (programmatic dependent launch, see ptx.cuh)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (NORM) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.zero_u4; i += (long long)gridDim.x * blockDim.x)
+            a.zero_base[i] = make_uint4(0, 0, 0, 0);
+        // x / ||x|| (core_system.py:407 / qdrant COSINE search), same rules as normalize_rows_kernel: zero and non-finite
+        // queries become the zero vector; the sum of squares is scaled by the largest magnitude against overflow
+        if (warp < NQ) {
+            float inv = 0.f;
+            if (warp < a.nq) {
+                const float* s = a.q + (size_t)warp * (size_t)a.q_ld;
+                float amax = 0.f;
+                for (int i = lane; i < a.d; i += 32) amax = fmaxf(amax, fabsf(s[i]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+                const bool rescale = amax > 1e18f || (amax < 1e-18f && amax > 0.f);
+                const float pre = rescale ? 1.0f / amax : 1.0f;
+                float ss = 0.f;
+                for (int i = lane; i < a.d; i += 32) {
+                    const float v = s[i] * pre;
+                    ss = fmaf(v, v, ss);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+                const float nrm = sqrtf(ss);
+                inv = (nrm != 0.f && isfinite(nrm)) ? pre / nrm : 0.f;
+            }
+            if (lane == 0) s_inv[warp] = inv;
+        }
+        __syncthreads();
+        if (blockIdx.x == 0 && a.qn_out) {
+            for (int i = threadIdx.x; i < RVO_SMALL_Q * (int)a.qn_ld; i += blockDim.x) {
+                const int q = i / (int)a.qn_ld, c = i - q * (int)a.qn_ld;
+                const float inv = q < NQ ? s_inv[q] : 0.f;
+                a.qn_out[i] = (q < a.nq && c < a.d && inv != 0.f) ? a.q[(size_t)q * (size_t)a.q_ld + c] * inv : 0.f;
+            }
+        }
+    }
 
     float qr[NQ][CPL][8];
 #pragma unroll
@@ -123,20 +165,41 @@ __global__ void __launch_bounds__(256) scan_small_kernel(const uint4* __restrict
         for (int c = 0; c < CPL; ++c) {
             const int idx = lane + 32 * c;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) qr[q][c][i] = idx < nchunks ? qn[(size_t)q * qn_ld + idx * 8 + i] : 0.f;
+            for (int i = 0; i < 8; ++i) {
+                float v = 0.f;
+                if (idx < a.nchunks) {
+                    if (NORM) {
+                        const int col = idx * 8 + i;
+                        const float inv = s_inv[q];
+                        v = (q < a.nq && col < a.d && inv != 0.f) ? a.q[(size_t)q * (size_t)a.q_ld + col] * inv : 0.f;
+                    } else {
+                        v = a.q[(size_t)q * (size_t)a.q_ld + idx * 8 + i];
+                    }
+                }
+                qr[q][c][i] = v;
+            }
         }
 
-    for (long long r0 = gw * 2; r0 < n_rows; r0 += nw * 2) {
-        const bool two = r0 + 1 < n_rows;
-        uint4 a[2][CPL];
+    unsigned long long tk[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) tk[q] = (!DENSE && q < a.nq) ? a.tau_key[q] : ~0ull;
+    const long long npairs = (a.n_rows + 1) >> 1;
+    const long long stride = DENSE ? a.pair_stride : 1;
+    const long long nsample = (npairs + stride - 1) / stride;
+    const int seg = DENSE ? 0 : (int)(gw % a.nseg);
+
+    for (long long j = gw; j < nsample; j += nw) {
+        const long long r0 = j * stride * 2;
+        const bool two = r0 + 1 < a.n_rows;
+        uint4 v[2][CPL];
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             const int idx = lane + 32 * c;
-            a[0][c] = make_uint4(0, 0, 0, 0);
-            a[1][c] = make_uint4(0, 0, 0, 0);
-            if (idx < nchunks) {
-                a[0][c] = __ldcs(db + tiled_u4(r0, idx, nk));
-                if (two) a[1][c] = __ldcs(db + tiled_u4(r0 + 1, idx, nk));
+            v[0][c] = make_uint4(0, 0, 0, 0);
+            v[1][c] = make_uint4(0, 0, 0, 0);
+            if (idx < a.nchunks) {
+                v[0][c] = __ldcs(a.db + tiled_u4(r0, idx, a.nk));
+                if (two) v[1][c] = __ldcs(a.db + tiled_u4(r0 + 1, idx, a.nk));
             }
         }
         float acc[2][NQ];
@@ -148,7 +211,7 @@ __global__ void __launch_bounds__(256) scan_small_kernel(const uint4* __restrict
         for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
-                const uint32_t w[4] = {a[r][c].x, a[r][c].y, a[r][c].z, a[r][c].w};
+                const uint32_t w[4] = {v[r][c].x, v[r][c].y, v[r][c].z, v[r][c].w};
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                     const float lo = __uint_as_float(w[h] << 16);
@@ -164,109 +227,82 @@ __global__ void __launch_bounds__(256) scan_small_kernel(const uint4* __restrict
         for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                float v = acc[r][q];
+                float x = acc[r][q];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                acc[r][q] = v;
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+                acc[r][q] = x;
             }
         if (lane == 0) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                out[(size_t)q * out_ld + r0] = acc[0][q];
-                if (two) out[(size_t)q * out_ld + r0 + 1] = acc[1][q];
-            }
-        }
-    }
-}
-
-// Any row length: queries live in shared memory (slower; rows longer than 2048 elements only).
-__global__ void __launch_bounds__(256) scan_small_generic_kernel(const uint4* __restrict__ db, long long n_rows,
-                                                                 int nk, int nchunks, int nq,
-                                                                 const float* __restrict__ qn, long long qn_ld,
-                                                                 float* __restrict__ out, long long out_ld) {
-    extern __shared__ float sq[];  // [nq][nchunks*8]
-    const int dq = nchunks * 8;
-    for (int i = threadIdx.x; i < nq * dq; i += blockDim.x) sq[i] = qn[(size_t)(i / dq) * qn_ld + (i % dq)];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long r = gw; r < n_rows; r += nw) {
-        float acc[RVO_SMALL_Q];
+                if (q >= a.nq) break;
+                if (DENSE) {
+                    a.out[(size_t)q * a.out_ld + 2 * j] = acc[0][q];
+                    if (two) a.out[(size_t)q * a.out_ld + 2 * j + 1] = acc[1][q];
+                } else {
 #pragma unroll
-        for (int q = 0; q < RVO_SMALL_Q; ++q) acc[q] = 0.f;
-        for (int c = lane; c < nchunks; c += 32) {
-            const uint4 v = __ldcs(db + tiled_u4(r, c, nk));
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < RVO_SMALL_Q; ++q)
-                if (q < nq) {
-                    const float* qq = sq + q * dq + c * 8;
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        acc[q] = fmaf(__uint_as_float(w[h] << 16), qq[2 * h], acc[q]);
-                        acc[q] = fmaf(__uint_as_float(w[h] & 0xFFFF0000u), qq[2 * h + 1], acc[q]);
+                    for (int r = 0; r < 2; ++r) {
+                        if (r == 1 && !two) break;
+                        const unsigned long long key = make_key(acc[r][q], (uint32_t)(r0 + r));
+                        if (key >= tk[q]) {
+                            const int pos = atomicAdd(a.cnt + q * a.nseg + seg, 1);
+                            if (pos < a.cap) a.cand[((size_t)q * a.nseg + seg) * (size_t)a.cap + pos] = key;
+                        }
                     }
                 }
-        }
-#pragma unroll
-        for (int q = 0; q < RVO_SMALL_Q; ++q) {
-            float v = acc[q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-            if (lane == 0 && q < nq) out[(size_t)q * out_ld + r] = v;
+            }
         }
     }
 }
 
 template <int NQ, int CPL>
-static int launch_small_t(const uint16_t* db, long long n_rows, int d_pad, const float* qn,
-                          long long qn_ld, float* out, long long out_ld, int sm_count, cudaStream_t stream) {
-    int per_sm = 0;
-    RVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_small_kernel<NQ, CPL>, 256, 0));
-    if (per_sm < 1) per_sm = 1;
-    long long want = (n_rows + 15) / 16;  // 8 warps x 2 rows per block per iteration
-    long long grid = (long long)sm_count * per_sm;
-    if (grid > want) grid = want;
-    RVO_CUDA(launch_pdl(scan_small_kernel<NQ, CPL>, dim3((unsigned)grid), dim3(256), 0, stream, (const uint4*)db, n_rows,
-                        d_pad / kTileCols, d_pad / 8, qn, qn_ld, out, out_ld));
+static int launch_small_t(const SmallScanArgs& a, bool dense, bool norm, int sm_count, cudaStream_t stream) {
+    const long long npairs = (a.n_rows + 1) / 2;
+    const long long nsample = dense ? (npairs + a.pair_stride - 1) / a.pair_stride : npairs;
+    long long want = (nsample + 7) / 8;  // 8 warps, one row pair each, per block per iteration
+    if (want < 1) want = 1;
+#define RVO_SMALL_LAUNCH(D_, N_)                                                                                     \
+    do {                                                                                                             \
+        int per_sm = 0;                                                                                              \
+        RVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_small_kernel<NQ, CPL, D_, N_>, 256, 0)); \
+        if (per_sm < 1) per_sm = 1;                                                                                  \
+        long long grid = (long long)sm_count * per_sm;                                                               \
+        if (grid > want) grid = want;                                                                                \
+        RVO_CUDA(launch_pdl(scan_small_kernel<NQ, CPL, D_, N_>, dim3((unsigned)grid), dim3(256), 0, stream, a));     \
+    } while (0)
+    if (dense && norm) RVO_SMALL_LAUNCH(true, true);
+    else if (dense) RVO_SMALL_LAUNCH(true, false);
+    else RVO_SMALL_LAUNCH(false, false);
+#undef RVO_SMALL_LAUNCH
     RVO_LAUNCHED();
     return RVO_OK;
 }
 
-// nq in 1..RVO_SMALL_Q; qn rows beyond nq (up to the instantiated NQ) must exist and be zero.
-int launch_scan_small(const uint16_t* db, long long n_rows, int d_pad, const float* qn, long long qn_ld,
-                      int nq, float* out, long long out_ld, int sm_count, cudaStream_t stream) {
-    if (n_rows <= 0) return RVO_OK;
-    const int cpl = (d_pad / 8 + 31) / 32;
-#define RVO_SMALL_CASE(NQ_, CPL_)                                                                          \
-    return launch_small_t<NQ_, CPL_>(db, n_rows, d_pad, qn, qn_ld, out, out_ld, sm_count, stream)
+// Rows longer than 2048 elements are not instantiated: the tensor path serves them (make_plan).
+int launch_scan_small(const SmallScanArgs& a, bool dense, bool norm, int sm_count, cudaStream_t stream) {
+    if (a.n_rows <= 0) return RVO_OK;
+    const int cpl = (a.nchunks + 31) / 32;
+#define RVO_SMALL_CASE(NQ_, CPL_) return launch_small_t<NQ_, CPL_>(a, dense, norm, sm_count, stream)
     if (cpl <= 4) {
-        if (nq == 1) RVO_SMALL_CASE(1, 4);
-        if (nq == 2) RVO_SMALL_CASE(2, 4);
+        if (a.nq == 1) RVO_SMALL_CASE(1, 4);
+        if (a.nq == 2) RVO_SMALL_CASE(2, 4);
         RVO_SMALL_CASE(4, 4);
     }
     if (cpl == 5) {
-        if (nq == 1) RVO_SMALL_CASE(1, 5);
-        if (nq == 2) RVO_SMALL_CASE(2, 5);
+        if (a.nq == 1) RVO_SMALL_CASE(1, 5);
+        if (a.nq == 2) RVO_SMALL_CASE(2, 5);
         RVO_SMALL_CASE(4, 5);
     }
-#undef RVO_SMALL_CASE
-    // long rows: generic kernel
-    const size_t smem = (size_t)nq * d_pad * 4;
-    if (smem > 200 * 1024) {
-        set_error("scan_small: row length %d too large", d_pad);
-        return RVO_E_INVALID;
+    if (cpl <= 8) {   // long rows (d_pad <= 2048): correct, register-heavy (rare configuration)
+        if (a.nq == 1) RVO_SMALL_CASE(1, 8);
+        if (a.nq == 2) RVO_SMALL_CASE(2, 8);
+        RVO_SMALL_CASE(4, 8);
     }
-    if (smem > 48 * 1024)
-        RVO_CUDA(cudaFuncSetAttribute(scan_small_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long grid = (long long)sm_count * 4;
-    long long want = (n_rows + 7) / 8;
-    if (grid > want) grid = want;
-    scan_small_generic_kernel<<<(unsigned)grid, 256, smem, stream>>>((const uint4*)db, n_rows, d_pad / kTileCols, d_pad / 8,
-                                                                    nq, qn, qn_ld, out, out_ld);
-    RVO_LAUNCHED();
-    return RVO_OK;
+#undef RVO_SMALL_CASE
+    set_error("scan_small: row length %d not covered by the fp32 scan (d_pad <= 2048)", a.nchunks * 8);
+    return RVO_E_UNSUPPORTED;
 }
+
+bool scan_small_supports(int d_pad) { return d_pad <= 2048; }
 
 }  // namespace rvo

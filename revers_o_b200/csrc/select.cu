@@ -70,51 +70,6 @@ __device__ __forceinline__ int next_pow2(int x) {
     return p;
 }
 
-// grid (num_chunks, nq): chunk c of query q -> its K best keys, sorted descending, zero padded.
-__global__ void __launch_bounds__(kSelThreads) chunk_topk_kernel(const ChunkTopkArgs a) {
-    __shared__ unsigned long long s[kChunk];
-    grid_dependency_wait();      // scores / keys come from the previous kernel of the chain
-    grid_launch_dependents();
-    const int q = blockIdx.y;
-    const long long c0 = (long long)blockIdx.x * kChunk;
-    long long n = a.n_fixed;
-    if (a.cnt) {
-        const int raw = a.cnt[q];
-        n = raw < a.cap ? raw : a.cap;
-    }
-    long long m = n - c0;
-    if (m > kChunk) m = kChunk;
-    unsigned long long* out = a.out + (size_t)q * (size_t)a.out_ld + (size_t)blockIdx.x * (size_t)a.K;
-    if (m <= 0) {
-        for (int i = threadIdx.x; i < a.K; i += blockDim.x) out[i] = 0ull;
-        return;
-    }
-    const int ns = next_pow2((int)m);
-    if (a.dense) {
-        const float* src = a.dense + (size_t)q * (size_t)a.dense_ld + (size_t)c0;
-        for (int i = threadIdx.x; i < ns; i += blockDim.x)
-            s[i] = i < m ? make_key(src[i], (uint32_t)(c0 + i)) : 0ull;
-    } else {
-        const unsigned long long* src = a.keys + (size_t)q * (size_t)a.keys_ld + (size_t)c0;
-        for (int i = threadIdx.x; i < ns; i += blockDim.x) s[i] = i < m ? src[i] : 0ull;
-    }
-    __syncthreads();
-    bitonic_desc_u64(s, ns);
-    for (int i = threadIdx.x; i < a.K; i += blockDim.x) out[i] = i < ns ? s[i] : 0ull;
-    // The k-th best of ANY subset of the DB is a lower bound of the k-th best of the whole DB, so
-    // admitting `score >= tau` in the next scan level never drops a true top-k item.
-    if (a.tau_out && threadIdx.x == 0 && gridDim.x == 1) {
-        float t = a.tau_floor;
-        if (a.tau_prev && a.tau_prev[q] > t) t = a.tau_prev[q];
-        const unsigned long long key = (a.tau_k - 1) < ns ? s[a.tau_k - 1] : 0ull;
-        if (key) {
-            const float c = key_score(key) - a.tau_margin;
-            if (c > t) t = c;
-        }
-        a.tau_out[q] = t;
-    }
-}
-
 // fp32 re-score of the candidates s[0..have) whose tensor score can still reach the top-k (score >= cut): 8 lanes
 // per candidate (four candidates per warp in flight, 16 independent 16-byte loads per lane for d = 1024), fp32
 // query (normalised) x bf16 DB row, fp32 FMA, then a 3-step shuffle reduction inside the 8-lane group.  Candidates
@@ -246,62 +201,6 @@ __device__ __forceinline__ void emit_overflow(const FinalArgs& a, int q) {
         if (a.push.world > 1) push_count(a.push, q, -1);
     }
     push_complete(a.push);
-}
-
-// grid (nq), 512 threads.  `top` holds the K2 best candidates of the query, sorted descending (small-Q path: exact fp32
-// scores, rescore == 0; kept general for lists of tensor scores).
-__global__ void __launch_bounds__(512) final_kernel(const FinalArgs a) {
-    __shared__ unsigned long long s[1024];
-    __shared__ int s_flag;
-    grid_dependency_wait();
-    grid_launch_dependents();
-    const int q = blockIdx.x;
-    const int K2 = a.K2;
-    const unsigned long long* src = a.top + (size_t)q * (size_t)a.top_ld;
-    int have_local = 0;
-    for (int i = threadIdx.x; i < K2; i += blockDim.x) {
-        const unsigned long long key = src[i];
-        s[i] = key;
-        have_local += key != 0ull;
-    }
-    // count non-empty keys (they form a prefix because `top` is sorted descending)
-    __shared__ int s_have;
-    if (threadIdx.x == 0) {
-        s_flag = 0;
-        s_have = 0;
-    }
-    __syncthreads();
-    if (have_local) atomicAdd(&s_have, have_local);
-    __syncthreads();
-    const int have = s_have;
-
-    bool overflow = false;
-    int raw = have;
-    if (a.cnt) {
-        raw = 0;
-        for (int sgm = 0; sgm < a.nseg; ++sgm) {
-            const int c = a.cnt[q * a.nseg + sgm];
-            raw += c;
-            if (c > a.cap) overflow = true;  // a sub-list dropped candidates
-        }
-    }
-    float cut = -__int_as_float(0x7f800000);
-    if (a.rescore && have >= a.k) {
-        cut = key_score(s[a.k - 1]) - (a.margin ? a.margin[q] : 0.f);
-        // K2 list is full, more survivors exist, and the worst kept one is still inside the margin:
-        // a survivor we did not keep could out-rank a kept one after the fp32 re-score.
-        if (have == K2 && raw > K2 && key_score(s[K2 - 1]) >= cut) overflow = true;
-    }
-    if (overflow) {
-        emit_overflow(a, q);
-        return;
-    }
-    if (a.rescore) {
-        rescore_candidates(s, have, cut, a.db, a.d_pad, a.qn + (size_t)q * (size_t)a.qn_ld);
-        __syncthreads();
-        sort_desc_u64(s, K2);
-    }
-    emit_topk(s, K2, a, q, &s_flag);
 }
 
 // ---- exact top-K of one query's candidates by histogram refinement ---------------------------------
@@ -730,6 +629,13 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
     sel_stamp(a, q, 4);           // first sort done
 
     if constexpr (FINAL) {
+        if (!f.rescore) {
+            // keys carry exact fp32 scores already (small-Q path): the sorted prefix IS the answer
+            if (tid == 0) s_count = 0;
+            __syncthreads();
+            emit_topk(sbuf, C, f, q, &s_count);
+            return;
+        }
         // ---- fused last level: every candidate that can still reach the top-k after the fp32 re-score is one whose
         // tensor score lies within the query's margin of the k-th best tensor score (common.cuh) ----
         const float NINF = -INF;
@@ -795,6 +701,183 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
             a.tau_hot_out[q] = hk ? fmaxf(key_score(hk), t) : t;
         }
     }
+}
+
+// ---- exact top-k of a dense score row (small-Q path) -------------------------------------------------------------------
+// One CTA of 1024 threads per query.  The fp32 scan of the Q <= 4 path leaves exact scores of the rows it visited (every
+// row of a small shard, or a strided sample of a large one); their ordering keys are unique, so the k-th largest key is
+// found by narrowing a key range with 2048-bin histograms until at most kDenseSort keys lie at or above the bound, which
+// are then compacted and sorted.  With at most 16 columns per thread the keys stay in REGISTERS across the rounds (the
+// reference's operating point, 10k rows: one read of 40 KB); otherwise every round re-reads the L2-resident row.
+//   FINAL  emit ids / scores / counts (score_threshold walk, id_offset, peer push) — the whole answer of a small shard
+//   TAU    tau_key_out[q] = k-th best key of the sample (0: fewer than k sampled rows, admit everything)
+constexpr int kDenseThreads = 1024;
+constexpr int kDenseSort = 2048;
+constexpr int kDenseCache = 16;
+constexpr int kDenseMaximaK = 128;
+
+template <bool CACHED, bool FINAL>
+__global__ void __launch_bounds__(kDenseThreads) dense_topk_kernel(const DenseTopkArgs a, const FinalArgs f) {
+    __shared__ int hist[kSelBins];
+    __shared__ unsigned long long sbuf[kDenseSort];
+    __shared__ unsigned long long s_red[2 * (kDenseThreads / 32)];
+    __shared__ unsigned long long s_lo, s_hi;
+    __shared__ int s_above, s_count, s_done, s_nnz, s_res[4];
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    grid_dependency_wait();
+    grid_launch_dependents();
+    const float* src = a.dense + (size_t)q * (size_t)a.dense_ld;
+    const long long pstride2 = a.pair_stride * 2;
+    auto key_of = [&](long long c) -> unsigned long long {
+        const long long row = (c >> 1) * pstride2 + (c & 1);
+        return row < a.n_rows ? make_key(__ldg(src + c), (uint32_t)row) : 0ull;
+    };
+    unsigned long long kc[CACHED ? kDenseCache : 1];
+    if (CACHED) {
+#pragma unroll
+        for (int i = 0; i < kDenseCache; ++i) {
+            const long long c = (long long)tid + (long long)i * kDenseThreads;
+            kc[i] = c < a.n_cols ? key_of(c) : 0ull;
+        }
+    }
+    auto for_each = [&](auto fn) {
+        if (CACHED) {
+#pragma unroll
+            for (int i = 0; i < kDenseCache; ++i)
+                if (kc[CACHED ? i : 0]) fn(kc[CACHED ? i : 0]);
+        } else {
+            for (long long c0 = tid; c0 < a.n_cols; c0 += 4 * kDenseThreads) {
+                unsigned long long k4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long c = c0 + (long long)u * kDenseThreads;
+                    k4[u] = c < a.n_cols ? key_of(c) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k4[u]) fn(k4[u]);
+            }
+        }
+    };
+    if (!FINAL && !CACHED && a.k <= kDenseMaximaK) {
+        // threshold from a LARGE sample in one pass: the k-th largest of the 1024 per-thread maxima.  The maxima are distinct
+        // elements of the sample, so their k-th largest is a lower bound of the sample's k-th largest key (hence of the
+        // shard's): a valid filter threshold, ~5 % more survivors than the exact one, without the multi-pass refinement
+        unsigned long long best = 0ull;
+        for_each([&](unsigned long long k) { best = k > best ? k : best; });
+        sbuf[tid] = best;
+        __syncthreads();
+        sort_desc_u64(sbuf, kDenseThreads);
+        if (tid == 0) a.tau_key_out[q] = sbuf[a.k - 1];      // 0 (fewer than k non-empty threads): admit everything
+        return;
+    }
+    // key range and number of valid keys
+    unsigned long long lmin = ~0ull, lmax = 0ull;
+    int lcnt = 0;
+    for_each([&](unsigned long long k) {
+        lmin = k < lmin ? k : lmin;
+        lmax = k > lmax ? k : lmax;
+        ++lcnt;
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long x = __shfl_xor_sync(0xFFFFFFFFu, lmin, o), y = __shfl_xor_sync(0xFFFFFFFFu, lmax, o);
+        lmin = x < lmin ? x : lmin;
+        lmax = y > lmax ? y : lmax;
+        lcnt += __shfl_xor_sync(0xFFFFFFFFu, lcnt, o);
+    }
+    if (tid == 0) s_nnz = 0;
+    __syncthreads();
+    if (lane == 0) {
+        s_red[warp] = lmin;
+        s_red[kDenseThreads / 32 + warp] = lmax;
+        if (lcnt) atomicAdd(&s_nnz, lcnt);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long mn = ~0ull, mx = 0ull;
+        for (int w = 0; w < kDenseThreads / 32; ++w) {
+            mn = s_red[w] < mn ? s_red[w] : mn;
+            mx = s_red[kDenseThreads / 32 + w] > mx ? s_red[kDenseThreads / 32 + w] : mx;
+        }
+        s_lo = mn;
+        s_hi = mx;
+        s_above = 0;
+        s_done = s_nnz <= kDenseSort / 2 ? 1 : 0;     // few enough: keep every key
+        if (s_done) s_lo = 0ull;
+    }
+    __syncthreads();
+    const int nnz = s_nnz;
+    const int want = a.k < nnz ? a.k : nnz;
+    for (int round = 0; round < 16 && !s_done; ++round) {
+        const unsigned long long lo = s_lo, hi = s_hi;
+        const int shift = hist_shift(lo, hi);
+        __syncthreads();
+        for (int i = tid; i < kSelBins; i += kDenseThreads) hist[i] = 0;
+        __syncthreads();
+        for_each([&](unsigned long long k) {
+            if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+        });
+        __syncthreads();
+        if (warp == 0) {
+            hist_find(hist, want - s_above, lane, s_res);
+            __syncwarp();
+            if (lane == 0) {
+                if (!s_res[3]) {          // cannot happen (want <= nnz): take everything rather than loop
+                    s_lo = 0ull;
+                    s_done = 1;
+                } else {
+                    const int cge = s_above + s_res[1];      // keys >= lower bound of the crossing bin
+                    s_lo = lo + ((unsigned long long)s_res[0] << shift);
+                    if (cge <= kDenseSort / 2 || shift == 0) {
+                        s_done = 1;
+                    } else {
+                        s_above = s_above + s_res[1] - s_res[2];
+                        s_hi = s_lo + ((1ull << shift) - 1ull);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned long long T = s_lo;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for_each([&](unsigned long long k) {
+        if (k >= T) {
+            const int at = atomicAdd(&s_count, 1);
+            if (at < kDenseSort) sbuf[at] = k;
+        }
+    });
+    __syncthreads();
+    const int C = s_count < kDenseSort ? s_count : kDenseSort;
+    const int ns = next_pow2(C > 2 ? C : 2);
+    for (int i = C + tid; i < ns; i += kDenseThreads) sbuf[i] = 0ull;
+    __syncthreads();
+    sort_desc_u64(sbuf, ns);
+    if (FINAL) {
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        emit_topk(sbuf, C, f, q, &s_count);
+    } else if (tid == 0) {
+        a.tau_key_out[q] = (a.k - 1) < C ? sbuf[a.k - 1] : 0ull;
+    }
+}
+
+int launch_dense_topk(const DenseTopkArgs& a, const FinalArgs* f, int nq, cudaStream_t stream) {
+    FinalArgs ff;
+    if (f) ff = *f;
+    else memset(&ff, 0, sizeof(ff));
+    const bool cached = a.n_cols <= (long long)kDenseCache * kDenseThreads;
+    if (f) {
+        if (cached) RVO_CUDA(launch_pdl(dense_topk_kernel<true, true>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
+        else RVO_CUDA(launch_pdl(dense_topk_kernel<false, true>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
+    } else {
+        if (cached) RVO_CUDA(launch_pdl(dense_topk_kernel<true, false>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
+        else RVO_CUDA(launch_pdl(dense_topk_kernel<false, false>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
+    }
+    RVO_LAUNCHED();
+    return RVO_OK;
 }
 
 // ---- seed threshold from per-thread maxima (see select.cuh) ----------------------------------------------------------
@@ -992,19 +1075,6 @@ __global__ void __launch_bounds__(256) merge_kernel(const int64_t* ids, const fl
 }
 
 // ---- host wrappers ------------------------------------------------------------------------------
-int launch_chunk_topk(const ChunkTopkArgs& a, int num_chunks, int nq, cudaStream_t stream) {
-    if (num_chunks <= 0 || nq <= 0) return RVO_OK;
-    RVO_CUDA(launch_pdl(chunk_topk_kernel, dim3(num_chunks, nq), dim3(kSelThreads), 0, stream, a));
-    RVO_LAUNCHED();
-    return RVO_OK;
-}
-
-int launch_final(const FinalArgs& a, int nq, cudaStream_t stream) {
-    RVO_CUDA(launch_pdl(final_kernel, dim3(nq), dim3(512), 0, stream, a));
-    RVO_LAUNCHED();
-    return RVO_OK;
-}
-
 int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts, long long ids_gs, long long scores_gs,
                  long long counts_gs, int G, int nq, int k, int64_t* out_ids, float* out_scores, int32_t* out_counts,
                  cudaStream_t stream, const unsigned long long* wait_flags, unsigned long long wait_epoch) {

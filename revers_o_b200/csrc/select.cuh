@@ -5,26 +5,15 @@
 
 namespace rvo {
 
-constexpr int kChunk = 4096;      // keys sorted per CTA in shared memory
 constexpr int kSelThreads = 512;
 
-struct ChunkTopkArgs {
-    const float* dense;                 // dense mode: scores [nq][dense_ld]  (keys == nullptr)
-    long long dense_ld;
-    const unsigned long long* keys;     // list mode: keys [nq][keys_ld]
-    long long keys_ld;
-    const int* cnt;                     // per-query element count (clipped to cap) or nullptr
-    int cap;
-    long long n_fixed;                  // element count when cnt == nullptr
-    int K;                              // keys kept per chunk
-    unsigned long long* out;            // [nq][out_ld]; chunk c writes [c*K, c*K+K)
-    long long out_ld;
-    // optional (single-chunk launches only): derive the next admission threshold of query q,
-    //   tau_out[q] = max(tau_prev[q], score(key[tau_k-1]) - tau_margin, tau_floor)
-    float* tau_out;
-    const float* tau_prev;
-    int tau_k;
-    float tau_margin, tau_floor;
+// exact top-k of dense fp32 scores (small-Q path, select.cu dense_topk_kernel)
+struct DenseTopkArgs {
+    const float* dense;                 // [nq][dense_ld] scores of the visited rows
+    long long dense_ld, n_cols;         // n_cols = 2 * visited row pairs
+    long long n_rows, pair_stride;      // column c is DB row (c >> 1) * 2 * pair_stride + (c & 1); valid iff < n_rows
+    int k;
+    unsigned long long* tau_key_out;    // threshold mode: k-th best ordering key of the sample per query
 };
 
 constexpr int kSelBins = 2048;    // histogram bins per refinement round
@@ -89,7 +78,9 @@ struct FinalArgs {
     PushArgs push;
 };
 
-int launch_chunk_topk(const ChunkTopkArgs& a, int num_chunks, int nq, cudaStream_t stream);
+// f != nullptr: emit the final answer (ids / scores / counts, threshold walk); f == nullptr: write a.tau_key_out
+struct FinalArgs;
+int launch_dense_topk(const DenseTopkArgs& a, const FinalArgs* f, int nq, cudaStream_t stream);
 int launch_select(const SelectArgs& a, int grid_q, cudaStream_t stream);
 // Seed level only (dense sample, k <= kSeedTauMaxK): tau_out[q] = max(k-th largest of the 512 per-thread maxima of the sample,
 // score_floor) - margin[q].  The per-thread maxima are distinct elements of the sample, so their k-th largest is a lower bound of
@@ -100,7 +91,6 @@ int launch_seed_tau(const float* dense, long long dense_ld, long long n_dense, i
 // last level fused with the fp32 re-score and the final ordering: `a` selects (a.K = candidates aimed at, a.out unused),
 // `f` supplies k, score_threshold, margin, db/qn and the outputs (f.top / f.cnt / f.K2 unused)
 int launch_select_final(const SelectArgs& a, const FinalArgs& f, int nq, cudaStream_t stream);
-int launch_final(const FinalArgs& a, int nq, cudaStream_t stream);
 // wait_flags != nullptr: every CTA first waits until wait_flags[g] >= wait_epoch for all g < G (peer pushes landed)
 int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts, long long ids_gs, long long scores_gs,
                  long long counts_gs, int G, int nq, int k, int64_t* out_ids, float* out_scores, int32_t* out_counts,

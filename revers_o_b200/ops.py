@@ -168,10 +168,10 @@ def mask_pool_to_db(feats: torch.Tensor, masks: torch.Tensor, db: torch.Tensor, 
 
 
 def search_topk(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, k: int,
-                score_threshold: float | None = None, id_offset: int = 0, out=None):
+                score_threshold: float | None = None, id_offset: int = 0, out=None, path: int = 0):
     """K2.  db: tiled bf16 DB storage (`db_alloc`) holding >= n_rows normalised rows, queries f32 [nq, d].
     Returns device tensors (ids int64 [nq,k], scores f32 [nq,k], counts int32 [nq]); async on the current stream.
-    counts[q] == -1 marks an overflowed query (see `search_topk_exact`)."""
+    counts[q] == -1 marks an overflowed query (see `search_topk_exact`).  `path`: _lib.RVO_PATH_* (0 = by batch size)."""
     require_cuda(db, "db")
     if not (queries.is_cuda or queries.is_pinned()):
         raise RvoError("queries must be a CUDA tensor or a pinned host tensor: the B200 library has no CPU path")
@@ -189,36 +189,47 @@ def search_topk(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, k:
     else:
         ids, scores, counts = out
     lib = _lib.load()
-    wkey = (n_rows, d, nq, k, _lib.option_epoch)
+    wkey = (n_rows, d, nq, k, path, _lib.option_epoch)
     nbytes = _ws_bytes.get(wkey)
     if nbytes is None:
-        nbytes = lib.rvo_search_workspace_bytes(n_rows, d, nq, k)
+        nbytes = lib.rvo_search_workspace_bytes_ex(n_rows, d, nq, k, path)
         if nbytes == 0:
-            raise RvoError(f"rvo_search_workspace_bytes rejected n_rows={n_rows} d={d} nq={nq} k={k}: "
+            raise RvoError(f"rvo_search_workspace_bytes rejected n_rows={n_rows} d={d} nq={nq} k={k} path={path}: "
                            + lib.rvo_last_error().decode())
         if len(_ws_bytes) > 256:
             _ws_bytes.clear()
         _ws_bytes[wkey] = nbytes
     ws = workspace(dev, nbytes)
     thr = -math.inf if score_threshold is None else float(score_threshold)
-    check(lib.rvo_search_topk(_ptr(db), n_rows, d, d_pad_of(d), _ptr(queries), nq, k, thr, int(id_offset), _ptr(ids),
-                              _ptr(scores), _ptr(counts), _ptr(ws), nbytes, _stream(dev)), "rvo_search_topk")
+    check(lib.rvo_search_topk_ex(_ptr(db), n_rows, d, d_pad_of(d), _ptr(queries), nq, k, thr, int(id_offset), int(path), _ptr(ids),
+                                 _ptr(scores), _ptr(counts), _ptr(ws), nbytes, _stream(dev)), "rvo_search_topk")
     return ids, scores, counts
 
 
 def search_topk_exact(db, n_rows, d, queries, k, score_threshold=None, id_offset=0):
-    """`search_topk` plus the documented overflow protocol: queries flagged -1 by the fused path are re-run in
-    batches of <= RVO_SMALL_Q through the exact fp32 scan, which cannot overflow.  Synchronises (reads counts)."""
+    """`search_topk` plus the documented overflow protocol: queries flagged -1 by the fused path are re-run in batches of
+    <= RVO_SMALL_Q through the exact fp32 scan, and — should its survivor lists overflow as well (adversarial row order) —
+    through the dense fp32 route, which cannot overflow whatever the data.  Synchronises (reads counts)."""
     ids, scores, counts = search_topk(db, n_rows, d, queries, k, score_threshold, id_offset)
     bad = (counts < 0).nonzero().flatten().tolist()  # host sync; pathological inputs only take the branch
-    for i in range(0, len(bad), RVO_SMALL_Q):
-        sel = bad[i:i + RVO_SMALL_Q]
-        sub = queries[sel].contiguous()
-        a, b, c = search_topk(db, n_rows, d, sub, k, score_threshold, id_offset)
-        for j, q in enumerate(sel):
-            ids[q].copy_(a[j])
-            scores[q].copy_(b[j])
-            counts[q] = c[j]
+    small_ok = d_pad_of(d) <= 2048
+    for path in ((_lib.RVO_PATH_SMALL, _lib.RVO_PATH_DENSE) if small_ok else ()):
+        still = []
+        for i in range(0, len(bad), RVO_SMALL_Q):
+            sel = bad[i:i + RVO_SMALL_Q]
+            sub = queries[sel].contiguous()
+            a, b, c = search_topk(db, n_rows, d, sub, k, score_threshold, id_offset, path=path)
+            cl = c.tolist()
+            for j, q in enumerate(sel):
+                if cl[j] < 0:
+                    still.append(q)
+                    continue
+                ids[q].copy_(a[j])
+                scores[q].copy_(b[j])
+                counts[q] = c[j]
+        bad = still
+        if not bad:
+            break
     return ids, scores, counts
 
 

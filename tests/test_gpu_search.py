@@ -427,3 +427,54 @@ def test_non_finite_vectors_are_stored_as_zero_vectors(dev):
     xf = x.copy(); xf[7] = 0; xf[9] = 0
     ref = O.search_batch(O.round_to_bf16(O._cosine_prepare(xf)), q[good], k, None, db_is_normalized=True)
     assert_topk_match(ids[good], sc[good], cnt[good], ref, k, TOL, "nonfinite")
+
+
+# ---- the reference's operating point (Q <= 4) on shards beyond the keep-every-score regime ----------------------------
+@pytest.mark.parametrize("n,d,nq,k,thr", [
+    (400_000, 1024, 1, 10, None),       # sampled: [sample scan] -> [k-th best key] -> [filtered full scan] -> [exact top-k]
+    (400_000, 1024, 4, 100, 0.3),
+    (250_001, 1280, 3, 512, None),      # odd row count, maximum k, PE-Core-G14 width
+    (131_072, 256, 2, 10, None),        # last size of the dense regime
+    (131_073, 256, 2, 10, None),        # first size of the sampled regime
+    (150_000, 2048, 2, 20, None),       # long rows (register-heavy instantiation)
+])
+def test_small_q_sampled_regime_matches_oracle(dev, n, d, nq, k, thr):
+    from revers_o_b200 import synth
+    q = synth.make_queries(nq, d, seed=21, device=dev)
+    db = synth.make_db(n, d, q, n_plant=min(128, 2 * k), seed=22, device=dev)
+    ids, sc, cnt = _run(db, n, d, q, k, thr)
+    assert_topk_match(ids, sc, cnt, _oracle(db, n, d, q, k, thr), k, TOL, f"small n{n}d{d}q{nq}k{k}")
+
+
+def test_small_q_paths_agree_bit_for_bit_and_dense_route_never_overflows(dev):
+    """AUTO (sampled), SMALL and DENSE compute a row's score with the same arithmetic: identical ids AND scores.  A shard whose
+    rows are all the same vector (every score ties, 300k survivors of any threshold) overflows the survivor lists of the
+    sampled route (count -1) — the dense route and `search_topk_exact` still return the exact answer (lowest rows first)."""
+    from revers_o_b200 import _lib, ops, synth
+    n, d, nq, k = 300_000, 512, 3, 50
+    q = synth.make_queries(nq, d, seed=31, device=dev)
+    db = synth.make_db(n, d, q, n_plant=64, seed=32, device=dev)
+    a = ops.search_topk(db, n, d, q, k)
+    b = ops.search_topk(db, n, d, q, k, path=_lib.RVO_PATH_DENSE)
+    c = ops.search_topk(db, n, d, q, k, path=_lib.RVO_PATH_SMALL)
+    torch.cuda.synchronize()
+    for x, y in ((a, b), (a, c)):
+        assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2])
+    # tensor path on the same 3 queries: same ids, scores within tolerance
+    t = ops.search_topk(db, n, d, q, k, path=_lib.RVO_PATH_TENSOR)
+    assert torch.equal(t[0], a[0]) and float((t[1] - a[1]).abs().max()) < 1e-5
+    # all-equal rows: rows 0..k-1 win every tie
+    one = torch.randn((1, d), generator=torch.Generator().manual_seed(1)).to(dev)
+    same = ops.db_alloc(n, d, dev)
+    ops.normalize_rows(one.expand(4096, d).contiguous(), db=same, row0=0)
+    blk = same[: 4096 // 128].clone()
+    for b0 in range(0, same.shape[0], blk.shape[0]):
+        m = min(blk.shape[0], same.shape[0] - b0)
+        same[b0: b0 + m].copy_(blk[:m])
+    qq = one.contiguous()
+    ids, sc, cnt = ops.search_topk(same, n, d, qq, k)
+    assert int(cnt[0]) in (-1, k)
+    ids, sc, cnt = ops.search_topk(same, n, d, qq, k, path=_lib.RVO_PATH_DENSE)
+    assert int(cnt[0]) == k and ids[0].tolist() == list(range(k)) and float(sc[0].min()) > 0.99
+    ids, sc, cnt = ops.search_topk_exact(same, n, d, qq, k)
+    assert int(cnt[0]) == k and ids[0].tolist() == list(range(k))
