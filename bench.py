@@ -18,12 +18,19 @@ Printed JSON (rank 0, one line):
                 inside the timed region): B200VectorDB.search_batch at N = 1, ShardedIndex.search + copies at N > 1
   roofline      the dominant kernel (full-shard scan) timed alone by the library's own CUDA events on its stream, against
                 MEASURED_PEAKS.json; `traffic` = DRAM bytes of that kernel from the committed ncu capture (profiles/traffic.json)
+  verify        the TIMED result checked in-run against a plain fp32 restatement on the GPU (every rank scores a query sample
+                against its shard, lists merged on the host): ids / scores, not just counts; verify_oracle (N = 1): the CPU
+                oracle itself on the downloaded DB
   north_star    BASELINE.json's metric layout — 12.5M x 1280 rows PER GPU (N = 8 is configs[3], 100M x 1280), Q = 4096 / 64 / 16 —
-                measured in the same run as a weak-scaling series (--no-north-star skips it)
-  mask_pool     the other half of the path (K1) on configs[2], N = 1 only
+                as a weak-scaling series; north_star_strong: the full 100M x 1280 DB over N = 2 / 4 ranks (N = 8: the weak point)
+  mask_pool     the other half of the path (K1) on configs[2], one batch per GPU (replicas, no collective)
+  selfjoin      configs[4]: 2M x 1024 near-duplicate self-join at cos >= 0.95 over the N ranks, with its tensor roofline
+  cfg0          configs[0], the reference's own operating point (10k x 1024, ONE query, top-10): resident, e2e, the qdrant-shaped
+                `search()` call on the host clock, and the CPU oracle at full size
   cpu_baseline  the CPU oracle (numpy port of the reference's qdrant-local search) timed on this box's host cores on a
                 bounded query sample, plus a labelled "fair batched" figure (one sgemm + argpartition)
   clocks, gpu_launches, local_shard_ms_per_step (N > 1: K2 alone, max over ranks)
+(--no-north-star: the primary workload only.)
 
 `--impl reference` times that CPU implementation alone (numpy-only process; the reference's own dependency
 qdrant-client is not installable here, so kind="port").
@@ -205,7 +212,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     from revers_o_b200 import _lib, ops, synth
-    from revers_o_b200.sharded import ShardedIndex, shard_bounds
+    from revers_o_b200.sharded import ShardedIndex, selfjoin_blocks, shard_bounds
     from revers_o_b200.vector_db import B200VectorDB, models
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,18 +233,17 @@ def run_b200(args):
     if n_local * d * 2 > 150e9:
         raise SystemExit(f"bench.py: workload {args.workload} needs {n_local * d * 2 / 1e9:.0f} GB per GPU at {world} GPU(s); "
                          "launch it on more ranks")
-    q_dev = synth.make_queries(nq, d, seed=7, device=dev)
-    db = synth.make_db(n_local, d, q_dev, n_plant=max(1, 128 // world), seed=1000 + rank, device=dev)
-    index = ShardedIndex(db, n_local, d, lo)
-    exchange = "none"
-    if world > 1:
-        exchange = "peer-memory push fused into K2 (NVLink stores + epoch flags)" if (
-            args.exchange != "nccl" and index.enable_peer_exchange(nq, k)) else "NCCL all_gather_into_tensor"
     lib = _lib.load()
     for kv in filter(None, os.environ.get("RVO_OPTS", "").split(",")):  # tuning sweeps only (scripts/gpu_sweep.sh)
         name, val = kv.split("=")
         _lib.set_option(name.strip(), int(val))
     peaks, peaks_kind = load_peaks()
+    extras = args.workload == "cfg1" and not args.no_north_star
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        traffic = json.load(open(tp))
+    except Exception:
+        traffic = {}
 
     def barrier():
         if world > 1:
@@ -285,7 +291,7 @@ def run_b200(args):
         small_ = nq_ <= _lib.RVO_SMALL_Q
         hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                "frac": hbm_ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peaks_kind,
-               "kernel": "scan_small_kernel" if small_ else "scan_tc2_kernel<FILTER> / scan_tc_kernel<FILTER> (full-shard level)",
+               "kernel": "scan_small_kernel (fp32, every row)" if small_ else "scan_tc2_kernel<FILTER> / scan_tc_kernel<FILTER> (full-shard level)",
                "kernel_ms": scan_avg, "algorithmic_bytes": alg_bytes, "share_of_step": scan_avg / ms_step}
         tensor = None if small_ else {
             "bound": "tensor", "achieved": tf_ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
@@ -294,12 +300,79 @@ def run_b200(args):
             "algorithmic_flops": alg_flops, "share_of_step": scan_avg / ms_step}
         return hbm, tensor
 
-    # ---- value: inputs resident in HBM --------------------------------------------------------------
+    def verify(idx, q, out, kk, n_sample=8, tol=1e-3):
+        """The TIMED result, checked in-run (not just `counts == k`): a plain fp32 restatement of the search on the GPU — every
+        rank scores a sample of the queries against its own shard with torch fp32 matmuls (checker code, not the product), the
+        per-rank lists are gathered and merged on the host by (score desc, id asc), and compared with what the step returned:
+        scores within 1e-3, identical id sets except ties within 1e-3 (north_star)."""
+        nq_ = q.shape[0]
+        sel = sorted(set(np.linspace(0, nq_ - 1, min(n_sample, nq_)).astype(int).tolist()))
+        qs = q[sel].float()
+        qs = qs / qs.norm(dim=1, keepdim=True)
+        best_s = torch.full((len(sel), kk), -float("inf"), device=dev)
+        best_i = torch.full((len(sel), kk), -1, dtype=torch.int64, device=dev)
+        nblk = (idx.n_local + 127) // 128
+        step_blk = 4096                                              # 512k rows per matmul
+        for b0 in range(0, nblk, step_blk):
+            b1 = min(nblk, b0 + step_blk)
+            rows = idx.db[b0:b1].permute(0, 2, 1, 3).reshape((b1 - b0) * 128, -1)[:, : idx.d].float()
+            sc = qs @ rows.T
+            valid = idx.n_local - b0 * 128
+            if valid < sc.shape[1]:
+                sc[:, valid:] = -float("inf")
+            kk2 = min(kk, sc.shape[1])
+            ts, ti = sc.topk(kk2, dim=1)
+            cs = torch.cat([best_s, ts], 1)
+            ci = torch.cat([best_i, ti + b0 * 128 + idx.id_offset], 1)
+            o = cs.argsort(dim=1, descending=True, stable=True)[:, :kk]
+            best_s, best_i = cs.gather(1, o), ci.gather(1, o)
+            del rows, sc
+        part = (best_s.cpu().numpy(), best_i.cpu().numpy())
+        parts = [part]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, part)
+        got_i, got_s, got_c = (t[sel].cpu().numpy() for t in out)
+        if rank != 0:
+            return None
+        bad_ids = 0
+        max_diff = 0.0
+        for j in range(len(sel)):
+            cs = np.concatenate([p[0][j] for p in parts])
+            ci = np.concatenate([p[1][j] for p in parts])
+            keep = ci >= 0
+            cs, ci = cs[keep], ci[keep]
+            o = np.lexsort((ci, -cs.astype(np.float64)))[:kk]
+            rs, ri = cs[o], ci[o]
+            c = int(got_c[j])
+            if c != len(ri):
+                bad_ids += abs(c - len(ri))
+                continue
+            max_diff = max(max_diff, float(np.max(np.abs(got_s[j, :c] - rs))) if c else 0.0)
+            boundary = min(got_s[j, c - 1], rs[-1]) if c else 0.0
+            smap = dict(zip(got_i[j, :c].tolist(), got_s[j, :c].tolist()))
+            rmap = dict(zip(ri.tolist(), rs.tolist()))
+            for i_ in set(smap) ^ set(rmap):
+                if abs(smap.get(i_, rmap.get(i_)) - boundary) > tol:
+                    bad_ids += 1
+        return {"checker": "fp32 restatement on the GPU (torch matmul per shard + host merge), compared with the timed step's result",
+                "queries_checked": len(sel), "k": kk, "max_abs_score_diff": max_diff, "ids_differing_beyond_1e-3_ties": bad_ids,
+                "ok": bool(bad_ids == 0 and max_diff <= tol)}
+
+    # ---- primary workload: value with inputs resident in HBM ------------------------------------------------
+    q_dev = synth.make_queries(nq, d, seed=7, device=dev)
+    db = synth.make_db(n_local, d, q_dev, n_plant=max(1, 128 // world), seed=1000 + rank, device=dev)
+    index = ShardedIndex(db, n_local, d, lo)
+    exchange = "none"
+    if world > 1:
+        exchange = "peer-memory push fused into K2 (NVLink stores + epoch flags)" if (
+            args.exchange != "nccl" and index.enable_peer_exchange(nq, k)) else "NCCL all_gather_into_tensor"
     sampler = ClockSampler(local)
     sampler.start()
     ms_step, launches, out = timed(lambda: index.search(q_dev, k), args.steps, max(3, args.warmup))
     value = nq / (ms_step / 1e3)
     counts_ok = bool((out[2] == k).all().item())
+    check = verify(index, q_dev, out, k)
 
     # N > 1: the same step without the exchange + merge (K2 on the local shard only), to show what the exchange costs
     local_ms = None
@@ -310,12 +383,7 @@ def run_b200(args):
     roofline, roofline_tensor = scan_rooflines(index, q_dev, k, ms_step, max(5, min(args.steps, 30)))
     small = nq <= _lib.RVO_SMALL_Q
     alg_bytes = n_local * d * 2
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            roofline["traffic"] = json.load(open(tp)).get(args.workload)
-        except Exception:
-            pass
+    roofline["traffic"] = traffic.get(args.workload)
     if roofline_tensor is not None and nq >= 1024:     # tensor-bound regime: the tensor roofline is the binding one
         roofline_tensor["traffic"] = roofline["traffic"]
         roofline, roofline_hbm = roofline_tensor, roofline
@@ -326,6 +394,7 @@ def run_b200(args):
     q_host = q_dev.cpu().numpy()
     h2d = q_host.nbytes
     d2h = nq * k * 12 + nq * 4
+    oracle_check = None
     if world == 1:
         vdb = B200VectorDB(device=dev)
         vdb.recreate_collection("bench", vectors_config=models.VectorParams(size=d, distance=models.Distance.COSINE))
@@ -359,66 +428,235 @@ def run_b200(args):
                 pi.copy_(a, non_blocking=True); ps.copy_(b, non_blocking=True); pc.copy_(c_, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return pi, ps, pc
-    e2e_ms, _, _ = timed(step_e2e, args.steps, max(3, args.warmup))
+    e2e_ms, _, e2e_out = timed(step_e2e, args.steps, max(3, args.warmup))
     clocks = sampler.stop()
+    # the e2e result is the same answer as the resident one
+    e2e_same = bool(np.array_equal(np.asarray(e2e_out[0]), out[0].cpu().numpy()) and
+                    np.array_equal(np.asarray(e2e_out[2]), out[2].cpu().numpy()))
 
-    # ---- north star series (BASELINE.json metric: 100M x 1280 at 1/2/4/8 GPUs): the 100M x 1280 DB does not fit
-    # one GPU, so every rank holds ITS 12.5M-row shard of the 8-GPU layout (weak scaling: N = 8 IS configs[3]) ----
-    north = None
+    # N = 1: the CPU ORACLE itself on a query sample of the timed configuration (the DB is downloaded: the same bf16 values)
+    if world == 1 and not args.no_cpu_baseline and n_local * d * 4 < 8e9:
+        from oracle import reverso_oracle as O
+        sel = sorted(set(np.linspace(0, nq - 1, min(4, nq)).astype(int).tolist()))
+        dbf = np.empty((n_local, d), np.float32)
+        for r0 in range(0, n_local, 1 << 18):
+            r1 = min(n_local, r0 + (1 << 18))
+            dbf[r0:r1] = ops.untile_rows(db, n_local, d, torch.arange(r0, r1, device=dev)).float().cpu().numpy()
+        ref = O.search_batch(dbf, q_host[sel], k, None, db_is_normalized=True)
+        del dbf
+        gi, gs, gc = (np.asarray(t)[sel] for t in e2e_out)
+        worst, bad = 0.0, 0
+        for j, (rid, rsc) in enumerate(ref):
+            if int(gc[j]) != len(rid):
+                bad += 1
+                continue
+            worst = max(worst, float(np.max(np.abs(gs[j, : len(rid)] - rsc))))
+            smap, rmap = dict(zip(gi[j].tolist(), gs[j].tolist())), dict(zip(rid.tolist(), rsc.tolist()))
+            boundary = min(gs[j, len(rid) - 1], rsc[-1])
+            bad += sum(1 for i_ in set(smap) ^ set(rmap) if abs(smap.get(i_, rmap.get(i_)) - boundary) > 1e-3)
+        oracle_check = {"checker": "oracle/reverso_oracle.py (numpy restatement of qdrant-local search) on the downloaded bf16-valued DB, "
+                                   "compared with the timed e2e result", "queries_checked": len(sel),
+                        "max_abs_score_diff": worst, "ids_differing_beyond_1e-3_ties": bad, "ok": bool(bad == 0 and worst <= 1e-3)}
+
     index.disable_peer_exchange()
-    if args.workload == "cfg1" and not args.no_north_star:
-        del index, db
-        if world == 1:
-            del vdb, c
-        torch.cuda.empty_cache()
-        north = {"workload": f"configs[3] shard layout: 12.5M x 1280 bf16 rows per GPU x {world} GPU(s) = "
-                             f"{12.5 * world:.1f}M rows total, top-100, all-gather + K3 merge when N > 1",
-                 "scaling": "weak", "rows_per_gpu": 12_500_000, "rows_total": 12_500_000 * world, "dim": 1280, "points": []}
-        ns_n, ns_d = 12_500_000, 1280
+    del index, db
+    if world == 1:
+        del vdb, c
+    torch.cuda.empty_cache()
+
+    # ---- north star series (BASELINE.json metric: 100M x 1280 at 1/2/4/8 GPUs) -----------------------------------------
+    # weak: every rank holds ITS 12.5M-row shard of the 8-GPU layout (N = 8 IS configs[3]);
+    # strong: the full 100M x 1280 DB row-sharded over the N ranks where it fits (N = 2: 128 GB per GPU, N = 4: 64 GB; N = 8 is
+    # the weak point; one GPU cannot hold 256 GB)
+    def ns_series(rows_per_gpu, queries_list, seed0, what):
+        ns_d = 1280
         q_all = synth.make_queries(4096, ns_d, seed=7, device=dev)
-        ns_db = synth.make_db(ns_n, ns_d, q_all, n_plant=16, seed=2000 + rank, device=dev)
-        ns_index = ShardedIndex(ns_db, ns_n, ns_d, rank * ns_n)
+        ns_db = synth.make_db(rows_per_gpu, ns_d, q_all, n_plant=16, seed=seed0 + rank, device=dev)
+        ns_index = ShardedIndex(ns_db, rows_per_gpu, ns_d, rank * rows_per_gpu)
         if world > 1 and args.exchange != "nccl":
             ns_index.enable_peer_exchange(4096, 100)
-        for ns_q in (4096, 64, 16):
+        pts = []
+        for ns_q in queries_list:
             qd_ = q_all[:ns_q].contiguous()
             # small batches: the first ~20 steps after the tensor-bound phase run up to 20 % slower (measured; clocks
             # settling), so they get a longer warm-up
-            ns_steps, ns_warm = (5, 3) if ns_q >= 1024 else (20, 20)
+            ns_steps, ns_warm = ((5, 3) if rows_per_gpu <= 12_500_000 else (3, 2)) if ns_q >= 1024 else (20, 20)
             ns_ms, _, ns_out = timed(lambda: ns_index.search(qd_, 100), ns_steps, ns_warm)
+            ns_check = verify(ns_index, qd_, ns_out, 100, n_sample=4)
             r_h, r_t = scan_rooflines(ns_index, qd_, 100, ns_ms, 3)
-            ns_traffic = {4096: "cfg3shard", 64: "cfg3shardq64", 16: "cfg3shardq16"}[ns_q]
-            try:
-                r_h["traffic"] = json.load(open(tp)).get(ns_traffic)
+            if rows_per_gpu == 12_500_000:
+                r_h["traffic"] = traffic.get({4096: "cfg3shard", 64: "cfg3shardq64", 16: "cfg3shardq16"}.get(ns_q))
                 if r_t is not None:
                     r_t["traffic"] = r_h["traffic"]
-            except Exception:
-                pass
-            north["points"].append({
-                "queries": ns_q, "value": ns_q / (ns_ms / 1e3), "unit": "queries/s", "ms_per_step": ns_ms, "steps": ns_steps,
-                "results_ok": bool((ns_out[2] == 100).all().item()),
-                "roofline": r_t if ns_q >= 1024 else r_h})
+            pts.append({"queries": ns_q, "value": ns_q / (ns_ms / 1e3), "unit": "queries/s", "ms_per_step": ns_ms, "steps": ns_steps,
+                        "results_ok": bool((ns_out[2] == 100).all().item()) and (ns_check is None or ns_check["ok"]),
+                        "verify": ns_check, "roofline": r_t if ns_q >= 1024 else r_h})
         ns_index.disable_peer_exchange()
         del ns_db, ns_index
         torch.cuda.empty_cache()
+        return {"workload": what, "rows_per_gpu": rows_per_gpu, "rows_total": rows_per_gpu * world, "dim": ns_d, "points": pts}
 
-    # ---- K1 (the other half of the path): mask pooling on BASELINE configs[2], rank 0 at N = 1 only ---------------
+    north = strong = None
+    if extras:
+        north = ns_series(12_500_000, (4096, 64, 16), 2000,
+                          f"configs[3] shard layout: 12.5M x 1280 bf16 rows per GPU x {world} GPU(s) = {12.5 * world:.1f}M rows "
+                          "total, top-100, exchange + K3 merge when N > 1")
+        north["scaling"] = "weak"
+        if world in (2, 4) and not args.no_strong:
+            rows = 100_000_000 // world // 128 * 128
+            strong = ns_series(rows, (4096,), 3000,
+                               f"configs[3] STRONG-scaled: the full 100M x 1280 bf16 DB row-sharded over {world} GPUs "
+                               f"({rows * 1280 * 2 / 1e9:.0f} GB per GPU), 4096-query batch, top-100, exchange + K3 merge")
+            strong["scaling"] = "strong"
+        elif world == 8:
+            strong = {"scaling": "strong", "note": "at 8 GPUs the strong-scaled configs[3] IS the weak series' point (12.5M rows per GPU)",
+                      "points": [p for p in north["points"] if p["queries"] == 4096]}
+        else:
+            strong = {"scaling": "strong", "note": "100M x 1280 bf16 = 256 GB does not fit one B200 (180 GB): strong points exist "
+                                                   "for N = 2, 4, 8", "points": []}
+
+    # ---- K1 (the other half of the path): mask pooling on BASELINE configs[2]; N > 1: independent replicas ---------------
     pool = None
-    if world == 1 and args.workload == "cfg1" and not args.no_north_star:
+    if extras:
         pB, pM, pG, pD = 256, 64, 24, 1024
-        feats, masks = synth.make_maskpool_inputs(pB, pM, pG, pD, seed=11, device=dev)
+        feats, masks = synth.make_maskpool_inputs(pB, pM, pG, pD, seed=11 + rank, device=dev)
         p_ms, p_launches, p_out = timed(lambda: ops.mask_pool(feats, masks), 20, 5)   # 311 MB of inputs > L2: streams HBM
         regions = int(p_out[3].item())
         alg = pB * pG * pG * pD * 2 + pB * pM * pG * pG + regions * pD * 4
         pool = {"workload": "configs[2]: 256 images x 64 masks x 24x24 patches x 1024-d bf16 features (random-init stand-in), "
-                            "fp32 L2-normalised region embeddings out",
-                "value": pB / (p_ms / 1e3), "unit": "images/s", "ms_per_batch": p_ms, "regions": regions,
-                "gpu_launches_per_batch": p_launches / 20,
+                            "fp32 L2-normalised region embeddings out" + (f"; {world} independent replicas (one batch per GPU)" if world > 1 else ""),
+                "value": world * pB / (p_ms / 1e3), "unit": "images/s", "ms_per_batch": p_ms, "regions_per_batch": regions,
+                "gpu_launches_per_batch": p_launches / 20, "scaling": "replicas only (no collective)",
                 "roofline": {"bound": "hbm", "achieved": alg / (p_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": alg / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg,
-                             "kernel": "mask_pool_tc_kernel (whole rvo_mask_pool call: memset + one launch)",
+                             "traffic": traffic.get("mask_pool"),
+                             "kernel": "mask_pool_tc_kernel (whole rvo_mask_pool call: memset + one launch), per GPU",
                              "peak_kind": peaks_kind}}
         del feats, masks, p_out
+        torch.cuda.empty_cache()
+
+    # ---- configs[4]: near-duplicate self-join, 2M x 1024, cos >= 0.95; DB replicated, query blocks dealt over the ranks ----
+    selfjoin = None
+    if extras and not args.no_selfjoin:
+        sn, sd, thr = 2_000_000, 1024, 0.95
+        sdb = synth.make_selfjoin_db(sn, sd, 0.05, dev, seed=5)               # same seed on every rank: replicated DB
+        ops.selfjoin_threshold(sdb, sn, sd, thr, 0, min(sn, 8192), out_cap=1 << 20)   # warm-up
+        blocks = selfjoin_blocks(sn, world, rank)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        ovf = torch.zeros(1, dtype=torch.int64, device=dev)
+        kept = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.kernel_launch_count()
+        e0.record()
+        for blo, bhi in blocks:
+            pairs, scores, count, over = ops.selfjoin_threshold(sdb, sn, sd, thr, blo, bhi, out_cap=1 << 21)
+            cnt += count
+            ovf += over
+            kept.append((blo, bhi, pairs, count))
+        e1.record()
+        barrier()
+        sj_s = max_over_ranks(e0.elapsed_time(e1)) / 1e3
+        sj_launches = _lib.kernel_launch_count() - l0
+        # in-run check: for a sample of this rank's query rows, every partner j > i with fp32 cos >= 0.95 (GPU restatement)
+        rows_f = None
+        bad_rows, checked = 0, 0
+        rs = np.random.RandomState(rank)
+        for blo, bhi, pairs, count in kept[:2]:
+            m = int(count.item())
+            pr = pairs[:m].cpu().numpy()
+            for i_ in rs.randint(blo, bhi, 8).tolist():
+                vi = ops.untile_rows(sdb, sn, sd, torch.tensor([i_], device=dev)).float()[0]
+                sc = torch.empty(0, device=dev)
+                want, near = set(), set()
+                for c0 in range((i_ + 1) // 128 * 128, sn, 1 << 19):
+                    c1 = min(sn, c0 + (1 << 19))
+                    blk = sdb[c0 // 128: (c1 + 127) // 128].permute(0, 2, 1, 3).reshape(-1, sdb.shape[1] * 64)[: c1 - c0, :sd].float()
+                    s_ = blk @ vi
+                    jj = torch.arange(c0, c1, device=dev)
+                    ok_ = jj > i_
+                    want |= set(jj[ok_ & (s_ >= thr)].tolist())
+                    near |= set(jj[ok_ & ((s_ - thr).abs() <= 1e-3)].tolist())
+                got = set(pr[pr[:, 0] == i_][:, 1].tolist())
+                checked += 1
+                if not ((got ^ want) <= near):
+                    bad_rows += 1
+        tot = torch.stack([cnt.squeeze(), ovf.squeeze(), torch.tensor(bad_rows, device=dev), torch.tensor(checked, device=dev)])
+        if world > 1:
+            dist.all_reduce(tot)
+        flops = float(sn) * sn * sd                       # 2 * (N^2 / 2) * D: only the upper triangle is scanned
+        selfjoin = {"workload": f"configs[4]: near-duplicate self-join, {sn} x {sd} bf16 frame embeddings, cos >= {thr}, 5 % planted "
+                                f"near-duplicates; DB replicated on {world} GPU(s), 4096-row query blocks dealt in snake order, no "
+                                "data-path collective",
+                    "value": sn / sj_s, "unit": "rows joined/s", "seconds": sj_s, "pairs": int(tot[0].item()),
+                    "overflowed_lists": int(tot[1].item()), "gpu_launches": int(sj_launches),
+                    "verify": {"checker": "fp32 restatement on the GPU of all partners of sampled query rows", "rows_checked": int(tot[3].item()),
+                               "rows_with_wrong_partner_sets": int(tot[2].item()), "ok": bool(int(tot[2].item()) == 0 and int(tot[1].item()) == 0)},
+                    "roofline": {"bound": "tensor", "achieved": flops / sj_s / 1e12 / world, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                 "frac": flops / sj_s / 1e12 / world / peaks["bf16_tflops"], "algorithmic_flops": flops,
+                                 "flops_definition": "N^2 * D: upper triangle only (block b scans rows >= b), per GPU = total / N",
+                                 "traffic": traffic.get("selfjoin"), "traffic_note": "every 4096-row query block re-streams the DB tail "
+                                 "(~N/4096/2 passes over the 4.1 GB DB ~ 1 TB of HBM reads at N = 2M); harmless while tensor-bound",
+                                 "kernel": "scan_tc2_kernel<FILTER> per 4096-row query block + pairs_kernel", "peak_kind": peaks_kind + " burst"}}
+        del sdb, kept
+        torch.cuda.empty_cache()
+
+    # ---- configs[0]: the reference's own operating point — 10k x 1024, ONE query, top-10 (rank 0, N = 1 semantics) ---------
+    cfg0 = None
+    if extras and rank == 0:
+        n0, d0, k0 = 10_000, 1024, 10
+        q0 = synth.make_queries(1, d0, seed=7, device=dev)
+        db0 = synth.make_db(n0, d0, q0, n_plant=32, seed=1000, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def time_local(fn, steps=300, warm=30):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                r_ = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps, r_
+        res_ms, res_out = time_local(lambda: ops.search_topk(db0, n0, d0, q0, k0, 0.0))
+        v0 = B200VectorDB(device=dev)
+        v0.recreate_collection("c0", vectors_config=models.VectorParams(size=d0, distance=models.Distance.COSINE))
+        c0 = v0._coll("c0")
+        c0.vectors, c0.n = db0, n0
+        c0.ids.append([f"{i:032x}" for i in range(n0)], assume_new=True)
+        c0.payloads.append_or_set(np.arange(n0), [{"filename": f"f{i}.jpg"} for i in range(n0)])
+        q0_pin = q0.cpu().pin_memory()
+        e2e0_ms, e2e0_out = time_local(lambda: v0.search_batch("c0", q0_pin, k0, 0.0))
+        q0_list = q0[0].cpu().numpy().tolist()
+        t0 = time.perf_counter()
+        for _ in range(200):
+            hits0 = v0.search("c0", q0_list, limit=k0, score_threshold=0.0)      # exactly core_system.py:659-664
+        api_ms = (time.perf_counter() - t0) / 200 * 1e3
+        from oracle import reverso_oracle as O
+        dbf0 = ops.untile_rows(db0, n0, d0).float().cpu().numpy()
+        rid, rsc = O.search(dbf0, q0[0].cpu().numpy(), k0, 0.0, db_is_normalized=True)
+        ok0 = bool(len(hits0) == len(rid) and [h.id for h in hits0] == [f"{i:032x}" for i in rid.tolist()]
+                   and np.max(np.abs(np.array([h.score for h in hits0]) - rsc)) <= 1e-3)
+        cpu0 = None
+        if not args.no_cpu_baseline:
+            tq = []
+            O.search(dbf0, q0[0].cpu().numpy(), k0, 0.0, db_is_normalized=True)
+            for _ in range(50):
+                t_ = time.perf_counter()
+                O.search(dbf0, q0[0].cpu().numpy(), k0, 0.0, db_is_normalized=True)
+                tq.append(time.perf_counter() - t_)
+            cpu0 = {"value": 1.0 / statistics.median(tq), "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": "full size: 10k x 1024 fp32 DB, one numpy gemv + full argsort per query, median of 50 (same process as "
+                              "torch: BLAS threads shared)"}
+        cfg0 = {"workload": WORKLOADS["cfg0"][4] + " — what core_system.search_similar issues (core_system.py:657-664)",
+                "value": 1e3 / res_ms, "unit": "queries/s", "ms_per_query": res_ms, "gpu_launches_per_query": 2,
+                "e2e": {"value": 1e3 / e2e0_ms, "unit": "queries/s", "ms_per_query": e2e0_ms, "h2d_bytes_per_step": d0 * 4,
+                        "d2h_bytes_per_step": k0 * 12 + 4, "api": "B200VectorDB.search_batch(pinned host query)"},
+                "api_search": {"ms_per_query": api_ms, "api": "B200VectorDB.search(collection, python list, limit, score_threshold) -> "
+                               "ScoredPoints with uuid + payload: the qdrant call core_system.py:659-664 makes, host clock"},
+                "verify": {"checker": "oracle/reverso_oracle.py on the downloaded DB", "ok": ok0}, "cpu_baseline": cpu0}
+        del db0, v0, c0
         torch.cuda.empty_cache()
 
     # ---- cpu baseline (rank 0, N=1): the oracle port in a numpy-only subprocess, bounded sample ----------
@@ -442,14 +680,17 @@ def run_b200(args):
             "config": {"workload": desc, "rows": n, "dim": d, "queries": nq, "k": k, "rows_per_gpu": n_local,
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU", "exchange": exchange,
                        "l2": f"inputs larger than L2: each step streams the {alg_bytes / 1e9:.2f} GB shard",
-                       "path": "small-q fp32 scan" if small else "tcgen05 scan + fused threshold select + fp32 rescore"},
+                       "path": "fp32 CUDA-core scan (Q <= 4)" if small else "tcgen05 scan + fused threshold select (hot lists) + fp32 rescore"},
             "e2e": {"value": nq / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "same_result_as_resident_step": e2e_same,
                     "api": "B200VectorDB.search_batch(pinned host tensor) -> numpy ids/scores/counts" if world == 1 else "ShardedIndex.search(pinned host queries, out=pinned host results): K2 + exchange + K3"},
             "gpu_launches": int(launches), "local_shard_ms_per_step": local_ms,
             "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_hbm": roofline_hbm,
-            "north_star": north, "mask_pool": pool, "cpu_baseline": cpu, "clocks": clocks,
-            "results_ok": counts_ok,
+            "verify": check, "verify_oracle": oracle_check,
+            "north_star": north, "north_star_strong": strong, "mask_pool": pool, "selfjoin": selfjoin, "cfg0": cfg0,
+            "cpu_baseline": cpu, "clocks": clocks,
+            "sass": "profiles/r02_sass_excerpt.txt (cuobjdump -sass of the shipped .so: UTCHMMA / LDTM / UTMALDG per kernel)",
+            "results_ok": bool(counts_ok and (check is None or check["ok"]) and e2e_same and (oracle_check is None or oracle_check["ok"])),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -469,7 +710,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "push", "nccl"],
                     help="N > 1: per-shard lists exchanged by the fused peer-memory push (default when available) or NCCL")
-    ap.add_argument("--no-north-star", action="store_true", help="skip the 12.5M x 1280 rows/GPU north-star series")
+    ap.add_argument("--no-north-star", action="store_true",
+                    help="primary workload only: skip the north-star series, K1, the self-join and configs[0]")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaled 100M x 1280 point (N = 2, 4)")
+    ap.add_argument("--no-selfjoin", action="store_true", help="skip configs[4] (2M x 1024 self-join)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -97,5 +97,28 @@ def make_maskpool_inputs(B: int, M: int, grid: int, D: int, seed: int = 11, devi
     return feats, torch.from_numpy(masks.reshape(B, M, P)).to(dev)
 
 
+def make_selfjoin_db(n: int, d: int, dup_frac: float, device, seed: int = 0, cluster: int = 0) -> torch.Tensor:
+    """configs[4] input: random unit rows with `dup_frac` of them replaced by near copies (cos ~0.93..0.999) of earlier rows
+    (video keyframes of slowly changing scenes); `cluster` > 0 additionally makes that many rows exact copies of row 0 (a static
+    scene: far more near-duplicates of one frame than a candidate list holds).  Tiled bf16 storage."""
+    from . import ops
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.randn((n, d), generator=g, device=dev)
+    x = x / x.norm(dim=1, keepdim=True)
+    nd = int(n * dup_frac)
+    src = torch.randint(0, n // 2, (nd,), generator=g, device=dev)
+    dst = n // 2 + torch.randperm(n - n // 2, generator=g, device=dev)[:nd]
+    a = torch.empty(nd, device=dev).uniform_(0.93, 0.999, generator=g).view(-1, 1)
+    noise = torch.randn((nd, d), generator=g, device=dev)
+    noise = noise - (noise * x[src]).sum(1, keepdim=True) * x[src]
+    noise = noise / noise.norm(dim=1, keepdim=True)
+    x[dst] = a * x[src] + torch.sqrt(1 - a * a) * noise
+    if cluster > 0:
+        rows = torch.randperm(n - 1, generator=g, device=dev)[:cluster] + 1
+        x[rows] = x[0].clone()
+    return ops.tile_rows(x.to(torch.bfloat16))
+
+
 def bf16_to_f32_numpy(t: torch.Tensor) -> np.ndarray:
     return t.detach().float().cpu().numpy()

@@ -15,21 +15,9 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _make(n, d, dup_frac, dev, seed=0):
-    """Random unit rows with `dup_frac` of them replaced by near copies (cos ~0.95..0.999) of earlier rows."""
-    from revers_o_b200 import ops
-    g = torch.Generator(device=dev).manual_seed(seed)
-    x = torch.randn((n, d), generator=g, device=dev)
-    x = x / x.norm(dim=1, keepdim=True)
-    nd = int(n * dup_frac)
-    src = torch.randint(0, n // 2, (nd,), generator=g, device=dev)
-    dst = n // 2 + torch.randperm(n - n // 2, generator=g, device=dev)[:nd]
-    a = torch.empty(nd, device=dev).uniform_(0.93, 0.999, generator=g).view(-1, 1)
-    noise = torch.randn((nd, d), generator=g, device=dev)
-    noise = noise - (noise * x[src]).sum(1, keepdim=True) * x[src]
-    noise = noise / noise.norm(dim=1, keepdim=True)
-    x[dst] = a * x[src] + torch.sqrt(1 - a * a) * noise
-    return ops.tile_rows(x.to(torch.bfloat16))
+def _make(n, d, dup_frac, dev, seed=0, cluster=0):
+    from revers_o_b200 import synth
+    return synth.make_selfjoin_db(n, d, dup_frac, dev, seed=seed, cluster=cluster)
 
 
 @pytest.mark.parametrize("n,d,lo,hi", [(6000, 256, 0, 6000), (9000, 1024, 0, 9000), (9000, 1024, 2000, 5000)])
@@ -53,3 +41,51 @@ def test_selfjoin_matches_oracle(dev, n, d, lo, hi):
     for key in set(got) & set(ref):
         assert abs(got[key] - ref[key]) <= 1e-3
     assert len(set(got) & set(ref)) >= 0.99 * len(ref)
+
+
+def test_selfjoin_with_a_static_scene_falls_back_exactly(dev):
+    """200k frames, 3000 of them exact copies of frame 0 (a static scene) — each of those rows has more
+    near-duplicates than a (deliberately small) candidate list holds, so the fixed-capacity join reports an overflow;
+    `ops.selfjoin_exact` / `B200VectorDB.find_near_duplicates` re-join with larger lists instead of failing.  Checked against an
+    fp32 restatement: the 3001-clique contributes exactly 3001*3000/2 pairs, every other pair matches the brute-force count of a
+    row sample."""
+    from revers_o_b200 import ops
+    n, d, thr, cl = 200_000, 256, 0.95, 3000
+    db = _make(n, d, 0.02, dev, seed=9, cluster=cl)
+    # with 64 candidates per sub-list (cand_cap 1024) the 3001-clique overflows: the fixed-capacity join says so ...
+    from revers_o_b200 import _lib
+    lib = _lib.load()
+    pairs = torch.empty((1 << 23, 2), dtype=torch.int64, device=dev)
+    scores = torch.empty((1 << 23,), dtype=torch.float32, device=dev)
+    count = torch.zeros((1,), dtype=torch.int64, device=dev)
+    over = torch.zeros((1,), dtype=torch.int32, device=dev)
+    nb = lib.rvo_selfjoin_workspace_bytes_ex(d, 1024)
+    ws = ops.workspace(dev, nb)
+    _lib.check(lib.rvo_selfjoin_threshold_ex(db.data_ptr(), n, d, ops.d_pad_of(d), 0, n, thr, 0, 1024, pairs.data_ptr(),
+                                             scores.data_ptr(), 1 << 23, count.data_ptr(), over.data_ptr(), ws.data_ptr(), nb,
+                                             torch.cuda.current_stream(dev).cuda_stream), "selfjoin_ex")
+    torch.cuda.synchronize()
+    assert int(over.item()) > 0 and int(count.item()) < (cl + 1) * cl // 2
+    # ... and the exact wrapper re-joins with larger lists (and a larger pair buffer) instead of failing
+    p, s = ops.selfjoin_exact(db, n, d, thr, max_pairs=1 << 20, cand_cap=1024)
+    p2, s2 = ops.selfjoin_exact(db, n, d, thr)                    # default capacity: the same pairs
+    assert set(map(tuple, p.tolist())) == set(map(tuple, p2.tolist()))
+    assert len(p) == len(set(map(tuple, p.tolist()))) and np.all(p[:, 0] < p[:, 1]) and np.all(s >= thr - 1e-6)
+    rows = ops.untile_rows(db, n, d).float()
+    clique = (rows @ rows[0] > 0.9999).nonzero().flatten()
+    assert clique.numel() == cl + 1
+    cset = set(clique.tolist())
+    in_clique = sum(1 for a, b in p.tolist() if a in cset and b in cset)
+    assert in_clique == (cl + 1) * cl // 2
+    # every pair of a sample of query rows, brute force in fp32 on the GPU
+    rs = np.random.RandomState(0)
+    sample = np.concatenate([rs.randint(0, n, 300), clique[:5].cpu().numpy()])
+    by_row = {}
+    for a, b in p.tolist():
+        by_row.setdefault(a, set()).add(b)
+    for i in sample.tolist():
+        sc = rows[i + 1:] @ rows[i]
+        want = set((torch.nonzero(sc >= thr).flatten() + i + 1).tolist())
+        near = set((torch.nonzero((sc - thr).abs() <= 1e-3).flatten() + i + 1).tolist())
+        got = by_row.get(i, set())
+        assert (got ^ want) <= near, (i, len(got), len(want))
