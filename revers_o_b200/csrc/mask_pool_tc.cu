@@ -46,6 +46,8 @@ struct PoolTcParams {
     long long db_row0;
     int* out_src;
     int B, M, P, D, lim, n_pad, num_pc, num_slab, num_stages;
+    int G;                 // region groups per image: work item w = image * G + group covers regions [group*n_pad, +n_pad)
+                           // (G > 1 when all D/128 slabs of all regions do not fit the 512 TMEM columns, e.g. D = 1280 x 64 regions)
     uint32_t off_b, b_buf_bytes, off_misc;
     uint32_t one_mul;      // 0x80 * one_mul = the 16-bit pattern of 1.0 in the feature dtype: 127 (bf16 0x3F80), 120 (fp16 0x3C00)
     uint32_t f16;          // features (and therefore the converted masks) are fp16 instead of bf16
@@ -160,7 +162,8 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
         // ===================== TMA producer: features, each element exactly once =====================
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
-            for (int b = blockIdx.x; b < p.B; b += gridDim.x)
+            for (int w = blockIdx.x; w < p.B * p.G; w += gridDim.x) {
+                const int b = w / p.G;
                 for (int h = 0; h <= last_half; ++h) {
                     const int s0 = h * spp, s1 = s0 + spp;
                     for (int pc = 0; pc < num_pc; ++pc)
@@ -173,6 +176,7 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
                             if (++stage == kPtStages) { stage = 0; phase ^= 1; }
                         }
                 }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -182,7 +186,8 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
             const uint32_t idesc = (make_idesc_bf16(128, (uint32_t)n_pad) & (p.f16 ? ~((1u << 7) | (1u << 10)) : ~0u)) | (1u << 15);
             uint32_t stage = 0, phase = 0, it = 0;
             const uint32_t sB0 = smem_u32(s_b);
-            for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
+            for (int w = blockIdx.x; w < p.B * p.G; w += gridDim.x, ++it) {
+                const int b = w / p.G;
                 for (int h = 0; h <= last_half; ++h) {
                     const int s0 = h * spp, s1 = s0 + spp;
                     mbar_wait(&bar_tempty[h], (it & 1u) ^ 1u);        // this half of the previous image drained from TMEM
@@ -282,7 +287,8 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
             }
         }
         uint32_t it = 0;
-        for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
+        for (int w = blockIdx.x; w < p.B * p.G; w += gridDim.x, ++it) {
+            const int b = w / p.G, m_base = (w - b * p.G) * n_pad;
             const uint32_t buf = it & 1u;
             const float* invarea = s_invarea + buf * 64;
             const int* outrow = s_outrow + buf * 64;
@@ -410,7 +416,7 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
             }
             if (p.out_src && warp == 2)
                 for (int m = lane; m < n_pad; m += 32)
-                    if (outrow[m] >= 0) p.out_src[outrow[m]] = b * p.M + m;
+                    if (outrow[m] >= 0) p.out_src[outrow[m]] = b * p.M + m_base + m;
             if (threadIdx.x == 64) trace_stamp(p, b, 6);
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_mfree[buf]);
@@ -421,13 +427,14 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
         const size_t img_bytes = (size_t)p.M * p.P;
         const bool vec = (p.P & 7) == 0 && (((uintptr_t)p.masks) & 7) == 0;   // one 8-byte load per 8-patch chunk
         // the 8-patch chunks of one 64-patch tile: n_pad rows x 8 chunks, thread t takes chunks t, t + 64, ...
-        auto load_tile = [&](int b, int pc, unsigned long long (&r)[8]) {
+        auto load_tile = [&](int w, int pc, unsigned long long (&r)[8]) {
+            const int b = w / p.G, m_base = (w - b * p.G) * n_pad;
             const uint8_t* src = p.masks + (size_t)b * img_bytes;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int idx = t + kPtCvtThreads * j, m = idx >> 3, p0 = pc * 64 + (idx & 7) * 8;
+                const int idx = t + kPtCvtThreads * j, m = m_base + (idx >> 3), p0 = pc * 64 + (idx & 7) * 8;
                 unsigned long long bytes = 0ull;
-                if (m < p.M && m < p.lim && p0 < p.P) {
+                if ((idx >> 3) < n_pad && m < p.M && m < p.lim && p0 < p.P) {
                     const uint8_t* row = src + (size_t)m * p.P;
                     if (vec) {
                         bytes = __ldg((const unsigned long long*)(row + p0));
@@ -441,16 +448,17 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
             }
         };
         unsigned long long cur[8], nxt[8];
-        if ((int)blockIdx.x < p.B) load_tile(blockIdx.x, 0, cur);
+        if ((int)blockIdx.x < p.B * p.G) load_tile(blockIdx.x, 0, cur);
         int img_base = 0, prefix_from = 0;   // warp 10: kept regions of the images before `prefix_from`
         uint32_t it = 0;
-        for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
+        for (int w = blockIdx.x; w < p.B * p.G; w += gridDim.x, ++it) {
+            const int b = w / p.G, m_base = (w - b * p.G) * n_pad;
             const uint32_t buf = it & 1u;
             for (int pc = 0; pc < num_pc; ++pc) {
                 // prefetch the next tile's mask bytes, then wait for this tile's smem to be released
                 const bool more = pc + 1 < num_pc;
-                const int nb = more ? b : b + (int)gridDim.x;
-                if (nb < p.B) load_tile(nb, more ? pc + 1 : 0, nxt);
+                const int nw = more ? w : w + (int)gridDim.x;
+                if (nw < p.B * p.G) load_tile(nw, more ? pc + 1 : 0, nxt);
                 mbar_wait(&bar_bfree[pc], (it & 1u) ^ 1u);          // previous image's MMAs no longer read tile pc
                 if (t == 0 && pc == 0) trace_stamp(p, b, 7);
                 uint8_t* tile = s_b + (size_t)pc * b_tile_bytes;
@@ -493,13 +501,20 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_f, const PoolTcPara
                     prefix_from = b;
                     const int base = img_base;
                     if (b == p.B - 1 && lane == 0) *p.out_total = img_base + __ldcg(p.counts + b);
+                    // non-empty regions of the image BEFORE this work item's group, then the group's own rows (all 64 slots
+                    // of the small arrays are rewritten: slots beyond the group or beyond M are marked empty)
                     int run = 0;
-                    for (int m0 = 0; m0 < 64; m0 += 32) {
+                    for (int m0 = 0; m0 < m_base; m0 += 32) {
                         const int m = m0 + lane;
-                        const int a = (m < p.M && m < p.lim) ? __ldcg(p.area + (size_t)b * p.M + m) : 0;
+                        const int a = (m < m_base && m < p.M && m < p.lim) ? __ldcg(p.area + (size_t)b * p.M + m) : 0;
+                        run += __popc(__ballot_sync(0xFFFFFFFFu, a > 0));
+                    }
+                    for (int ml0 = 0; ml0 < 64; ml0 += 32) {
+                        const int ml = ml0 + lane, m = m_base + ml;
+                        const int a = (ml < n_pad && m < p.M && m < p.lim) ? __ldcg(p.area + (size_t)b * p.M + m) : 0;
                         const unsigned bal = __ballot_sync(0xFFFFFFFFu, a > 0);
-                        s_outrow[buf * 64 + m] = a > 0 ? base + run + __popc(bal & ((1u << lane) - 1u)) : -1;
-                        s_invarea[buf * 64 + m] = a > 0 ? 1.0f / (float)a : 0.f;
+                        s_outrow[buf * 64 + ml] = a > 0 ? base + run + __popc(bal & ((1u << lane) - 1u)) : -1;
+                        s_invarea[buf * 64 + ml] = a > 0 ? 1.0f / (float)a : 0.f;
                         run += __popc(bal);
                     }
                     __syncwarp();
@@ -525,9 +540,16 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int M, int P, int D, int lim, float* out,
                         int32_t* out_counts, int32_t* out_src, int32_t* out_total, int* img_base, int* area,
                         unsigned int* ticket, int sm_count, cudaStream_t stream, uint16_t* db, long long db_row0, int feat_f16) {
-    const int n_pad = (M + 15) / 16 * 16;
+    const int n_full = (M + 15) / 16 * 16;
     const int num_pc = (P + 63) / 64, num_slab = D / 128;
-    if (D % 128 != 0 || n_pad > 64 || num_slab * n_pad > 512) return 1;
+    if (D % 128 != 0 || n_full > 64 || num_slab <= 0) return 1;
+    // all D/128 slabs of a work item's regions live in TMEM (512 columns): when an image's regions do not fit together
+    // (PE-Core-G14: 10 slabs x 64 regions) they are split into groups, one work item each — the feature tiles of the image are
+    // streamed once per group (the second pass mostly hits L2)
+    int n_pad = n_full;
+    if (num_slab * n_pad > 512) n_pad = 512 / num_slab / 16 * 16;
+    if (n_pad < 16) return 1;
+    const int G = (n_full + n_pad - 1) / n_pad;
     if (num_pc > kPtMaxPc) return 1;
     const size_t b_buf = (size_t)num_pc * n_pad * 128;
     const size_t tail = (128 * 2 + 64 + 256) * 4 + (kPtBars + 1) * 8;
@@ -573,6 +595,7 @@ int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int 
     p.out_src = out_src;
     p.B = B; p.M = M; p.P = P; p.D = D; p.lim = lim;
     p.n_pad = n_pad; p.num_pc = num_pc; p.num_slab = num_slab; p.num_stages = stages;
+    p.G = G;
     p.off_b = (uint32_t)off_b;
     p.b_buf_bytes = (uint32_t)b_buf;
     p.off_misc = (uint32_t)off_misc;
@@ -581,12 +604,25 @@ int launch_mask_pool_tc(const uint16_t* feats, const uint8_t* masks, int B, int 
     p.trace = (unsigned long long*)g_pool_trace;
     RVO_CUDA(cudaFuncSetAttribute(mask_pool_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RVO_CUDA(cudaFuncSetAttribute(mask_pool_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = B < sm_count ? B : sm_count;
-    // ONE launch: the grid is persistent with at most one CTA per SM (all co-resident), which the in-kernel rendezvous
-    // on `arrived` relies on; the launcher zeroes the counter on the same stream
+    const int grid = B * G < sm_count ? B * G : sm_count;
+    // ONE launch, COOPERATIVE: the grid is persistent with at most one CTA per SM and the in-kernel rendezvous on `arrived`
+    // needs every CTA resident at once.  The cooperative attribute makes the driver guarantee that (the launch waits for the
+    // SMs, or fails if the grid could never fit) — two pooling calls on different streams can no longer hold half of the SMs
+    // each and wait for one another.  The launcher zeroes the counter on the same stream.
     RVO_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
-    if (db) mask_pool_tc_kernel<true><<<grid, kPtThreads, smem, stream>>>(tm, p);
-    else mask_pool_tc_kernel<false><<<grid, kPtThreads, smem, stream>>>(tm, p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kPtThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (db) RVO_CUDA(cudaLaunchKernelEx(&cfg, mask_pool_tc_kernel<true>, tm, p));
+    else RVO_CUDA(cudaLaunchKernelEx(&cfg, mask_pool_tc_kernel<false>, tm, p));
     RVO_LAUNCHED();
     return RVO_OK;
 }

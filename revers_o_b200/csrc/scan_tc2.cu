@@ -186,6 +186,11 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
             } else {
                 int n = 0;
                 const uint32_t key_row_bits = 0xFFFFFFFFu - (uint32_t)row;
+                // sub-list of a survivor, decided when its queue entry is read back (see scan_tc.cu)
+                auto with_seg = [&](unsigned long long ent) -> unsigned long long {
+                    const int sg = __uint_as_float((uint32_t)(ent >> 32)) >= tauh_s[(int)(ent & 0xFFFFu)] ? hot_seg : seg;
+                    return ent | ((unsigned long long)sg << 16);
+                };
                 auto flush_sync = [&](int from, int cnt) {
                     for (int e = from; e < cnt; e += 4) {
                         int slot_pos[4];
@@ -193,7 +198,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                             if (e + u < cnt) {
-                                ent[u] = s_queue[(e + u) * kEpiThreads + qt];
+                                ent[u] = with_seg(s_queue[(e + u) * kEpiThreads + qt]);
                                 slot_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(ent[u] & 0xFFFFu)) * p.nseg + (int)((ent[u] >> 16) & 0xFFu), 1);
                             }
 #pragma unroll
@@ -229,10 +234,8 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     if (__uint_as_float(v[g][h * 8 + i]) >= tt[i]) {
-                                        const int col = cc * 16 + h * 8 + i;
-                                        const int sg = __uint_as_float(v[g][h * 8 + i]) >= tauh_s[col] ? hot_seg : seg;
                                         s_queue[n * kEpiThreads + qt] = ((unsigned long long)v[g][h * 8 + i] << 32) |
-                                                                        (unsigned)((sg << 16) | col);
+                                                                        (unsigned)(cc * 16 + h * 8 + i);
                                         ++n;
                                     }
                                 }
@@ -256,7 +259,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (u < n) {
-                        pend_ent[u] = s_queue[u * kEpiThreads + qt];
+                        pend_ent[u] = with_seg(s_queue[u * kEpiThreads + qt]);
                         pend_pos[u] = atomicAdd(p.cand_cnt + (q0 + (int)(pend_ent[u] & 0xFFFFu)) * p.nseg + (int)((pend_ent[u] >> 16) & 0xFFu), 1);
                     }
                 pend_n = n < 4 ? n : 4;

@@ -23,10 +23,11 @@ def _ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
 
-def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Per-(device, thread) scratch buffer, grown on demand, 1024-byte aligned (torch allocations are 512-byte
-    aligned, so one KiB of slack is kept and the view is offset)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), threading.get_ident())
+def workspace(device: torch.device, nbytes: int, key=None) -> torch.Tensor:
+    """Per-(device, thread[, key]) scratch buffer, grown on demand, 1024-byte aligned (torch allocations are 512-byte
+    aligned, so one KiB of slack is kept and the view is offset).  Calls that may run CONCURRENTLY on different streams of one
+    thread (pipelined searches) pass a `key` so that they do not share scratch."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), threading.get_ident(), key)
     with _ws_lock:
         buf = _workspaces.get(key)
         if buf is None or buf.numel() < nbytes + 1024:
@@ -106,7 +107,7 @@ def normalize_rows(src: torch.Tensor, dst_bf16: torch.Tensor | None = None, want
     return dst_bf16, f32
 
 
-def mask_pool(feats: torch.Tensor, masks: torch.Tensor, max_regions: int = 0):
+def mask_pool(feats: torch.Tensor, masks: torch.Tensor, max_regions: int = 0, out=None, ws_key=None):
     """K1.  feats bf16 or fp16 [B,P,D], masks uint8 [B,M,P] -> (out f32 [B*M, D] (first `total` rows valid),
     counts int32 [B], src int32 [B*M], total int32 [1]) — all device tensors, no host sync."""
     require_cuda(feats, "feats")
@@ -117,13 +118,13 @@ def mask_pool(feats: torch.Tensor, masks: torch.Tensor, max_regions: int = 0):
     M = masks.shape[1]
     assert masks.shape == (B, M, P)
     dev = feats.device
-    out = torch.empty((B * M, D), dtype=torch.float32, device=dev)
-    counts = torch.empty((B,), dtype=torch.int32, device=dev)
-    src = torch.empty((B * M,), dtype=torch.int32, device=dev)
-    total = torch.empty((1,), dtype=torch.int32, device=dev)
+    if out is None:         # `out`: the four result tensors of a previous call with the same shape, reused (steady-state serving)
+        out = (torch.empty((B * M, D), dtype=torch.float32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
+               torch.empty((B * M,), dtype=torch.int32, device=dev), torch.empty((1,), dtype=torch.int32, device=dev))
+    out, counts, src, total = out
     lib = _lib.load()
     nbytes = lib.rvo_mask_pool_workspace_bytes(B, M, P, D)
-    ws = workspace(dev, nbytes)
+    ws = workspace(dev, nbytes, ws_key)
     check(lib.rvo_mask_pool(_ptr(feats), _feat_dtype(feats), _ptr(masks), B, M, P, D, int(max_regions), _ptr(out), _ptr(counts), _ptr(src),
                             _ptr(total), _ptr(ws), nbytes, _stream(dev)), "rvo_mask_pool")
     return out, counts, src, total
@@ -168,7 +169,7 @@ def mask_pool_to_db(feats: torch.Tensor, masks: torch.Tensor, db: torch.Tensor, 
 
 
 def search_topk(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, k: int,
-                score_threshold: float | None = None, id_offset: int = 0, out=None, path: int = 0):
+                score_threshold: float | None = None, id_offset: int = 0, out=None, path: int = 0, ws_key=None):
     """K2.  db: tiled bf16 DB storage (`db_alloc`) holding >= n_rows normalised rows, queries f32 [nq, d].
     Returns device tensors (ids int64 [nq,k], scores f32 [nq,k], counts int32 [nq]); async on the current stream.
     counts[q] == -1 marks an overflowed query (see `search_topk_exact`).  `path`: _lib.RVO_PATH_* (0 = by batch size)."""
@@ -199,7 +200,7 @@ def search_topk(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, k:
         if len(_ws_bytes) > 256:
             _ws_bytes.clear()
         _ws_bytes[wkey] = nbytes
-    ws = workspace(dev, nbytes)
+    ws = workspace(dev, nbytes, ws_key)
     thr = -math.inf if score_threshold is None else float(score_threshold)
     check(lib.rvo_search_topk_ex(_ptr(db), n_rows, d, d_pad_of(d), _ptr(queries), nq, k, thr, int(id_offset), int(path), _ptr(ids),
                                  _ptr(scores), _ptr(counts), _ptr(ws), nbytes, _stream(dev)), "rvo_search_topk")

@@ -208,6 +208,33 @@ class _Collection:
         return plan
 
 
+class SearchHandle:
+    """A batch in flight (B200VectorDB.search_batch_async).  `result()` waits for it and returns (ids, scores, counts) as numpy
+    arrays; it must be called exactly once (it also releases the collection for writers)."""
+
+    def __init__(self, db, lock, lane, args, q_src):
+        self._db, self._lock, self._lane, self._args, self._q = db, lock, lane, args, q_src
+
+    def result(self):
+        lane = self._lane
+        if lane is None:
+            raise RvoError("result() was already collected")
+        try:
+            lane.done.synchronize()
+            out_i, out_s, out_c = lane.ids_np.copy(), lane.scores_np.copy(), lane.counts_np.copy()
+            if out_c.min() < 0:      # overflow protocol (pathological tie mass): exact fp32 scan of the flagged queries
+                vectors, n, dim, row0, k, thr = self._args
+                bad = np.nonzero(out_c < 0)[0]
+                qbad = lane.q_dev[torch.from_numpy(bad).to(lane.q_dev.device)].contiguous()
+                a, b, cc = ops.search_topk_exact(vectors, n, dim, qbad, k, thr, row0)
+                out_i[bad], out_s[bad], out_c[bad] = a.cpu().numpy(), b.cpu().numpy(), cc.cpu().numpy()
+            return out_i, out_s, out_c
+        finally:
+            lane.busy = None
+            self._lane = None
+            self._lock.__exit__(None, None, None)
+
+
 class B200VectorDB:
     def __init__(self, path: str | None = None, device: str | torch.device | None = None, devices: list | None = None,
                  shard_rows: int = 1 << 22, **_):
@@ -285,6 +312,85 @@ class B200VectorDB:
                 dev, vectors, n, row0 = active[0] if active else (c.shards[0].device, c.shards[0].vectors, 0, 0)
                 return self._search_one(c.dim, dev, vectors, n, row0, queries, k, score_threshold, as_device)
             return self._search_sharded(c.dim, active, queries, k, score_threshold, as_device)
+
+    # ---- pipelined serving: overlap the copies / host work of one batch with the scan of another --------------------------
+    def search_batch_async(self, collection_name: str, queries, limit: int = 10, score_threshold: float | None = None,
+                           depth: int = 2) -> "SearchHandle":
+        """Submit a batch and return at once; `handle.result()` gives what `search_batch` would have returned.  Up to `depth`
+        batches are in flight per calling thread, each on its own CUDA stream with its own scratch and pinned I/O buffers:
+        the host-to-device copy, the threshold-seeding kernels and the device-to-host copy of one batch run under the scan
+        of another (a serving loop calls `h2 = db.search_batch_async(...); r1 = h1.result(); ...`).  Single-device collections;
+        a sharded collection is served by `search_batch` (its shards already run concurrently).  queries: [Q, D] float32 numpy
+        or torch CPU tensor (pinned: no staging copy)."""
+        k = int(limit)
+        if k > RVO_MAX_K:
+            raise RvoError(f"limit={k} above the supported maximum {RVO_MAX_K}")
+        if isinstance(queries, torch.Tensor):
+            if queries.is_cuda:
+                raise RvoError("search_batch_async takes host queries (the pipeline exists to hide their copy)")
+            qh = queries.detach()
+            if qh.dtype != torch.float32 or not qh.is_contiguous() or qh.dim() != 2:
+                qh = qh.to(torch.float32).reshape(-1, qh.shape[-1]).contiguous()
+        else:
+            qa = np.ascontiguousarray(queries, dtype=np.float32)
+            qh = torch.from_numpy(qa.reshape(-1, qa.shape[-1]))
+        lock = self._lock.read()
+        lock.__enter__()                                # released by handle.result(): no upsert rewrites rows under the scan
+        try:
+            c = self._coll(collection_name)
+            active = [s for s in c.shards if s.n > 0]
+            if len(active) > 1:
+                raise RvoError("search_batch_async serves single-device collections; use search_batch for sharded ones")
+            sh = active[0] if active else c.shards[0]
+            self._check_dim(qh.shape[1], c.dim)
+            nq = qh.shape[0]
+            lanes = self._lanes(sh.device, nq, c.dim, k, depth)
+            lane = lanes["ring"][lanes["next"] % depth]
+            lanes["next"] += 1
+            if lane.busy is not None:
+                raise RvoError(f"more than {depth} batches in flight on this thread: collect a result first")
+            lane.stream.wait_stream(torch.cuda.current_stream(sh.device))   # rows upserted on the caller's stream are complete
+            with torch.cuda.stream(lane.stream):
+                src = qh
+                if not qh.is_pinned():
+                    lane.q_stage.copy_(qh)
+                    src = lane.q_stage
+                lane.q_dev.copy_(src, non_blocking=True)
+                ops.search_topk(sh.vectors, sh.n, c.dim, lane.q_dev, k, score_threshold, sh.row0,
+                                out=(lane.ids, lane.scores, lane.counts), ws_key=("lane", id(lane)))
+                lane.res_host.copy_(lane.res_dev, non_blocking=True)
+                lane.done.record(lane.stream)
+            h = SearchHandle(self, lock, lane, (sh.vectors, sh.n, c.dim, sh.row0, k, score_threshold), src)
+            lane.busy = h
+            return h
+        except BaseException:
+            lock.__exit__(None, None, None)
+            raise
+
+    def _lanes(self, dev: torch.device, nq: int, d: int, k: int, depth: int):
+        key = ("lanes", dev.index, nq, d, k, depth, threading.get_ident())
+        L = self._staging.get(key)
+        if L is None:
+            nb_i, nb_s, nb_c = nq * k * 8, nq * k * 4, nq * 4
+            nb = (nb_i + nb_s + nb_c + 7) // 8 * 8
+            ring = []
+            for _ in range(depth):
+                res_dev = torch.empty(nb, dtype=torch.uint8, device=dev)
+                res_host = torch.empty(nb, dtype=torch.uint8).pin_memory()
+                host = res_host.numpy()
+                ring.append(SimpleNamespace(
+                    stream=torch.cuda.Stream(dev), done=torch.cuda.Event(), busy=None,
+                    q_stage=torch.empty((nq, d), dtype=torch.float32).pin_memory(),
+                    q_dev=torch.empty((nq, d), dtype=torch.float32, device=dev), res_dev=res_dev, res_host=res_host,
+                    ids=res_dev[:nb_i].view(torch.int64).view(nq, k),
+                    scores=res_dev[nb_i: nb_i + nb_s].view(torch.float32).view(nq, k),
+                    counts=res_dev[nb_i + nb_s: nb_i + nb_s + nb_c].view(torch.int32),
+                    ids_np=host[:nb_i].view(np.int64).reshape(nq, k),
+                    scores_np=host[nb_i: nb_i + nb_s].view(np.float32).reshape(nq, k),
+                    counts_np=host[nb_i + nb_s: nb_i + nb_s + nb_c].view(np.int32)))
+            L = {"ring": ring, "next": 0}
+            self._staging[key] = L
+        return L
 
     def _check_dim(self, got: int, dim: int) -> None:
         if got != dim:

@@ -199,3 +199,38 @@ def test_search_batch_input_kinds_agree(dev):
     for other in (torch.from_numpy(q), torch.from_numpy(q).pin_memory(), torch.from_numpy(q).to(dev)):
         got = vdb.search_batch("c", other, k)
         assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+
+
+def test_pipelined_search_matches_the_blocking_call(dev):
+    """search_batch_async (two batches in flight on their own streams, scratch and pinned buffers) returns exactly what
+    search_batch returns, keeps writers out until the result is collected, and survives an upsert between batches."""
+    from collections import deque
+    from revers_o_b200.vector_db import B200VectorDB, models
+    rs = np.random.RandomState(4)
+    n, d, nq, k = 40_000, 256, 48, 20
+    vdb = B200VectorDB(device=dev)
+    vdb.recreate_collection("c", vectors_config=models.VectorParams(size=d, distance=models.Distance.COSINE))
+    vdb.upsert_batch("c", list(range(n)), rs.randn(n, d).astype(np.float32))
+    batches = [rs.randn(nq, d).astype(np.float32) for _ in range(7)]
+    want = [vdb.search_batch("c", b, k, 0.05) for b in batches]
+    got, inflight = [], deque()
+    for i, b in enumerate(batches):
+        inflight.append(vdb.search_batch_async("c", torch.from_numpy(b).pin_memory() if i % 2 else b, k, 0.05))
+        if len(inflight) == 2:
+            got.append(inflight.popleft().result())
+    while inflight:
+        got.append(inflight.popleft().result())
+    for w, g in zip(want, got):
+        assert all(np.array_equal(a, b) for a, b in zip(w, g))
+    h1 = vdb.search_batch_async("c", batches[0], k)
+    h2 = vdb.search_batch_async("c", batches[1], k)
+    with pytest.raises(Exception):
+        vdb.search_batch_async("c", batches[2], k)          # depth 2: a third batch needs a result collected first
+    r1, r2 = h1.result(), h2.result()
+    with pytest.raises(Exception):
+        h1.result()
+    # an upsert between batches is seen by the next one (and could not run while a batch was in flight)
+    new = batches[3][0] / np.linalg.norm(batches[3][0])
+    vdb.upsert("c", [models.PointStruct(id=n + 7, vector=new.tolist(), payload=None)])
+    ids, sc, cnt = vdb.search_batch_async("c", batches[3], 1).result()
+    assert ids[0, 0] == n and sc[0, 0] > 0.999

@@ -102,7 +102,8 @@ def test_config2_full_shape(dev):
 
 
 # ---- K1 fused with ingest: embeddings straight into the tiled bf16 DB ------------------------------------------------
-@pytest.mark.parametrize("B,M,grid,D,row0", [(7, 64, 24, 1024, 0), (200, 20, 24, 256, 1000), (3, 50, 16, 1280, 128)])
+@pytest.mark.parametrize("B,M,grid,D,row0", [(7, 64, 24, 1024, 0), (200, 20, 24, 256, 1000), (3, 50, 16, 1280, 128),
+                                             (9, 64, 24, 1280, 256), (5, 64, 24, 2048, 0)])
 def test_mask_pool_to_db_matches_two_step_ingest(dev, B, M, grid, D, row0):
     """rvo_mask_pool_to_db == rvo_mask_pool followed by rvo_normalize_rows into the DB (what qdrant's COSINE upsert of the
     reference does with the region embeddings, core_system.py:608-621): same rows, at most one bf16 ulp apart."""
@@ -178,3 +179,47 @@ def test_fp16_features_are_consumed_natively(dev, path):
     # and they are NOT the bf16-rounded features' embeddings (the cast the round-1 drop-in applied)
     emb_bf16, _, _ = O.mask_pool(feats.to(torch.bfloat16).float().cpu().numpy(), masks.cpu().numpy())
     assert np.max(np.abs(got - emb)) < 0.2 * np.max(np.abs(emb_bf16 - emb))
+
+
+@pytest.mark.parametrize("B,M,grid,D", [(6, 50, 24, 1280), (160, 64, 24, 1280), (4, 64, 24, 2048), (3, 33, 24, 4096)])
+def test_wide_features_stay_on_the_tensor_path(dev, B, M, grid, D):
+    """PE-Core-G14 width (D = 1280) at the reference's region cap (50, core_system.py:363) and at the
+    benchmark's 64 masks — all D/128 slabs of all regions no longer fit the 512 TMEM columns, so an image's regions are split
+    into groups (one work item each).  Same results as the oracle, ONE launch (not the four of the CUDA-core kernels), counts and
+    compaction order across groups intact."""
+    from revers_o_b200 import _lib, ops, synth
+    feats, masks = synth.make_maskpool_inputs(B, M, grid, D, seed=B + M, device=dev, n_empty=3)
+    masks[0, : M // 2] = 0                      # a whole first group empty: later groups' rows still land compacted
+    l0 = _lib.kernel_launch_count()
+    out, counts, src, total = ops.mask_pool(feats, masks, 50 if M == 50 else 0)
+    torch.cuda.synchronize()
+    assert _lib.kernel_launch_count() - l0 == 1
+    sel = list(range(min(B, 6)))
+    emb, rc, rsrc = O.mask_pool(feats[sel].float().cpu().numpy(), masks[sel].cpu().numpy())
+    assert np.array_equal(counts[: len(sel)].cpu().numpy(), rc)
+    t = int(rc.sum())
+    got = out[:t].cpu().numpy()
+    assert np.array_equal(src[:t].cpu().numpy(), rsrc[:, 0] * M + rsrc[:, 1])
+    assert np.max(np.abs(got - emb)) < 1e-5 and np.max(np.abs(got - emb) / np.maximum(np.abs(emb), 1e-3)) < 1e-3
+    tt = int(total.item())
+    assert tt == int(counts.sum().item()) and torch.allclose(out[:tt].norm(dim=1), torch.ones(tt, device=dev), atol=1e-5)
+
+
+def test_two_pooling_calls_on_two_streams_do_not_deadlock(dev):
+    """the grid-wide rendezvous of the pooling kernel is launched cooperatively, so two calls from two Gradio worker
+    threads (their own streams) cannot each hold part of the SMs and wait for the other forever."""
+    from revers_o_b200 import ops, synth
+    feats, masks = synth.make_maskpool_inputs(256, 64, 24, 1024, seed=2, device=dev)
+    ref = ops.mask_pool(feats, masks)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    outs = []
+    for rep in range(6):
+        for st in (s1, s2):
+            with torch.cuda.stream(st):
+                # separate scratch per stream: the workspace is per calling thread, so give each stream its own call chain
+                outs.append(ops.mask_pool(feats, masks, ws_key=id(st)))
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o[1], ref[1]) and int(o[3].item()) == int(ref[3].item())
+        assert torch.allclose(o[0][: int(ref[3].item())], ref[0][: int(ref[3].item())], atol=1e-6)

@@ -72,7 +72,7 @@ def test_selfjoin_with_a_static_scene_falls_back_exactly(dev):
     assert set(map(tuple, p.tolist())) == set(map(tuple, p2.tolist()))
     assert len(p) == len(set(map(tuple, p.tolist()))) and np.all(p[:, 0] < p[:, 1]) and np.all(s >= thr - 1e-6)
     rows = ops.untile_rows(db, n, d).float()
-    clique = (rows @ rows[0] > 0.9999).nonzero().flatten()
+    clique = (rows @ rows[0] > 0.99).nonzero().flatten()     # bf16 rows: self-dot is 1 +- 1e-3
     assert clique.numel() == cl + 1
     cset = set(clique.tolist())
     in_clique = sum(1 for a, b in p.tolist() if a in cset and b in cset)
