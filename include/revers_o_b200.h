@@ -112,8 +112,11 @@ int rvo_mask_pool(const uint16_t* feats, int32_t feat_dtype, const uint8_t* mask
  *             regions land, compacted in (image, region) order, at DB rows db_row0, db_row0 + 1, ...;
  *             capacity needed: db_row0 + B * min(M, max_regions) rows
  *   out_f32   [dev] float32 [B*M, D] optional copy of the embeddings (as rvo_mask_pool's `out`); may be NULL
- * Returns RVO_E_UNSUPPORTED for shapes outside the tensor-core kernel (D % 128 != 0, more than 64 regions
- * per image, D/128 * M_pad > 512, more than 1024 patches): call rvo_mask_pool + rvo_normalize_rows instead.
+ * Returns RVO_E_UNSUPPORTED for shapes outside the tensor-core kernel (D % 128 != 0, D > 4096, more than 64 regions
+ * per image, more than 1024 patches): call rvo_mask_pool + rvo_normalize_rows instead.  When all D/128 channel slabs of an
+ * image's regions do not fit the 512 TMEM columns together (PE-Core-G14: D = 1280 with more than 48 regions) the regions are
+ * processed in groups inside the same single launch.  The launch is COOPERATIVE (its compaction offsets need a grid-wide
+ * rendezvous): concurrent calls on different streams serialise instead of deadlocking.
  * ---------------------------------------------------------------------------------------------- */
 int rvo_mask_pool_to_db(const uint16_t* feats, int32_t feat_dtype, const uint8_t* masks, int32_t B, int32_t M, int32_t P, int32_t D,
                         int32_t max_regions, uint16_t* db, int64_t db_row0, float* out_f32, int32_t* out_counts,

@@ -5,23 +5,30 @@ BASELINE.json `north_star`.  It is the checker for `tests/`, `__graft_entry__.sm
 `cpu_baseline` / `--impl reference` legs of `bench.py`.  Nothing under `revers_o_b200/` may
 import it: the product path is the CUDA library and must fail loudly without it.
 
-PARITY UNPINNED.  The reference (`/root/reference`) ships no tests, fixtures or golden vectors for
-this path, and the search arithmetic lives in an un-vendored, un-pinned third-party
-dependency that is not installed in this image and cannot be fetched (no network):
+PARITY: EMBEDDING HALF PINNED, SEARCH HALF UNPINNED.  The reference (`/root/reference`) ships no tests, fixtures or golden
+vectors for this path.  What pins this module instead:
 
-  * `qdrant-client>=1.3.0` (requirements.txt:39), *local mode* (`QdrantClient(path=...)`),
-    call sites core_system.py:100,521,600-603,621,659-664.  Its published algorithm for a COSINE
-    collection, restated here:  vectors are stored as float32 and L2-normalised at upsert; at search
-    the query is L2-normalised, `scores = vectors @ query` over all live points in float32,
-    candidates are visited in `np.argsort(scores)[::-1]` order (unstable sort => order among equal
-    scores is unspecified), the walk stops at the first `score < score_threshold` (so a score equal
-    to the threshold is KEPT) or after `limit` hits.
-  * `facebookresearch/perception_models` @ unpinned HEAD (setup.sh:230) — the PE encoder.  Out of
-    scope (random-init features per north_star); only the output layouts accepted by
-    core_system.py:345-353 matter and are restated in `global_embedding`.
-
-Parity is therefore anchored on the reference's own call sites (cited per function below) and on
-hand-computable known-answer cases (tests/golden/, tests/test_oracle.py).
+  * Embedding half (`l2_normalize`, `global_embedding`, `binarize_mask`, `extract_embeddings_reference`): checked against
+    OUTPUTS OF THE REFERENCE ITSELF, run in this container — tests/golden/make_reference_trace.py loads the unmodified
+    /root/reference/core_system.py + ui.py (stand-ins only for the third-party packages that are not installed), drives the
+    UI callbacks and records every vector the reference computed and handed to the vector DB; the committed fixtures
+    (tests/golden/reference_trace.{json,npz}) are compared with this restatement to 2e-7
+    (tests/test_reference_source.py::test_oracle_embedding_half_is_pinned_to_reference_outputs), and the generator is re-run
+    against the live reference every round (::test_committed_trace_is_what_the_unmodified_reference_does_today).
+  * Search half (`search`, `QdrantLocalOracle`): UNPINNED.  The arithmetic lives in an un-vendored, un-pinned third-party
+    dependency that is not installed in this image and cannot be fetched (no network, no wheel in /opt/wheelhouse):
+    `qdrant-client>=1.3.0` (requirements.txt:39), *local mode* (`QdrantClient(path=...)`), call sites
+    core_system.py:100,521,600-603,621,659-664.  Its published algorithm for a COSINE collection, restated here:  vectors are
+    stored as float32 and L2-normalised at upsert; at search the query is L2-normalised, `scores = vectors @ query` over all
+    live points in float32, candidates are visited in `np.argsort(scores)[::-1]` order (unstable sort => order among equal
+    scores is unspecified), the walk stops at the first `score < score_threshold` (so a score equal to the threshold is KEPT) or
+    after `limit` hits.  It is anchored on the reference's call sites (recorded argument for argument in the trace above: python
+    lists of floats, limit, score_threshold, what the reference does with `.score` / `.payload`), on hand-computable
+    known-answer cases (tests/golden/golden.npz, tests/test_oracle.py) and on scikit-learn / scipy cross-checks.
+  * `mask_pool` restates the reference's STATED design (main.py:8-9) — the reference does not implement it — and
+    is pinned to the reference only in its degenerate case (all-ones mask == `features.mean(dim=1)`, core_system.py:346).
+  * `facebookresearch/perception_models` @ unpinned HEAD (setup.sh:230) — the PE encoder — is out of scope (random-init features
+    per north_star); only the output layouts accepted by core_system.py:345-353 matter and are restated in `global_embedding`.
 
 numpy only (no torch import: SURVEY.md §6 notes a 40x gemv slowdown when torch is imported first).
 """

@@ -197,7 +197,42 @@ class ShardedIndex:
                 stage[: b1 - b0].numpy()[...] = view[b0:b1]
                 db[b0:b1].copy_(stage[: b1 - b0].view(torch.bfloat16), non_blocking=True)
                 torch.cuda.current_stream(dev).synchronize()      # the staging buffer is reused by the next chunk
-        return cls(db, n_local, dim, row0, group)
+        idx = cls(db, n_local, dim, row0, group)
+        idx.attach_tables(path, collection_name)
+        return idx
+
+    # ---- host-side tables indexed by GLOBAL row ("uuid strings / payloads stay in a host-side table") -----
+    def attach_tables(self, path: str, collection_name: str) -> None:
+        """Map the collection's id column and payload log (vector_db.py on-disk format 2): `<collection>.ids` is memory-mapped
+        (fixed-width records: no parse, pages touched on demand), payloads are parsed per hit.  Every rank maps the same files."""
+        import json
+        import os
+
+        import numpy as np
+
+        from .tables import IdTable, PayloadStore
+        self.ids = self.payloads = None
+        try:
+            with open(os.path.join(path, "meta.json")) as f:
+                m = json.load(f)["collections"][collection_name]
+        except (OSError, KeyError):
+            return
+        n = int(m["n"])
+        if m.get("ids_dtype") and n:
+            arr = np.memmap(os.path.join(path, f"{collection_name}.ids"), dtype=np.dtype(m["ids_dtype"]), mode="r", shape=(n,))
+            self.ids = IdTable.from_array(arr)
+        if "idx_bytes" in m:
+            self.payloads = PayloadStore.open(os.path.join(path, f"{collection_name}.payload.jsonl"),
+                                              os.path.join(path, f"{collection_name}.payload.idx"), n, int(m["idx_bytes"]))
+
+    def hits(self, ids_row, scores_row, count: int) -> list:
+        """One query's merged result as the `ScoredPoint`s core_system.py:671-676 consumes (id, score, payload)."""
+        from .vector_db import ScoredPoint
+        out = []
+        for i, s in zip(ids_row[:count].tolist(), scores_row[:count].tolist()):
+            out.append(ScoredPoint(id=self.ids[i] if getattr(self, "ids", None) is not None else i, version=0, score=float(s),
+                                   payload=self.payloads[i] if getattr(self, "payloads", None) is not None else None))
+        return out
 
     def search_local(self, queries: torch.Tensor, k: int, score_threshold=None):
         return ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset)
@@ -238,6 +273,13 @@ class ShardedIndex:
         return oi, os_, oc
 
     def search_exact(self, queries: torch.Tensor, k: int, score_threshold=None):
+        ids, scores, counts = self._search_exact(queries, k, score_threshold)
+        if bool((counts == -2).any().item()):
+            raise _lib.RvoError("peer exchange timed out (option exchange_timeout_ms): a rank did not publish its lists; "
+                                "re-run with disable_peer_exchange() (NCCL all-gather)")
+        return ids, scores, counts
+
+    def _search_exact(self, queries: torch.Tensor, k: int, score_threshold=None):
         """`search` plus the overflow protocol of rvo_search_topk: queries whose merged count is -1 (more than 2048
         candidates inside the bf16 admission margin on some shard) are re-run on every rank through the exact fp32 scan
         (`ops.search_topk_exact`) and merged again.  Every rank computes the same merged counts, so all ranks take the

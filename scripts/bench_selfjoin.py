@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from revers_o_b200 import ops
 from revers_o_b200.sharded import selfjoin_blocks
-from test_gpu_selfjoin import _make
+from revers_o_b200 import synth
+_make = lambda n, d, f, dev, seed=0: synth.make_selfjoin_db(n, d, f, dev, seed=seed)
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)

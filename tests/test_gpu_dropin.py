@@ -184,6 +184,10 @@ def test_saved_collection_loads_shard_wise(dev, tmp_path):
                                 torch.stack([p[2] for p in parts]), k)
     torch.cuda.synchronize()
     assert torch.equal(mi, fi) and torch.equal(mc, fc) and torch.allclose(ms, fs, atol=1e-6)
+    # the torchrun-side index carries the same id / payload tables (memory-mapped id column, lazily parsed payload log)
+    hits = idx.hits(mi[0].cpu().numpy(), ms[0].cpu().numpy(), int(mc[0]))
+    want = vdb.search("c", q[0].cpu().numpy().tolist(), limit=k)
+    assert [h.id for h in hits] == [h.id for h in want] and hits[0].id.startswith("id") and hits[0].payload == want[0].payload
 
 
 def test_search_batch_input_kinds_agree(dev):
