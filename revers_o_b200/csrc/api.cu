@@ -495,6 +495,7 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
         da.n_rows = n_rows;
         da.pair_stride = sp.pair_stride;
         da.k = k;
+        da.trace = (unsigned long long*)(uintptr_t)opt_select_trace.load();
         fa.rescore = 0;
         fa.margin = nullptr;
         if (!sampled) return launch_dense_topk(da, &fa, nq, stream);

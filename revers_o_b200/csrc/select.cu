@@ -717,7 +717,7 @@ constexpr int kDenseCache = 16;
 constexpr int kDenseMaximaK = 128;
 
 template <bool CACHED, bool FINAL>
-__global__ void __launch_bounds__(kDenseThreads) dense_topk_kernel(const DenseTopkArgs a, const FinalArgs f) {
+__global__ void __launch_bounds__(kDenseThreads, 1) dense_topk_kernel(const DenseTopkArgs a, const FinalArgs f) {
     __shared__ int hist[kSelBins];
     __shared__ unsigned long long sbuf[kDenseSort];
     __shared__ unsigned long long s_red[2 * (kDenseThreads / 32)];
@@ -728,6 +728,14 @@ __global__ void __launch_bounds__(kDenseThreads) dense_topk_kernel(const DenseTo
     grid_launch_dependents();
     const float* src = a.dense + (size_t)q * (size_t)a.dense_ld;
     const long long pstride2 = a.pair_stride * 2;
+    auto stamp = [&](int slot) {
+        if (a.trace && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            a.trace[(size_t)q * 16 + slot] = t;
+        }
+    };
+    stamp(0);
     auto key_of = [&](long long c) -> unsigned long long {
         const long long row = (c >> 1) * pstride2 + (c & 1);
         return row < a.n_rows ? make_key(__ldg(src + c), (uint32_t)row) : 0ull;
@@ -740,45 +748,107 @@ __global__ void __launch_bounds__(kDenseThreads) dense_topk_kernel(const DenseTo
             kc[i] = c < a.n_cols ? key_of(c) : 0ull;
         }
     }
-    auto for_each = [&](auto fn) {
-        if (CACHED) {
-#pragma unroll
-            for (int i = 0; i < kDenseCache; ++i)
-                if (kc[CACHED ? i : 0]) fn(kc[CACHED ? i : 0]);
-        } else {
-            for (long long c0 = tid; c0 < a.n_cols; c0 += 4 * kDenseThreads) {
-                unsigned long long k4[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const long long c = c0 + (long long)u * kDenseThreads;
-                    k4[u] = c < a.n_cols ? key_of(c) : 0ull;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k4[u]) fn(k4[u]);
-            }
-        }
-    };
+    // visit every valid key: from registers (CACHED) or from the L2-resident row, twelve independent loads in flight per thread
+    // (one CTA reads the whole row: without them a pass is pure L2 latency).  A macro, not a lambda: the register array must be
+    // indexed by compile-time constants only or it is demoted to local memory.
+#define RVO_FOR_EACH_KEY(KEY, BODY)                                                              \
+    do {                                                                                         \
+        if (CACHED) {                                                                            \
+            _Pragma("unroll") for (int i_ = 0; i_ < kDenseCache; ++i_) {                         \
+                const unsigned long long KEY = kc[CACHED ? i_ : 0];                              \
+                if (KEY) { BODY; }                                                               \
+            }                                                                                    \
+        } else {                                                                                 \
+            for (long long c0_ = tid; c0_ < a.n_cols; c0_ += 12 * kDenseThreads) {               \
+                unsigned long long k12_[12];                                                     \
+                _Pragma("unroll") for (int u_ = 0; u_ < 12; ++u_) {                              \
+                    const long long c_ = c0_ + (long long)u_ * kDenseThreads;                    \
+                    k12_[u_] = c_ < a.n_cols ? key_of(c_) : 0ull;                                \
+                }                                                                                \
+                _Pragma("unroll") for (int u_ = 0; u_ < 12; ++u_) {                              \
+                    const unsigned long long KEY = k12_[u_];                                     \
+                    if (KEY) { BODY; }                                                           \
+                }                                                                                \
+            }                                                                                    \
+        }                                                                                        \
+    } while (0)
     if (!FINAL && !CACHED && a.k <= kDenseMaximaK) {
         // threshold from a LARGE sample in one pass: the k-th largest of the 1024 per-thread maxima.  The maxima are distinct
         // elements of the sample, so their k-th largest is a lower bound of the sample's k-th largest key (hence of the
         // shard's): a valid filter threshold, ~5 % more survivors than the exact one, without the multi-pass refinement
         unsigned long long best = 0ull;
-        for_each([&](unsigned long long k) { best = k > best ? k : best; });
+        RVO_FOR_EACH_KEY(k, best = k > best ? k : best);
         sbuf[tid] = best;
         __syncthreads();
         sort_desc_u64(sbuf, kDenseThreads);
         if (tid == 0) a.tau_key_out[q] = sbuf[a.k - 1];      // 0 (fewer than k non-empty threads): admit everything
         return;
     }
-    // key range and number of valid keys
+    // ---- fast path: bound from the per-thread maxima ------------------------------------------------------------------
+    // The 1024 per-thread maxima are distinct keys, so the k-th largest of them is a lower bound of the k-th largest key
+    // overall.  One histogram of the MAXIMA only (1024 shared-memory atomics spread over the upper tail — histogramming every
+    // key piles the bulk of the scores onto a few bins and serialises) gives the lower edge of the bin holding it; the keys at
+    // or above that edge (the top-k plus a handful) are compacted and sorted.  Exact; two passes over the keys.
+    {
+        unsigned long long best = 0ull;
+        RVO_FOR_EACH_KEY(k, best = k > best ? k : best);
+        for (int i = tid; i < kSelBins; i += kDenseThreads) hist[i] = 0;
+        if (tid == 0) {
+            s_count = 0;
+            s_nnz = 0;
+        }
+        __syncthreads();
+        // cosine scores of normalised rows and queries lie in [-1.01, 1.01]: a fixed key range, no min/max reduction
+        const unsigned long long lo = (unsigned long long)f32_orderable(-1.01f) << 32;
+        const unsigned long long hi = ((unsigned long long)f32_orderable(1.01f) << 32) | 0xFFFFFFFFull;
+        const int shift = hist_shift(lo, hi);
+        const unsigned have = __ballot_sync(0xFFFFFFFFu, best != 0ull);
+        if (lane == 0 && have) atomicAdd(&s_nnz, __popc(have));
+        if (best) {
+            const unsigned long long b = best <= lo ? 0ull : (best >= hi ? (unsigned long long)(kSelBins - 1) : (best - lo) >> shift);
+            atomicAdd(&hist[(int)b], 1);
+        }
+        __syncthreads();
+        const int nthr = s_nnz;                       // threads that hold at least one key
+        if (warp == 0) {
+            const int need = a.k < nthr ? a.k : nthr;
+            if (need > 0) hist_find(hist, need, lane, s_res);
+            __syncwarp();
+            if (lane == 0) s_lo = (need > 0 && a.k <= nthr && s_res[3] && s_res[0] > 0) ? lo + ((unsigned long long)s_res[0] << shift) : 0ull;
+        }
+        __syncthreads();
+        const unsigned long long T0 = s_lo;           // 0: fewer than k threads hold keys (tiny shard) — keep everything
+        stamp(1);
+        RVO_FOR_EACH_KEY(k, if (k >= T0) {
+            const int at = atomicAdd(&s_count, 1);
+            if (at < kDenseSort) sbuf[at] = k;
+        });
+        __syncthreads();
+        stamp(2);
+        if (s_count <= kDenseSort) {
+            const int C = s_count;
+            const int ns = next_pow2(C > 2 ? C : 2);
+            for (int i = C + tid; i < ns; i += kDenseThreads) sbuf[i] = 0ull;
+            __syncthreads();
+            sort_desc_u64(sbuf, ns);
+            stamp(4);
+            if (FINAL) {
+                if (tid == 0) s_count = 0;
+                __syncthreads();
+                emit_topk(sbuf, C, f, q, &s_count);
+                stamp(5);
+                if (a.trace && tid == 0) a.trace[(size_t)q * 16 + 9] = (unsigned long long)C;
+            } else if (tid == 0) {
+                a.tau_key_out[q] = (a.k - 1) < C ? sbuf[a.k - 1] : 0ull;
+            }
+            return;
+        }
+        __syncthreads();                              // more than kDenseSort keys at or above the edge (tie mass): rigorous path
+    }
+    // ---- rigorous path: key range, then histogram refinement over every key ---------------------------------------------------
     unsigned long long lmin = ~0ull, lmax = 0ull;
     int lcnt = 0;
-    for_each([&](unsigned long long k) {
-        lmin = k < lmin ? k : lmin;
-        lmax = k > lmax ? k : lmax;
-        ++lcnt;
-    });
+    RVO_FOR_EACH_KEY(k, lmin = k < lmin ? k : lmin; lmax = k > lmax ? k : lmax; ++lcnt);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long x = __shfl_xor_sync(0xFFFFFFFFu, lmin, o), y = __shfl_xor_sync(0xFFFFFFFFu, lmax, o);
@@ -809,15 +879,14 @@ __global__ void __launch_bounds__(kDenseThreads) dense_topk_kernel(const DenseTo
     __syncthreads();
     const int nnz = s_nnz;
     const int want = a.k < nnz ? a.k : nnz;
+    stamp(1);     // keys loaded, range known
     for (int round = 0; round < 16 && !s_done; ++round) {
         const unsigned long long lo = s_lo, hi = s_hi;
         const int shift = hist_shift(lo, hi);
         __syncthreads();
         for (int i = tid; i < kSelBins; i += kDenseThreads) hist[i] = 0;
         __syncthreads();
-        for_each([&](unsigned long long k) {
-            if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
-        });
+        RVO_FOR_EACH_KEY(k, if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1));
         __syncthreads();
         if (warp == 0) {
             hist_find(hist, want - s_above, lane, s_res);
@@ -841,28 +910,32 @@ __global__ void __launch_bounds__(kDenseThreads) dense_topk_kernel(const DenseTo
         __syncthreads();
     }
     const unsigned long long T = s_lo;
+    stamp(2);     // bound found
     if (tid == 0) s_count = 0;
     __syncthreads();
-    for_each([&](unsigned long long k) {
-        if (k >= T) {
-            const int at = atomicAdd(&s_count, 1);
-            if (at < kDenseSort) sbuf[at] = k;
-        }
+    RVO_FOR_EACH_KEY(k, if (k >= T) {
+        const int at = atomicAdd(&s_count, 1);
+        if (at < kDenseSort) sbuf[at] = k;
     });
     __syncthreads();
+    stamp(3);     // compacted
     const int C = s_count < kDenseSort ? s_count : kDenseSort;
     const int ns = next_pow2(C > 2 ? C : 2);
     for (int i = C + tid; i < ns; i += kDenseThreads) sbuf[i] = 0ull;
     __syncthreads();
     sort_desc_u64(sbuf, ns);
+    stamp(4);     // sorted
     if (FINAL) {
         if (tid == 0) s_count = 0;
         __syncthreads();
         emit_topk(sbuf, C, f, q, &s_count);
+        stamp(5);
+        if (a.trace && tid == 0) a.trace[(size_t)q * 16 + 9] = (unsigned long long)C;
     } else if (tid == 0) {
         a.tau_key_out[q] = (a.k - 1) < C ? sbuf[a.k - 1] : 0ull;
     }
 }
+#undef RVO_FOR_EACH_KEY
 
 int launch_dense_topk(const DenseTopkArgs& a, const FinalArgs* f, int nq, cudaStream_t stream) {
     FinalArgs ff;

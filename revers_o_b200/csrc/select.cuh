@@ -14,6 +14,7 @@ struct DenseTopkArgs {
     long long n_rows, pair_stride;      // column c is DB row (c >> 1) * 2 * pair_stride + (c & 1); valid iff < n_rows
     int k;
     unsigned long long* tau_key_out;    // threshold mode: k-th best ordering key of the sample per query
+    unsigned long long* trace;          // option "select_trace": [nq][16] globaltimer stamps of the kernel's phases (debug)
 };
 
 constexpr int kSelBins = 2048;    // histogram bins per refinement round

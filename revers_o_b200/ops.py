@@ -207,6 +207,45 @@ def search_topk(db: torch.Tensor, n_rows: int, d: int, queries: torch.Tensor, k:
     return ids, scores, counts
 
 
+class PreparedSearch:
+    """`search_topk` with everything but the launch resolved once: argument checks, workspace size and buffer, output tensors and
+    the ctypes argument tuple.  Calling it costs one ctypes call plus the current-stream lookup — what a serving loop that repeats
+    the same shape (the UI's Q = 1, a batch job's Q = 256) pays per search instead of ~15 us of Python bookkeeping.  The tensors
+    it was built from must stay alive and unchanged in address (it holds references)."""
+
+    def __init__(self, db, n_rows, d, queries, k, score_threshold=None, id_offset=0, out=None, path=0, ws_key=None):
+        require_cuda(db, "db")
+        assert db.dtype == torch.bfloat16 and db.dim() == 4 and db.is_contiguous() and db.shape[2:] == (TILE_ROWS, TILE_COLS)
+        assert queries.dtype == torch.float32 and queries.dim() == 2 and queries.is_contiguous()
+        assert queries.is_cuda or queries.is_pinned()
+        nq = queries.shape[0]
+        assert queries.shape[1] == d and n_rows <= db_capacity(db) and db.shape[1] * TILE_COLS == d_pad_of(d)
+        if not (1 <= k <= RVO_MAX_K):
+            raise RvoError(f"k={k} outside 1..{RVO_MAX_K}")
+        self.dev = db.device
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.int64, device=self.dev), torch.empty((nq, k), dtype=torch.float32, device=self.dev),
+                   torch.empty((nq,), dtype=torch.int32, device=self.dev))
+        self.out = out
+        self.lib = _lib.load()
+        nbytes = self.lib.rvo_search_workspace_bytes_ex(n_rows, d, nq, k, path)
+        if nbytes == 0:
+            raise RvoError(f"rvo_search_workspace_bytes rejected n_rows={n_rows} d={d} nq={nq} k={k} path={path}: "
+                           + self.lib.rvo_last_error().decode())
+        self._keep = (db, queries, workspace(self.dev, nbytes, ws_key))
+        thr = -math.inf if score_threshold is None else float(score_threshold)
+        self.args = (_ptr(db), n_rows, d, d_pad_of(d), _ptr(queries), nq, k, thr, int(id_offset), int(path), _ptr(out[0]),
+                     _ptr(out[1]), _ptr(out[2]), _ptr(self._keep[2]), nbytes)
+        self.epoch = _lib.option_epoch
+        self._fn = self.lib.rvo_search_topk_ex
+
+    def __call__(self):
+        rc = self._fn(*self.args, torch.cuda.current_stream(self.dev).cuda_stream)
+        if rc:
+            check(rc, "rvo_search_topk")
+        return self.out
+
+
 def search_topk_exact(db, n_rows, d, queries, k, score_threshold=None, id_offset=0):
     """`search_topk` plus the documented overflow protocol: queries flagged -1 by the fused path are re-run in batches of
     <= RVO_SMALL_Q through the exact fp32 scan, and — should its survivor lists overflow as well (adversarial row order) —

@@ -439,7 +439,16 @@ class B200VectorDB:
         # RVO_ZC_OUT=1 the last kernel stores straight into the pinned host blob (and with RVO_ZC_IN=1 the first kernel reads
         # the queries from pinned host memory): measured equal within noise on one GPU and 30-40 us per step WORSE with two
         # processes on one box, so the copies stay the default
-        ops.search_topk(vectors, n, dim, qd, k, score_threshold, row0, out=(io.ids, io.scores, io.counts))
+        if qd is io.q_dev:
+            # the steady state of a serving loop: same shape, same DB, same threshold -> a prepared call (one ctypes call)
+            key = (vectors.data_ptr(), n, row0, score_threshold, _lib.option_epoch)
+            if io.prepared_key != key:
+                io.prepared = ops.PreparedSearch(vectors, n, dim, io.q_dev, k, score_threshold, row0,
+                                                 out=(io.ids, io.scores, io.counts))
+                io.prepared_key = key
+            io.prepared()
+        else:
+            ops.search_topk(vectors, n, dim, qd, k, score_threshold, row0, out=(io.ids, io.scores, io.counts))
         if io.res_dev is not io.res_host:
             io.res_host.copy_(io.res_dev, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
@@ -539,10 +548,14 @@ class B200VectorDB:
             nb = (nb_i + nb_s + nb_c + 7) // 8 * 8
             q_stage = torch.empty((nq, d), dtype=torch.float32).pin_memory()
             res_host = torch.empty(nb, dtype=torch.uint8).pin_memory()     # device-addressable (UVA): kernels write into it
-            res_dev = res_host if os.environ.get("RVO_ZC_OUT", "0") == "1" else torch.empty(nb, dtype=torch.uint8, device=dev)
+            # a small result blob (the UI's Q = 1: 124 bytes) is written by the last kernel straight into the pinned host blob:
+            # one copy launch less per search; larger blobs go through a device blob + one D2H copy (measured no worse)
+            zc_out = os.environ.get("RVO_ZC_OUT", "auto")
+            zero_copy = zc_out == "1" or (zc_out == "auto" and nb <= 16384)
+            res_dev = res_host if zero_copy else torch.empty(nb, dtype=torch.uint8, device=dev)
             host = res_host.numpy()
             io = SimpleNamespace(
-                q_stage=q_stage, q_stage_np=q_stage.numpy(),
+                q_stage=q_stage, q_stage_np=q_stage.numpy(), prepared=None, prepared_key=None,
                 q_dev=torch.empty((nq, d), dtype=torch.float32, device=dev),
                 res_dev=res_dev, res_host=res_host,
                 ids=res_dev[:nb_i].view(torch.int64).view(nq, k),
