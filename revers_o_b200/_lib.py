@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librevers_o_b200.so")
+LIB_PATH = os.environ.get("RVO_LIB_PATH") or os.path.join(_HERE, "lib", "librevers_o_b200.so")   # override: A/B builds only
 
 RVO_E_UNSUPPORTED = -5
 RVO_MAX_K = 512
