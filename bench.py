@@ -377,9 +377,35 @@ def run_b200(args):
             args.exchange != "nccl" and index.enable_peer_exchange(nq, k)) else "NCCL all_gather_into_tensor"
     sampler = ClockSampler(local)
     sampler.start()
-    ms_step, launches, out = timed(lambda: index.search(q_dev, k), args.steps, max(3, args.warmup))
+    ms_serial, launches, out_serial = timed(lambda: index.search(q_dev, k), args.steps, max(3, args.warmup))
+    serial_check = verify(index, q_dev, out_serial, k)
+    out_serial = tuple(t.clone() for t in out_serial)
+
+    # The same K steps through the pipelined public API (ShardedIndex.submit / collect, two batches in flight): the scan of step
+    # i+1 is enqueued before the exchange + merge of step i, so a rank scans while it waits for the slowest peer's lists; on one
+    # GPU the two batches run on two streams.  This is `value`; the synchronous call is reported next to it as `serial`.
+    def pipe_block(steps):
+        prev, res = None, None
+        for _ in range(steps):
+            t = index.submit(q_dev, k)
+            if prev is not None:
+                res = index.collect(prev)
+            prev = t
+        return index.collect(prev)
+
+    pipe_block(max(3, args.warmup))
+    barrier()
+    l0 = _lib.kernel_launch_count()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    pe0.record()
+    out = pipe_block(args.steps)
+    pe1.record()
+    barrier()
+    ms_step = max_over_ranks(pe0.elapsed_time(pe1)) / args.steps
+    launches = _lib.kernel_launch_count() - l0
     value = nq / (ms_step / 1e3)
-    counts_ok = bool((out[2] == k).all().item())
+    counts_ok = bool((out[2] == k).all().item()) and bool(torch.equal(out[0], out_serial[0]) and torch.equal(out[2], out_serial[2]))
     check = verify(index, q_dev, out, k)
 
     # N > 1: the same step without the exchange + merge (K2 on the local shard only), to show what the exchange costs
@@ -712,10 +738,14 @@ def run_b200(args):
         line = {
             "metric": "exact top-%d cosine queries/s" % k, "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "serial": {"value": nq / (ms_serial / 1e3), "unit": "queries/s", "ms_per_step": ms_serial,
+                       "api": "ShardedIndex.search (synchronous: every step ends with its own exchange + merge)",
+                       "verify_ok": None if serial_check is None else serial_check["ok"]},
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": desc, "rows": n, "dim": d, "queries": nq, "k": k, "rows_per_gpu": n_local,
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU", "exchange": exchange,
                        "l2": f"inputs larger than L2: each step streams the {alg_bytes / 1e9:.2f} GB shard",
+                       "pipeline_depth": 2, "api": "ShardedIndex.submit / collect (two batches in flight; `serial` = ShardedIndex.search)",
                        "path": "fp32 CUDA-core scan (Q <= 4)" if small else "tcgen05 scan + fused threshold select (hot lists) + fp32 rescore"},
             "e2e": {"value": nq / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "same_result_as_resident_step": e2e_same, "pipelined": pipe,

@@ -40,6 +40,9 @@ PROTOTYPES = {
     "rvo_search_topk_push": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                        C.c_int64, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
                                        C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rvo_search_topk_fused": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
+                                        C.c_int64, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rvo_merge_topk_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rvo_search_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),

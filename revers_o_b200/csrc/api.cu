@@ -13,6 +13,7 @@ namespace rvo {
 
 extern bool g_force_cuda_core_pool;
 extern std::atomic<long long> g_exchange_timeout_ms;
+extern std::atomic<long long> g_merge_trace;
 extern void* g_pool_trace;
 static std::atomic<long long> opt_select_trace{0};
 size_t selfjoin_workspace_bytes(int d, long long cand_cap);
@@ -315,6 +316,7 @@ int rvo_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "time_scan")) opt_time_scan = value;
     else if (!strcmp(name, "hot")) opt_hot = value;
     else if (!strcmp(name, "exchange_timeout_ms")) g_exchange_timeout_ms = value > 0 ? value : 1;
+    else if (!strcmp(name, "merge_trace")) g_merge_trace = value;
     else if (!strcmp(name, "pool_path")) g_force_cuda_core_pool = value == 1;
     else if (!strcmp(name, "pdl")) g_use_pdl = value;
     else if (!strcmp(name, "select_trace")) opt_select_trace = value;
@@ -625,17 +627,28 @@ int rvo_search_topk_ex(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
 }
 
 // ---- peer-memory exchange ------------------------------------------------------------------------------
-// Region of one rank: [2 parities][world slots of slot_bytes] | flags u64 [2][world] | done u32 [2].  Slot g of a parity
-// receives rank g's packed result blob [ids | scores | counts] of one search; flag g its epoch.
+// Region of one rank: [4 slot sets][world slots of slot_bytes] | flags u64 [4][world] | done u32 [4].  Slot g of set (epoch % 4)
+// receives rank g's packed result blob [ids | scores | counts] of search `epoch`; flag g its epoch.  FOUR sets let a rank enqueue
+// the scan of search e+1 BEFORE the merge of search e (ShardedIndex.submit / collect): its push of search e+4 reuses set e % 4 only
+// after its own merge of e+2, which waited for every peer's push of e+2, which every peer enqueued after its merge of e.
+constexpr int kExchangeSlots = 4;
+// Behind it, for the FUSED exchange (rvo_search_topk_fused): [4 slot sets][world ranks][nq_max queries] records of rec_bytes
+// ([k ids | k scores | count]) | per-(rank, query) epoch flags u64 [4][world][nq_max].
 struct ExchangeLayout {
     size_t slot_bytes, flags_off, done_off, bytes;
+    size_t rec_bytes, lists_off, lists_set_bytes, qflags_off, qflags_set_bytes;
 };
 static ExchangeLayout exchange_layout(int world, int nq_max, int k_max) {
     ExchangeLayout L;
     L.slot_bytes = align_up(rvo_packed_result_bytes(nq_max, k_max), 256);
-    L.flags_off = 2 * (size_t)world * L.slot_bytes;
-    L.done_off = L.flags_off + 2 * (size_t)world * 8;
-    L.bytes = L.done_off + 64;
+    L.flags_off = kExchangeSlots * (size_t)world * L.slot_bytes;
+    L.done_off = L.flags_off + kExchangeSlots * (size_t)world * 8;
+    L.rec_bytes = align_up((size_t)k_max * 12 + 4, 16);
+    L.lists_off = align_up(L.done_off + 64, 256);
+    L.lists_set_bytes = (size_t)world * nq_max * L.rec_bytes;
+    L.qflags_off = L.lists_off + kExchangeSlots * L.lists_set_bytes;
+    L.qflags_set_bytes = (size_t)world * nq_max * 8;
+    L.bytes = L.qflags_off + kExchangeSlots * L.qflags_set_bytes;
     return L;
 }
 
@@ -691,7 +704,7 @@ int rvo_search_topk_push(const uint16_t* db, int64_t n_rows, int32_t d, int64_t 
     RVO_REQUIRE(nq > 0 && nq <= nq_max && k > 0 && k <= k_max && epoch > 0, "search_topk_push: nq/k beyond the region's maxima");
     for (int g = 0; g < world; ++g) RVO_REQUIRE(regions[g], "search_topk_push: null region %d", g);
     const ExchangeLayout L = exchange_layout(world, nq_max, k_max);
-    const int par = (int)(epoch & 1);
+    const int par = (int)(epoch & (kExchangeSlots - 1));
     PushArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.world = world;
@@ -714,6 +727,40 @@ int rvo_search_topk_push(const uint16_t* db, int64_t n_rows, int32_t d, int64_t 
                        workspace, workspace_bytes, stream, &pa);
 }
 
+int rvo_search_topk_fused(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_pad, const float* queries, int32_t nq,
+                          int32_t k, float score_threshold, int64_t id_offset, void* const* regions, int32_t world,
+                          int32_t rank, int32_t nq_max, int32_t k_max, uint64_t epoch, int64_t* out_ids, float* out_scores,
+                          int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    RVO_REQUIRE(regions && world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world, "search_topk_fused: bad world/rank");
+    RVO_REQUIRE(nq > 0 && nq <= nq_max && k > 0 && k <= k_max && epoch > 0, "search_topk_fused: nq/k beyond the region's maxima");
+    for (int g = 0; g < world; ++g) RVO_REQUIRE(regions[g], "search_topk_fused: null region %d", g);
+    if ((long long)world * k > 2048 || k > 512) {
+        set_error("search_topk_fused: world * k = %lld beyond the in-kernel merge (2048): use rvo_search_topk_push + "
+                  "rvo_merge_topk_exchange", (long long)world * k);
+        return RVO_E_UNSUPPORTED;
+    }
+    const ExchangeLayout L = exchange_layout(world, nq_max, k_max);
+    const int par = (int)(epoch & (kExchangeSlots - 1));
+    PushArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.world = world;
+    pa.rank = rank;
+    pa.nq = nq;
+    pa.k = k;
+    pa.epoch = epoch;
+    pa.fused = 1;
+    pa.nq_max = nq_max;
+    pa.rec_bytes = (unsigned int)L.rec_bytes;
+    pa.timeout_ns = (unsigned long long)g_exchange_timeout_ms.load() * 1000000ull;
+    for (int g = 0; g < world; ++g) {
+        unsigned char* base = (unsigned char*)regions[g];
+        pa.lists[g] = base + L.lists_off + (size_t)par * L.lists_set_bytes;
+        pa.qflags[g] = (unsigned long long*)(base + L.qflags_off + (size_t)par * L.qflags_set_bytes);
+    }
+    return search_impl(db, n_rows, d, d_pad, queries, nq, k, score_threshold, id_offset, out_ids, out_scores, out_counts,
+                       workspace, workspace_bytes, stream, &pa);
+}
+
 int rvo_merge_topk_exchange(const void* local_region, int32_t world, int32_t nq, int32_t k, int32_t nq_max, int32_t k_max,
                             uint64_t epoch, int64_t* out_ids, float* out_scores, int32_t* out_counts, void* stream) {
     DeviceGuard device_guard;
@@ -723,7 +770,7 @@ int rvo_merge_topk_exchange(const void* local_region, int32_t world, int32_t nq,
     int rc = select_device_of(local_region, nullptr);
     if (rc) return rc;
     const ExchangeLayout L = exchange_layout(world, nq_max, k_max);
-    const int par = (int)(epoch & 1);
+    const int par = (int)(epoch & (kExchangeSlots - 1));
     const unsigned char* base = (const unsigned char*)local_region + (size_t)par * world * L.slot_bytes;
     const unsigned long long* flags = (const unsigned long long*)((const unsigned char*)local_region + L.flags_off) + (size_t)par * world;
     return launch_merge((const int64_t*)base, (const float*)(base + (size_t)nq * k * 8), (const int32_t*)(base + (size_t)nq * k * 12),

@@ -151,21 +151,156 @@ __device__ __forceinline__ void push_count(const PushArgs& pa, int q, int count)
 // thread's stores are fenced at system scope before the block barrier; thread 0's counter increment orders after them.
 __device__ __forceinline__ void push_complete(const PushArgs& pa) {
     if (pa.world <= 1) return;
-    __threadfence_system();
+    // the block barrier orders every thread's peer stores before thread 0; thread 0's system-scope fence is cumulative, so
+    // they are visible to the peers before the counter / flag updates that follow (the cooperative-groups grid-sync idiom).
+    // One fence per CTA instead of one per thread: a system-scope fence costs microseconds.
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int prev = atomicAdd(pa.done, 1u);
         if (prev == gridDim.x - 1) {
             __threadfence_system();
             *pa.done = 0u;                     // ready for the next use of this parity (two searches later)
-            for (int g = 0; g < pa.world; ++g) st_release_sys_u64(pa.peer_flag[g], pa.epoch);
+            for (int g = 0; g < pa.world; ++g)      // the fence above orders them; a release per store would fence world times
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(pa.peer_flag[g]), "l"(pa.epoch) : "memory");
         }
     }
 }
 
+constexpr int kFusedMax = 2048;      // world * k the in-kernel merge holds in shared memory
+struct FusedScratch {                // shared memory the in-kernel merge may overwrite once the CTA's own list is in registers
+    long long* sid;                  // [kFusedMax]
+    float* ssc;                      // [kFusedMax]
+    int* scnt;                       // [kMaxPeers + 2]
+};
+
+__device__ __forceinline__ bool list_before(float sa, long long ia, float sb, long long ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+// Fused exchange + merge (PushArgs::fused).  Called by the whole CTA with element `threadIdx.x` of its list in registers
+// (k <= blockDim.x) and the list's count (-1: overflowed).  Record of (source rank r, query q) in rank g's region:
+// lists[g] + (r * nq_max + q) * rec_bytes = [k ids | k scores | count].
+__device__ __forceinline__ void fused_exchange_merge(const FinalArgs& a, int q, long long my_id, float my_sc, int my_count,
+                                                     const FusedScratch& fs) {
+    const PushArgs& pa = a.push;
+    const int tid = threadIdx.x, G = pa.world, k = pa.k;
+    const size_t rec_off = ((size_t)pa.rank * pa.nq_max + q) * pa.rec_bytes;
+    for (int g = 0; g < G; ++g) {
+        unsigned char* rec = pa.lists[g] + rec_off;
+        if (tid < k) {
+            ((long long*)rec)[tid] = my_id;
+            ((float*)(rec + (size_t)k * 8))[tid] = my_sc;
+        }
+        if (tid == 0) *(int*)(rec + (size_t)k * 12) = my_count;
+    }
+    // block barrier, then ONE system-scope fence (cumulative over the CTA's stores), then the per-query flags
+    __syncthreads();
+    if (tid < G) {
+        // lanes 0..G-1 of warp 0: ONE fence instruction for the warp (cumulative over the barrier), then the G flag stores in
+        // parallel as relaxed system-scope stores — `st.release.sys` per flag would pay a system-scope fence for each of them
+        // (measured: +27 us per search at 8 GPUs)
+        __threadfence_system();
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(pa.qflags[tid] + (size_t)pa.rank * pa.nq_max + q), "l"(pa.epoch)
+                     : "memory");
+    }
+    if (tid == 0) {
+        fs.scnt[kMaxPeers] = 0;      // timeout flag
+        fs.scnt[kMaxPeers + 1] = 0;  // bad (overflowed) list seen
+    }
+    __syncthreads();
+    const unsigned long long* myflags = pa.qflags[pa.rank];
+    if (tid < G && tid != pa.rank) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys_u64(myflags + (size_t)tid * pa.nq_max + q) < pa.epoch) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            if (t1 - t0 > pa.timeout_ns) {
+                fs.scnt[kMaxPeers] = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    int64_t* oid = a.out_ids + (size_t)q * (size_t)k;
+    float* osc = a.out_scores + (size_t)q * (size_t)k;
+    if (fs.scnt[kMaxPeers]) {        // a peer never published: report, do not hang or trap (the host raises / falls back)
+        for (int i = tid; i < k; i += blockDim.x) {
+            oid[i] = -1;
+            osc[i] = -__int_as_float(0x7f800000);
+        }
+        if (tid == 0) a.out_counts[q] = -2;
+        return;
+    }
+    const unsigned char* base = pa.lists[pa.rank];
+    if (tid < G) {
+        const int c = __ldcg((const int*)(base + ((size_t)tid * pa.nq_max + q) * pa.rec_bytes + (size_t)k * 12));
+        if (c < 0) fs.scnt[kMaxPeers + 1] = 1;
+        fs.scnt[tid] = c < 0 ? 0 : (c > k ? k : c);
+    }
+    __syncthreads();
+    const int n = G * k;
+    for (int e = tid; e < n; e += blockDim.x) {
+        const int g = e / k, i = e - g * k;
+        if (i < fs.scnt[g]) {
+            const unsigned char* rec = base + ((size_t)g * pa.nq_max + q) * pa.rec_bytes;
+            fs.sid[e] = __ldcg((const long long*)rec + i);
+            fs.ssc[e] = __ldcg((const float*)(rec + (size_t)k * 8) + i);
+        }
+    }
+    __syncthreads();
+    const bool bad = fs.scnt[kMaxPeers + 1] != 0;
+    int total = 0;
+    for (int g = 0; g < G; ++g) total += fs.scnt[g];
+    const int n_out = bad ? 0 : (total < k ? total : k);
+    // every list is sorted by (score desc, id asc) and ids are unique: the merged position of an element is its own index plus,
+    // for every other list, the number of that list's elements ranked before it (one binary search each)
+    for (int e = tid; e < n; e += blockDim.x) {
+        const int g = e / k, i = e - g * k;
+        if (i >= fs.scnt[g] || bad) continue;
+        const float sc = fs.ssc[e];
+        const long long id = fs.sid[e];
+        int pos = i;
+        for (int h = 0; h < G && pos < k; ++h) {
+            if (h == g) continue;
+            int lo = 0, hi = fs.scnt[h];
+            const float* hs = fs.ssc + h * k;
+            const long long* hid = fs.sid + h * k;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (list_before(hs[mid], hid[mid], sc, id)) lo = mid + 1;
+                else hi = mid;
+            }
+            pos += lo;
+        }
+        if (pos < k) {
+            oid[pos] = id;
+            osc[pos] = sc;
+        }
+    }
+    for (int i = n_out + tid; i < k; i += blockDim.x) {
+        oid[i] = -1;
+        osc[i] = -__int_as_float(0x7f800000);
+    }
+    if (tid == 0) a.out_counts[q] = bad ? -1 : n_out;
+}
+
 // emit: first k keys of the sorted list with score >= score_threshold (the reference's walk stops at the first score
 // below it; `score == threshold` is kept).  s_n must be 0 on entry; whole block.
-__device__ __forceinline__ void emit_topk(const unsigned long long* s, int n_sorted, const FinalArgs& a, int q, int* s_n) {
+__device__ __forceinline__ void emit_topk(const unsigned long long* s, int n_sorted, const FinalArgs& a, int q, int* s_n,
+                                          const FusedScratch* fs = nullptr) {
+    if (a.push.fused && fs) {
+        // the shard's list goes straight into the exchange records; the caller's outputs receive the MERGED list
+        const int i = threadIdx.x;
+        const unsigned long long key = (i < a.k && i < n_sorted) ? s[i] : 0ull;
+        const bool ok = key != 0ull && key_score(key) >= a.score_threshold;
+        const long long id = ok ? (long long)key_row(key) + a.id_offset : -1;
+        const float sc = ok ? key_score(key) : -__int_as_float(0x7f800000);
+        const int cnt = __syncthreads_count(ok);
+        fused_exchange_merge(a, q, id, sc, cnt, *fs);
+        return;
+    }
     int64_t* oid = a.out_ids + (size_t)q * (size_t)a.k;
     float* osc = a.out_scores + (size_t)q * (size_t)a.k;
     int n_out_local = 0;
@@ -188,7 +323,12 @@ __device__ __forceinline__ void emit_topk(const unsigned long long* s, int n_sor
     push_complete(a.push);
 }
 
-__device__ __forceinline__ void emit_overflow(const FinalArgs& a, int q) {
+__device__ __forceinline__ void emit_overflow(const FinalArgs& a, int q, const FusedScratch* fs = nullptr) {
+    if (a.push.fused && fs) {
+        __syncthreads();
+        fused_exchange_merge(a, q, -1, -__int_as_float(0x7f800000), -1, *fs);
+        return;
+    }
     int64_t* oid = a.out_ids + (size_t)q * (size_t)a.k;
     float* osc = a.out_scores + (size_t)q * (size_t)a.k;
     for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
@@ -367,7 +507,7 @@ constexpr int kHotQMax = 2048;             // query dimensions kept in shared me
 // cover the query — a hot sub-list overflowed, fewer than k hot keys, more than kHotActMax candidates inside the margin — and
 // the caller takes the general path over ALL sub-lists.
 __device__ __forceinline__ bool select_hot(const SelectArgs& a, const FinalArgs& f, int q, int* hist, unsigned long long* sbuf,
-                                           float* s_q, int* s_res, int* s_count) {
+                                           float* s_q, int* s_res, int* s_count, const FusedScratch* fs) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int base[kHotSplit + 1];
     base[0] = 0;
@@ -446,7 +586,7 @@ __device__ __forceinline__ bool select_hot(const SelectArgs& a, const FinalArgs&
     if (tid == 0) *s_count = 0;
     __syncthreads();
     sel_stamp(a, q, 7);
-    emit_topk(sbuf, n_act < f.k ? n_act : f.k, f, q, s_count);
+    emit_topk(sbuf, n_act < f.k ? n_act : f.k, f, q, s_count, fs);
     sel_stamp(a, q, 8);
     if (a.trace && tid == 0) {
         a.trace[(size_t)q * 16 + 9] = (unsigned long long)n_hot;
@@ -486,11 +626,16 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
         if (c > a.cap) s_over = 1;   // a sub-list dropped candidates
     }
     __syncthreads();
+    FusedScratch fs_;
+    fs_.sid = (long long*)sbuf;          // the in-kernel merge of the fused exchange reuses the selection's shared memory
+    fs_.ssc = (float*)hist;
+    fs_.scnt = s_cnt;
+    const FusedScratch* fs = (FINAL && f.push.fused) ? &fs_ : nullptr;
     if constexpr (FINAL) {
-        if (!a.dense && a.hot_nseg > 0 && select_hot(a, f, q, hist, sbuf, s_q, s_res, &s_count)) return;
+        if (!a.dense && a.hot_nseg > 0 && select_hot(a, f, q, hist, sbuf, s_q, s_res, &s_count, fs)) return;
         __syncthreads();
         if (s_over) {
-            emit_overflow(f, q);
+            emit_overflow(f, q, fs);
             return;
         }
     }
@@ -633,7 +778,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
             // keys carry exact fp32 scores already (small-Q path): the sorted prefix IS the answer
             if (tid == 0) s_count = 0;
             __syncthreads();
-            emit_topk(sbuf, C, f, q, &s_count);
+            emit_topk(sbuf, C, f, q, &s_count, fs);
             return;
         }
         // ---- fused last level: every candidate that can still reach the top-k after the fp32 re-score is one whose
@@ -648,7 +793,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
         if (!covered) {
             compact(Kc);                                  // a superset of the k best: the cut stays valid
             if (s_count > kSelSort) {                     // more than kSelSort candidates inside the margin
-                emit_overflow(f, q);
+                emit_overflow(f, q, fs);
                 return;
             }
             C = s_count;
@@ -674,7 +819,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_kernel(const SelectArgs
         sel_stamp(a, q, 6);       // re-scored
         sort_desc_u64(sbuf, ns2);
         sel_stamp(a, q, 7);       // second sort done
-        emit_topk(sbuf, ns2, f, q, &s_count);
+        emit_topk(sbuf, ns2, f, q, &s_count, fs);
         sel_stamp(a, q, 8);
         if (a.trace && tid == 0) { a.trace[(size_t)q * 16 + 9] = (unsigned long long)C; a.trace[(size_t)q * 16 + 10] = (unsigned long long)n_act; a.trace[(size_t)q * 16 + 11] = (unsigned long long)nnz; }
         return;
@@ -1047,6 +1192,7 @@ int launch_select_final(const SelectArgs& a, const FinalArgs& f, int nq, cudaStr
 // ---- K3: merge of per-shard lists -------------------------------------------------------------
 constexpr int kMaxMergeLists = 64;
 std::atomic<long long> g_exchange_timeout_ms{60000};   // option "exchange_timeout_ms"
+std::atomic<long long> g_merge_trace{0};               // option "merge_trace": device buffer [3] u64 (start, flags seen, end)
 __device__ __forceinline__ bool before(float sa, long long ia, float sb, long long ib) {
     return sa > sb || (sa == sb && ia < ib);
 }
@@ -1060,9 +1206,10 @@ __global__ void __launch_bounds__(256) merge_kernel(const int64_t* ids, const fl
                                                     int G, int k, int64_t* out_ids,
                                                     float* out_scores, int32_t* out_counts,
                                                     const unsigned long long* wait_flags, unsigned long long wait_epoch,
-                                                    unsigned long long wait_timeout_ns) {
+                                                    unsigned long long wait_timeout_ns, unsigned long long* tr) {
     extern __shared__ unsigned char sm[];
     __shared__ int s_timeout;
+    if (tr && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr[0]));
     if (wait_flags) {
         // peer-memory exchange: rank g's push of this search has landed in the local region once its flag shows the epoch
         // A late peer (host-side GC, lazy module load, ingest) only delays this rank, as a collective would.  After
@@ -1083,6 +1230,7 @@ __global__ void __launch_bounds__(256) merge_kernel(const int64_t* ids, const fl
             }
         }
         __syncthreads();
+        if (tr && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr[1]));
         if (s_timeout) {
             for (int i = threadIdx.x; i < k; i += blockDim.x) {
                 out_ids[(size_t)blockIdx.x * k + i] = -1;
@@ -1145,6 +1293,7 @@ __global__ void __launch_bounds__(256) merge_kernel(const int64_t* ids, const fl
         out_scores[(size_t)q * k + i] = -__int_as_float(0x7f800000);
     }
     if (threadIdx.x == 0) out_counts[q] = s_bad ? -1 : n_out;
+    if (tr && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr[2]));
 }
 
 // ---- host wrappers ------------------------------------------------------------------------------
@@ -1160,7 +1309,8 @@ int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts,
         RVO_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_kernel<<<nq, 256, smem, stream>>>(ids, scores, counts, ids_gs, scores_gs, counts_gs, G, k, out_ids, out_scores,
                                             out_counts, wait_flags, wait_epoch,
-                                            (unsigned long long)g_exchange_timeout_ms.load() * 1000000ull);
+                                            (unsigned long long)g_exchange_timeout_ms.load() * 1000000ull,
+                                            (unsigned long long*)(uintptr_t)g_merge_trace.load());
     RVO_LAUNCHED();
     return RVO_OK;
 }

@@ -58,6 +58,15 @@ struct PushArgs {
     unsigned char* peer_slot[kMaxPeers];       // this rank's slot (current parity) in peer g's region; [rank] unused
     unsigned long long* peer_flag[kMaxPeers];  // this rank's flag (current parity) in peer g's region; [rank] = local
     unsigned int* done;                        // local CTA counter of the current parity (zero between uses)
+    // fused exchange + merge (rvo_search_topk_fused): the CTA of query q stores its list as ONE record into every rank's region,
+    // publishes a per-(rank, query) flag, waits for the peers' flags of the SAME query and merges the `world` lists itself —
+    // no grid-wide counter, no separate merge launch.
+    int fused;
+    int nq_max;
+    unsigned int rec_bytes;                    // bytes of one (rank, query) record: [k ids int64 | k scores f32 | count i32], 16-aligned
+    unsigned char* lists[kMaxPeers];           // record area of the current slot set in rank g's region ([g] == rank: local)
+    unsigned long long* qflags[kMaxPeers];     // per-(source rank, query) epoch flags of the current slot set in rank g's region
+    unsigned long long timeout_ns;
 };
 
 struct FinalArgs {

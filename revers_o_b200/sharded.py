@@ -88,6 +88,7 @@ class ShardedIndex:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self._bufs: dict = {}
+        self._pipe = None          # submit / collect state
         self._xchg = None          # peer-memory exchange state (enable_peer_exchange)
 
     # ---- peer-memory exchange: K2's last kernel pushes the result into every peer's region over NVLink ----------------
@@ -135,6 +136,10 @@ class ShardedIndex:
         self._xchg = {"region": region, "peers": peers, "table": table, "nq_max": int(nq_max), "k_max": int(k_max), "epoch": 0}
         return True
 
+    def _use_fused(self, k: int) -> bool:
+        import os
+        return self.world * k <= 2048 and os.environ.get("RVO_FUSED", "1") != "0"
+
     def disable_peer_exchange(self) -> None:
         """Collective.  Unmaps the peers' regions and frees the local one (after every rank has stopped using them)."""
         if self._xchg is None:
@@ -166,6 +171,15 @@ class ShardedIndex:
         ws = ops.workspace(dev, nbytes)
         thr = -math.inf if score_threshold is None else float(score_threshold)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if self._use_fused(k):
+            # exchange AND merge inside the last search kernel: the outputs are the merged lists, no second launch
+            oi, os_, oc = out if out is not None else (b["oi"], b["os"], b["oc"])
+            check(lib.rvo_search_topk_fused(self.db.data_ptr(), self.n_local, self.d, ops.d_pad_of(self.d), queries.data_ptr(), nq, k,
+                                            thr, self.id_offset, x["table"], self.world, self.rank, x["nq_max"], x["k_max"], epoch,
+                                            oi.data_ptr(), os_.data_ptr(), oc.data_ptr(), ws.data_ptr(), nbytes, stream),
+                  "rvo_search_topk_fused")
+            x["epoch"] = epoch
+            return oi, os_, oc
         check(lib.rvo_search_topk_push(self.db.data_ptr(), self.n_local, self.d, ops.d_pad_of(self.d), queries.data_ptr(), nq, k,
                                        thr, self.id_offset, x["table"], self.world, self.rank, x["nq_max"], x["k_max"],
                                        epoch, ws.data_ptr(), nbytes, stream), "rvo_search_topk_push")
@@ -271,6 +285,101 @@ class ShardedIndex:
                                                 oi.data_ptr(), os_.data_ptr(), oc.data_ptr(),
                                                 torch.cuda.current_stream(dev).cuda_stream), "rvo_merge_topk_packed")
         return oi, os_, oc
+
+    # ---- pipelined serving: the scan of batch i+1 is enqueued BEFORE the exchange + merge of batch i ---------------------------
+    def submit(self, queries: torch.Tensor, k: int, score_threshold=None):
+        """Enqueue K2 of one batch (and, with the peer exchange, its push) and return a ticket for `collect`.  At most TWO
+        tickets may be outstanding; every rank of the group must submit / collect in the same order.  A serving loop calls
+        `t1 = submit(q1); t2 = submit(q2); r1 = collect(t1); t3 = submit(q3); r2 = collect(t2); ...`: while a rank waits for
+        the slowest peer's lists of batch i it is already scanning batch i+1 (the synchronous `search` makes every step as slow
+        as the slowest rank plus the rendezvous).  One GPU: the two batches run on two streams with their own scratch, so the
+        threshold-seeding kernels and the select of one batch fill the ramp and tail of the other's scan."""
+        import math
+        nq = queries.shape[0]
+        dev = self.db.device
+        lib = _lib.load()
+        p = self._pipe
+        if p is None or p["key"] != (nq, k):
+            p = self._pipe = {"key": (nq, k), "n": 0, "out": [None, None], "pending": [],
+                              "streams": [torch.cuda.Stream(dev), torch.cuda.Stream(dev)] if self.world == 1 else None,
+                              "events": [torch.cuda.Event(), torch.cuda.Event()]}
+            nb = packed_bytes(nq, k)
+            for j in range(2):
+                p["out"][j] = {"oi": torch.empty((nq, k), dtype=torch.int64, device=dev),
+                               "os": torch.empty((nq, k), dtype=torch.float32, device=dev),
+                               "oc": torch.empty((nq,), dtype=torch.int32, device=dev),
+                               "blob": torch.zeros(nb, dtype=torch.uint8, device=dev),
+                               "gathered": torch.empty((self.world, nb), dtype=torch.uint8, device=dev) if self.world > 1 else None}
+        if len(p["pending"]) >= 2:
+            raise _lib.RvoError("two batches are already in flight: collect one first")
+        j = p["n"] & 1
+        p["n"] += 1
+        o = p["out"][j]
+        thr = -math.inf if score_threshold is None else float(score_threshold)
+        x = self._xchg
+        ticket = {"j": j, "nq": nq, "k": k, "mode": "local", "epoch": 0}
+        if self.world == 1:
+            st = p["streams"][j]
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st):
+                ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset,
+                                out=(o["oi"], o["os"], o["oc"]), ws_key=("pipe", id(self), j))
+                p["events"][j].record(st)
+        elif x is not None and _lib.RVO_SMALL_Q < nq <= x["nq_max"] and k <= x["k_max"] and self._use_fused(k):
+            # the fused exchange has no separate merge to defer: the whole search is one chain of launches
+            epoch = x["epoch"] + 1
+            nbytes = lib.rvo_search_workspace_bytes(self.n_local, self.d, nq, k)
+            ws = ops.workspace(dev, nbytes)
+            check(lib.rvo_search_topk_fused(self.db.data_ptr(), self.n_local, self.d, ops.d_pad_of(self.d), queries.data_ptr(), nq, k,
+                                            thr, self.id_offset, x["table"], self.world, self.rank, x["nq_max"], x["k_max"], epoch,
+                                            o["oi"].data_ptr(), o["os"].data_ptr(), o["oc"].data_ptr(), ws.data_ptr(), nbytes,
+                                            torch.cuda.current_stream(dev).cuda_stream), "rvo_search_topk_fused")
+            x["epoch"] = epoch
+            ticket.update(mode="fused", epoch=epoch)
+        elif x is not None and _lib.RVO_SMALL_Q < nq <= x["nq_max"] and k <= x["k_max"]:
+            epoch = x["epoch"] + 1
+            nbytes = lib.rvo_search_workspace_bytes(self.n_local, self.d, nq, k)
+            ws = ops.workspace(dev, nbytes)
+            check(lib.rvo_search_topk_push(self.db.data_ptr(), self.n_local, self.d, ops.d_pad_of(self.d), queries.data_ptr(), nq, k,
+                                           thr, self.id_offset, x["table"], self.world, self.rank, x["nq_max"], x["k_max"], epoch,
+                                           ws.data_ptr(), nbytes, torch.cuda.current_stream(dev).cuda_stream), "rvo_search_topk_push")
+            x["epoch"] = epoch
+            ticket.update(mode="push", epoch=epoch)
+        else:
+            blob = o["blob"]
+            views = (blob[: nq * k * 8].view(torch.int64).view(nq, k), blob[nq * k * 8: nq * k * 12].view(torch.float32).view(nq, k),
+                     blob[nq * k * 12: nq * k * 12 + nq * 4].view(torch.int32))
+            ops.search_topk(self.db, self.n_local, self.d, queries, k, score_threshold, self.id_offset, out=views)
+            ticket.update(mode="nccl")
+        p["pending"].append(ticket)
+        return ticket
+
+    def collect(self, ticket):
+        """Exchange + merge of a submitted batch (tickets in submission order).  Returns (ids, scores, counts): views of buffers
+        that are reused two submissions later."""
+        p = self._pipe
+        if not p or not p["pending"] or p["pending"][0] is not ticket:
+            raise _lib.RvoError("collect() takes the oldest outstanding ticket")
+        p["pending"].pop(0)
+        o = p["out"][ticket["j"]]
+        dev = self.db.device
+        nq, k = ticket["nq"], ticket["k"]
+        lib = _lib.load()
+        if ticket["mode"] == "local":
+            torch.cuda.current_stream(dev).wait_event(p["events"][ticket["j"]])
+        elif ticket["mode"] == "fused":
+            pass
+        elif ticket["mode"] == "push":
+            x = self._xchg
+            check(lib.rvo_merge_topk_exchange(x["region"], self.world, nq, k, x["nq_max"], x["k_max"], ticket["epoch"],
+                                              o["oi"].data_ptr(), o["os"].data_ptr(), o["oc"].data_ptr(),
+                                              torch.cuda.current_stream(dev).cuda_stream), "rvo_merge_topk_exchange")
+        else:
+            dist.all_gather_into_tensor(o["gathered"].view(-1), o["blob"], group=self.group)
+            check(lib.rvo_merge_topk_packed(o["gathered"].data_ptr(), o["gathered"].stride(0), self.world, nq, k,
+                                            o["oi"].data_ptr(), o["os"].data_ptr(), o["oc"].data_ptr(),
+                                            torch.cuda.current_stream(dev).cuda_stream), "rvo_merge_topk_packed")
+        return o["oi"], o["os"], o["oc"]
 
     def search_exact(self, queries: torch.Tensor, k: int, score_threshold=None):
         ids, scores, counts = self._search_exact(queries, k, score_threshold)

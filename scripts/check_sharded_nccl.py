@@ -36,6 +36,16 @@ def main():
         # the same search through the peer-memory exchange (NVLink stores fused into K2's last kernel) must agree bit for bit,
         # repeatedly (both slot parities, reuse of the flags)
         pushed = idx.enable_peer_exchange(nq_max=max(nq, 8), k_max=k)
+        if pushed and nq > 4:
+            # the separate-merge protocol (push + rvo_merge_topk_exchange) must agree with the fused one used by default
+            os.environ["RVO_FUSED"] = "0"
+            ui, us, uc = (t.clone() for t in idx.search(q, k, thr))
+            os.environ["RVO_FUSED"] = "1"
+            fi_, fs_, fc_ = (t.clone() for t in idx.search(q, k, thr))
+            torch.cuda.synchronize()
+            if not (torch.equal(ui, fi_) and torch.equal(us, fs_) and torch.equal(uc, fc_)):
+                ok = False
+                msgs.append("fused exchange != separate merge")
         if pushed:
             for _ in range(5):
                 pi, ps, pc = idx.search(q, k, thr)
@@ -44,6 +54,20 @@ def main():
                 same_push = bool(torch.equal(pc[~bad], cnt[~bad]) and torch.equal(pi[~bad], ids[~bad]) and torch.equal(ps[~bad], sc[~bad]))
                 if not same_push:
                     break
+            # pipelined serving (submit / collect, scan of batch i+1 enqueued before the merge of batch i): nine DIFFERENT query
+            # batches through the four slot sets — a stale or overwritten slot would surface as a wrong list
+            if same_push and nq > 4:
+                variants = [q.roll(j, dims=0).contiguous() for j in range(9)]
+                want = [tuple(t.clone() for t in idx.search(v, k, thr)) for v in variants]
+                got, prev = [], None
+                for v in variants:
+                    t = idx.submit(v, k, thr)
+                    if prev is not None:
+                        got.append(tuple(t_.clone() for t_ in idx.collect(prev)))
+                    prev = t
+                got.append(tuple(t_.clone() for t_ in idx.collect(prev)))
+                torch.cuda.synchronize()
+                same_push = all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) for a, b in zip(want, got))
             idx.disable_peer_exchange()
         else:
             same_push = True

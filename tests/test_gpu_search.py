@@ -478,3 +478,30 @@ def test_small_q_paths_agree_bit_for_bit_and_dense_route_never_overflows(dev):
     assert int(cnt[0]) == k and ids[0].tolist() == list(range(k)) and float(sc[0].min()) > 0.99
     ids, sc, cnt = ops.search_topk_exact(same, n, d, qq, k)
     assert int(cnt[0]) == k and ids[0].tolist() == list(range(k))
+
+
+def test_submit_collect_pipeline_on_one_gpu(dev):
+    """ShardedIndex.submit / collect (two batches in flight on two streams) == the synchronous search, batch by batch."""
+    from revers_o_b200 import synth
+    from revers_o_b200.sharded import ShardedIndex
+    n, d, k = 90_000, 512, 30
+    qs = [synth.make_queries(40, d, seed=60 + i, device=dev) for i in range(5)]
+    db = synth.make_db(n, d, qs[0], n_plant=64, seed=61, device=dev)
+    idx = ShardedIndex(db, n, d, 1000)
+    want = [tuple(t.clone() for t in idx.search(q, k, 0.1)) for q in qs]
+    got, prev = [], None
+    for q in qs:
+        t = idx.submit(q, k, 0.1)
+        if prev is not None:
+            got.append(tuple(x.clone() for x in idx.collect(prev)))
+        prev = t
+    got.append(tuple(x.clone() for x in idx.collect(prev)))
+    torch.cuda.synchronize()
+    for w, g in zip(want, got):
+        assert torch.equal(w[0], g[0]) and torch.equal(w[1], g[1]) and torch.equal(w[2], g[2])
+    a, b = idx.submit(qs[0], k), idx.submit(qs[1], k)
+    with pytest.raises(Exception):
+        idx.submit(qs[2], k)
+    with pytest.raises(Exception):
+        idx.collect(b)                      # tickets come back in submission order
+    idx.collect(a), idx.collect(b)
