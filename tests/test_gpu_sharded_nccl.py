@@ -1,6 +1,8 @@
-"""Real multi-GPU parity (NCCL, world_size 2): row-sharded K2 + ONE all-gather + K3 == unsharded search == CPU oracle;
-self-join pair counts add up across ranks.  Needs two GPUs on the box (skipped otherwise); the single-GPU
-virtual-shard version of the same check is tests/test_gpu_search.py::test_virtual_shards_merge."""
+"""Real multi-GPU parity (world_size 2, scripts/check_sharded_nccl.py under torchrun): row-sharded K2 + ONE NCCL all-gather + K3 ==
+the peer-memory push with a separate merge == the FUSED exchange (merge inside K2's last kernel) == pipelined submit / collect ==
+unsharded search == CPU oracle; self-join pair counts add up across ranks.  Needs two GPUs on the box (skipped otherwise); the
+single-GPU virtual-shard versions are tests/test_gpu_search.py::test_id_offset_and_virtual_shards_merge and
+tests/test_gpu_multidevice.py (one-process sharded collection)."""
 import os
 import socket
 import subprocess
