@@ -86,6 +86,7 @@ class _RWLock:
     def __init__(self):
         self._cond = threading.Condition(threading.Lock())
         self._readers = 0
+        self._by_thread: dict = {}   # reader holds per thread: a thread that still holds one must not ask for the write side
         self._writer = None      # owning thread id (re-entrant for the writer)
         self._depth = 0
 
@@ -100,6 +101,7 @@ class _RWLock:
                 while self._writer is not None:
                     self._cond.wait()
                 self._readers += 1
+                self._by_thread[me] = self._by_thread.get(me, 0) + 1
                 mode = "r"
         try:
             yield
@@ -109,6 +111,11 @@ class _RWLock:
                     self._depth -= 1
                 else:
                     self._readers -= 1
+                    left = self._by_thread.get(me, 1) - 1
+                    if left:
+                        self._by_thread[me] = left
+                    else:
+                        self._by_thread.pop(me, None)
                     if self._readers == 0:
                         self._cond.notify_all()
 
@@ -119,6 +126,9 @@ class _RWLock:
             if self._writer == me:
                 self._depth += 1
             else:
+                if self._by_thread.get(me):
+                    # e.g. an upsert between search_batch_async() and result() on the same thread: it would wait for itself
+                    raise RvoError("this thread still has searches in flight on the database: collect their results before writing")
                 while self._writer is not None or self._readers > 0:
                     self._cond.wait()
                 self._writer, self._depth = me, 1
@@ -233,6 +243,19 @@ class SearchHandle:
             lane.busy = None
             self._lane = None
             self._lock.__exit__(None, None, None)
+
+    def __del__(self):      # a handle dropped without result(): the collection must not stay read-locked
+        if getattr(self, "_lane", None) is not None:
+            try:
+                self._lane.done.synchronize()
+            except Exception:
+                pass
+            self._lane.busy = None
+            self._lane = None
+            try:
+                self._lock.__exit__(None, None, None)
+            except Exception:
+                pass
 
 
 class B200VectorDB:

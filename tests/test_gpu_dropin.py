@@ -233,6 +233,14 @@ def test_pipelined_search_matches_the_blocking_call(dev):
     r1, r2 = h1.result(), h2.result()
     with pytest.raises(Exception):
         h1.result()
+    h3 = vdb.search_batch_async("c", batches[2], k)
+    with pytest.raises(Exception):          # a write while this thread's own search is in flight would wait for itself: refused
+        vdb.upsert("c", [models.PointStruct(id=-5, vector=batches[3][1].tolist(), payload=None)])
+    h3.result()
+    h4 = vdb.search_batch_async("c", batches[2], k)
+    del h4                                  # a dropped handle releases the collection
+    import gc
+    gc.collect()
     # an upsert between batches is seen by the next one (and could not run while a batch was in flight)
     new = batches[3][0] / np.linalg.norm(batches[3][0])
     vdb.upsert("c", [models.PointStruct(id=n + 7, vector=new.tolist(), payload=None)])

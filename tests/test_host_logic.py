@@ -102,3 +102,51 @@ def test_read_shard_blocks_covers_the_file_exactly(tmp_path):
     from revers_o_b200._lib import RvoError
     with pytest.raises(RvoError):
         read_shard_blocks(str(tmp_path), "missing", 2, 0)
+
+
+def test_rw_lock_readers_overlap_writers_exclude_and_self_deadlock_is_refused():
+    """vector_db._RWLock: searches (readers) overlap, upserts (writers) are exclusive and re-entrant, and a thread that still
+    holds a read side (an in-flight search_batch_async) is refused the write side instead of waiting for itself."""
+    import threading
+    import time
+
+    import pytest
+
+    from revers_o_b200._lib import RvoError
+    from revers_o_b200.vector_db import _RWLock
+    lk = _RWLock()
+    inside, peak, log = [0], [0], []
+
+    def reader():
+        with lk.read():
+            inside[0] += 1
+            peak[0] = max(peak[0], inside[0])
+            time.sleep(0.05)
+            inside[0] -= 1
+
+    ts = [threading.Thread(target=reader) for _ in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert peak[0] >= 2                                     # readers ran together
+
+    def writer():
+        with lk.write():
+            with lk.write():                                # re-entrant for the owner
+                with lk.read():                             # the writer may read its own state
+                    log.append(("w", inside[0]))
+                    time.sleep(0.05)
+
+    r = lk.read()
+    r.__enter__()                                           # an outstanding search on THIS thread
+    with pytest.raises(RvoError):
+        with lk.write():
+            pass
+    w = threading.Thread(target=writer)
+    w.start()
+    time.sleep(0.02)
+    assert not log                                          # the writer waits for the reader
+    r.__exit__(None, None, None)
+    w.join()
+    assert log == [("w", 0)]
+    with lk.write():
+        pass
