@@ -32,7 +32,7 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static std::atomic<long long> opt_force_path{0}, opt_m_sub{0}, opt_cand_cap{32768}, opt_final_ratio{48}, opt_time_scan{0}, opt_hot{1};
+static std::atomic<long long> opt_force_path{0}, opt_m_sub{0}, opt_cand_cap{32768}, opt_final_ratio{48}, opt_time_scan{0}, opt_hot{1}, opt_seed_max{1};
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static bool g_ev_valid = false;
 
@@ -315,6 +315,7 @@ int rvo_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "final_ratio")) opt_final_ratio = value;
     else if (!strcmp(name, "time_scan")) opt_time_scan = value;
     else if (!strcmp(name, "hot")) opt_hot = value;
+    else if (!strcmp(name, "seed_max")) opt_seed_max = value;
     else if (!strcmp(name, "exchange_timeout_ms")) g_exchange_timeout_ms = value > 0 ? value : 1;
     else if (!strcmp(name, "merge_trace")) g_merge_trace = value;
     else if (!strcmp(name, "pool_path")) g_force_cuda_core_pool = value == 1;
@@ -541,8 +542,11 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
     sa.tau_k = k;
 
     // level 0: DENSE pass over the seed sample (or the whole shard when it is small)
-    rc = launch_scan_tc(kModeDense, db, n_rows, sp.seed_stride, sp.d_pad, sp.qb, sp.tc, nullptr, nullptr, nullptr, 0,
-                        sp.dense, sp.dense_ld, sm, stream);
+    // When the sample only seeds a threshold through seed_tau_kernel, the scan writes one maximum per 32 sample rows instead of
+    // every score (kModeDenseMax): 32x less to write and to read back, same guarantee.
+    const bool seed_max = sp.n_levels > 0 && k <= kSeedTauMaxK && opt_seed_max.load() != 0;
+    rc = launch_scan_tc(seed_max ? kModeDenseMax : kModeDense, db, n_rows, sp.seed_stride, sp.d_pad, sp.qb, sp.tc, nullptr, nullptr,
+                        nullptr, 0, sp.dense, sp.dense_ld, sm, stream);
     if (rc) return rc;
     sa.dense = sp.dense;
     sa.dense_ld = sp.dense_ld;
@@ -556,7 +560,8 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
     sa.tau_out = sp.tau;
     const bool seed_is_last = sp.n_levels == 1;    // the seed threshold feeds the full scan directly: it also proposes tau_hot
     if (k <= kSeedTauMaxK)   // one pass + one 512-key sort: k-th largest of the per-thread maxima (select.cuh)
-        rc = launch_seed_tau(sp.dense, sp.dense_ld, sp.seed_cols, nq, nq_pad, k, sp.margin, score_threshold, sp.tau, stream,
+        rc = launch_seed_tau(sp.dense, sp.dense_ld, seed_max ? sp.seed_cols / 32 : sp.seed_cols, nq, nq_pad, k, sp.margin,
+                             score_threshold, sp.tau, stream,
                              sp.hot_rank, seed_is_last ? sp.tau_hot : nullptr);
     else {
         sa.hot_rank = sp.hot_rank;
@@ -573,7 +578,7 @@ static int search_impl(const uint16_t* db, int64_t n_rows, int32_t d, int64_t d_
         const float* tau_in = sp.tau + (size_t)L * nq_pad;
         if (last && (rc = scan_timer(true, stream))) return rc;
         rc = launch_scan_tc(kModeFilter, db, n_rows, sp.level_stride[L], sp.d_pad, sp.qb, sp.tc, tau_in, sp.cand, cnt, sp.cap,
-                            nullptr, 0, sm, stream, last && use_hot ? sp.tau_hot : nullptr, kCandSegs);
+                            nullptr, 0, sm, stream, last && use_hot && opt_hot.load() != 2 ? sp.tau_hot : nullptr, kCandSegs);
         if (rc) return rc;
         if (last && (rc = scan_timer(false, stream))) return rc;
         memset(&sa, 0, sizeof(sa));

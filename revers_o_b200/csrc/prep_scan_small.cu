@@ -84,6 +84,88 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
     }
 }
 
+// Register-resident variant for d_pad <= 32 * NV: the row is read ONCE — NV independent loads per lane, all in flight together —
+// and stays in registers for the magnitude, norm, rounding-error and store passes.  The generic kernel above makes four dependent
+// passes over global memory (7 us for a 256 x 1024 query batch; this one is bounded by a single DRAM round trip).  Lane l owns
+// elements l, l + 32, ... and accumulates them in that order, exactly like the generic kernel: both produce the same bits, so
+// a query normalised through either (any alignment, any d) ranks identically.
+template <int NV>
+__global__ void __launch_bounds__(256) normalize_rows_reg_kernel(const float* __restrict__ src, long long n, int d,
+                                                                 long long src_ld, uint16_t* __restrict__ dst_bf16,
+                                                                 long long dst_ld, long long tiled_row0,
+                                                                 float* __restrict__ dst_f32, long long f32_ld,
+                                                                 float* __restrict__ margin_out, long long n_pad_rows,
+                                                                 uint4* __restrict__ zero_base, long long zero_u4) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    float v[NV];
+    const bool live = row < n;
+    if (live) {
+        const float* s = src + (size_t)row * (size_t)src_ld;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = lane + 32 * j < d ? __ldg(s + lane + 32 * j) : 0.f;
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < zero_u4; i += (long long)gridDim.x * blockDim.x)
+        zero_base[i] = make_uint4(0, 0, 0, 0);
+    if (!live) {
+        if (row < n_pad_rows && tiled_row0 < 0) {
+            if (dst_bf16)
+                for (long long i = lane; i < dst_ld; i += 32) dst_bf16[(size_t)row * (size_t)dst_ld + i] = 0;
+            if (dst_f32)
+                for (long long i = lane; i < f32_ld; i += 32) dst_f32[(size_t)row * (size_t)f32_ld + i] = 0.f;
+            if (margin_out && lane == 0) margin_out[row] = 0.f;
+        }
+        return;
+    }
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) amax = fmaxf(amax, fabsf(v[j]));   // padding elements are 0: no effect
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+    const bool rescale = amax > 1e18f || (amax < 1e-18f && amax > 0.f);
+    const float pre = rescale ? 1.0f / amax : 1.0f;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const float x = v[j] * pre;
+        ss = fmaf(x, x, ss);                                          // fma(0, 0, ss) == ss for the padding elements
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    const float nrm = sqrtf(ss);
+    const bool usable = nrm != 0.f && isfinite(nrm);
+    const float inv = usable ? pre / nrm : 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = (usable && lane + 32 * j < d) ? v[j] * inv : 0.f;   // select: NaN * 0 would stay NaN
+    if (dst_bf16) {
+        const int nk = (int)(dst_ld / kTileCols);
+        float e2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < dst_ld) {
+                const __nv_bfloat16 b = __float2bfloat16_rn(v[j]);
+                const float e = __bfloat162float(b) - v[j];
+                e2 = fmaf(e, e, e2);
+                if (tiled_row0 < 0) dst_bf16[(size_t)row * (size_t)dst_ld + c] = __bfloat16_as_ushort(b);
+                else dst_bf16[tiled_offset(tiled_row0 + row, c, nk)] = __bfloat16_as_ushort(b);
+            }
+        }
+        if (margin_out && tiled_row0 < 0) {
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) e2 += __shfl_xor_sync(0xFFFFFFFFu, e2, o2);
+            if (lane == 0) margin_out[row] = query_margin(sqrtf(e2));
+        }
+    }
+    if (dst_f32) {
+        float* o = dst_f32 + (size_t)row * (size_t)f32_ld;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            if (lane + 32 * j < f32_ld) o[lane + 32 * j] = v[j];
+    }
+}
+
 int launch_normalize_rows(const float* src, long long n, int d, long long src_ld, uint16_t* dst_bf16, long long dst_ld,
                           long long tiled_row0, float* dst_f32, long long f32_ld, cudaStream_t stream,
                           float* margin_out, long long n_pad_rows, void* zero_base, size_t zero_bytes) {
@@ -91,9 +173,11 @@ int launch_normalize_rows(const float* src, long long n, int d, long long src_ld
     if (n_pad_rows <= 0 && zero_bytes == 0) return RVO_OK;
     long long blocks = (n_pad_rows + 7) / 8;
     if (blocks < 1) blocks = 1;
-    normalize_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, n, d, src_ld, dst_bf16, dst_ld, tiled_row0, dst_f32,
-                                                                f32_ld, margin_out, n_pad_rows, (uint4*)zero_base,
-                                                                (long long)(zero_bytes / 16));
+    // rows of up to 2048 (padded) elements stay in registers; both kernels give the same bits
+    const long long widest = dst_ld > f32_ld ? (dst_ld > d ? dst_ld : d) : (f32_ld > d ? f32_ld : d);
+    auto kern = widest > 2048 ? normalize_rows_kernel : widest <= 1024 ? normalize_rows_reg_kernel<32> : normalize_rows_reg_kernel<64>;
+    kern<<<(unsigned)blocks, 256, 0, stream>>>(src, n, d, src_ld, dst_bf16, dst_ld, tiled_row0, dst_f32, f32_ld, margin_out,
+                                               n_pad_rows, (uint4*)zero_base, (long long)(zero_bytes / 16));
     RVO_LAUNCHED();
     return RVO_OK;
 }

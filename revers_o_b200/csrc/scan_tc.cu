@@ -222,6 +222,15 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
                         uint32_t v[16];
                         tmem_ld_x16(taddr + (uint32_t)c * 16u, v);
                         tmem_ld_wait();
+                        if (p.dense_max) {   // warp-uniform: one maximum per (query, 32 sample rows)
+                            float f[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) f[i] = valid ? __uint_as_float(v[i]) : -__int_as_float(0x7f800000);
+                            const float m = warp_colmax16(f, lane);
+                            if ((lane & 1) == 0)
+                                p.dense[(size_t)(q0 + c * 16 + ((lane >> 1) & 15)) * (size_t)p.dense_ld + (size_t)(col >> 5)] = m;
+                            continue;
+                        }
                         {   // rows past the end of the DB (zero-filled by TMA) must never rank: -inf
                             float* o = p.dense + (size_t)(q0 + c * 16) * (size_t)p.dense_ld + (size_t)col;
 #pragma unroll
@@ -506,10 +515,11 @@ int launch_scan_tc(int mode, const uint16_t* db, long long n_rows, long long sup
     p.cap = cap;
     p.dense = dense;
     p.dense_ld = dense_ld;
+    p.dense_max = mode == kModeDenseMax;
 
     const long long total = p.num_super * pl.num_qblk;
     const int grid = (int)(total < sm_count ? total : sm_count);
-    if (mode == kModeDense) {
+    if (mode == kModeDense || mode == kModeDenseMax) {
         RVO_CUDA(cudaFuncSetAttribute(scan_tc_kernel<kModeDense>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));
         RVO_CUDA(launch_pdl(scan_tc_kernel<kModeDense>, dim3(grid), dim3(kScanThreads), pl.smem_bytes, stream, tm_db, tm_q, p));

@@ -25,6 +25,10 @@ constexpr int kCandSegs = kCandSplit + kHotSplit;         // sub-lists per query
 constexpr int kTauSmemBytes = 4 * 256 * 4;                // [2][256] tau + [2][256] tau_hot, double-buffered by work item
 constexpr int kModeDense = 0;
 constexpr int kModeFilter = 1;
+constexpr int kModeDenseMax = 2;   // launch-time variant of DENSE: only the maximum of every 32 consecutive sample rows is written
+                                   // (dense[q][sample / 32]) — all the seed threshold needs (select.cu seed_tau_kernel: the k-th
+                                   // largest of maxima over DISJOINT row groups is a lower bound of the k-th best score), 32x less
+                                   // output to write and to read back
 
 struct ScanParams {
     long long n_rows;        // DB rows
@@ -42,7 +46,35 @@ struct ScanParams {
     // DENSE
     float* dense;                  // [nq_pad][dense_ld]
     long long dense_ld;
+    int dense_max;                 // 1: kModeDenseMax
 };
+
+#ifdef __CUDACC__
+// Column maxima over the 32 rows of a warp.  Every lane holds 16 column values of its own row; after the butterfly (16 shuffles)
+// lane L holds, for column (L >> 1) & 15, the maximum over all 32 lanes (the two lanes of a pair hold the same value).
+__device__ __forceinline__ float warp_colmax16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float keep = h16 ? v[i + 8] : v[i], send = h16 ? v[i] : v[i + 8];
+        a[i] = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, send, 16));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = h8 ? a[i + 4] : a[i], send = h8 ? a[i] : a[i + 4];
+        b[i] = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, send, 8));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = h4 ? b[i + 2] : b[i], send = h4 ? b[i] : b[i + 2];
+        c[i] = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, send, 4));
+    }
+    const float keep = h2 ? c[1] : c[0], send = h2 ? c[0] : c[1];
+    const float d = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, send, 2));
+    return fmaxf(d, __shfl_xor_sync(0xFFFFFFFFu, d, 1));
+}
+#endif
 
 struct TcPlan {
     int nq_blk, num_qblk, nq_pad, m_sub, num_stages, resident, slot_w, num_slots;

@@ -175,6 +175,15 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
                     uint32_t v[16];
                     tmem_ld_x16(taddr + (uint32_t)c * 16u, v);
                     tmem_ld_wait();
+                    if (p.dense_max) {   // warp-uniform: one maximum per (query, 32 sample rows)
+                        float f[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] = valid ? __uint_as_float(v[i]) : -__int_as_float(0x7f800000);
+                        const float m = warp_colmax16(f, lane);
+                        if ((lane & 1) == 0)
+                            p.dense[(size_t)(q0 + c * 16 + ((lane >> 1) & 15)) * (size_t)p.dense_ld + (size_t)(col >> 5)] = m;
+                        continue;
+                    }
                     float* o = p.dense + (size_t)(q0 + c * 16) * (size_t)p.dense_ld + (size_t)col;
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
@@ -351,6 +360,7 @@ int launch_scan_tc2(int mode, const uint16_t* db, long long n_rows, long long su
     p.cap = cap;
     p.dense = dense;
     p.dense_ld = dense_ld;
+    p.dense_max = mode == kModeDenseMax;
 
     const long long total = p.num_super * pl.num_qblk;
     long long pairs = sm_count / 2;
@@ -370,7 +380,7 @@ int launch_scan_tc2(int mode, const uint16_t* db, long long n_rows, long long su
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl.load() ? 2 : 1;
-    if (mode == kModeDense) {
+    if (mode == kModeDense || mode == kModeDenseMax) {
         RVO_CUDA(cudaFuncSetAttribute(scan_tc2_kernel<kModeDense>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));
         RVO_CUDA(cudaLaunchKernelEx(&cfg, scan_tc2_kernel<kModeDense>, tm_db, tm_q, p));

@@ -32,6 +32,7 @@ from __future__ import annotations
 import json
 import os
 import threading
+import weakref
 from contextlib import contextmanager
 from dataclasses import dataclass
 from types import SimpleNamespace
@@ -370,7 +371,7 @@ class B200VectorDB:
             lanes = self._lanes(sh.device, nq, c.dim, k, depth)
             lane = lanes["ring"][lanes["next"] % depth]
             lanes["next"] += 1
-            if lane.busy is not None:
+            if lane.busy is not None and lane.busy() is not None:
                 raise RvoError(f"more than {depth} batches in flight on this thread: collect a result first")
             lane.stream.wait_stream(torch.cuda.current_stream(sh.device))   # rows upserted on the caller's stream are complete
             with torch.cuda.stream(lane.stream):
@@ -384,7 +385,7 @@ class B200VectorDB:
                 lane.res_host.copy_(lane.res_dev, non_blocking=True)
                 lane.done.record(lane.stream)
             h = SearchHandle(self, lock, lane, (sh.vectors, sh.n, c.dim, sh.row0, k, score_threshold), src)
-            lane.busy = h
+            lane.busy = weakref.ref(h)      # weak: a handle dropped without result() must still run its __del__
             return h
         except BaseException:
             lock.__exit__(None, None, None)
