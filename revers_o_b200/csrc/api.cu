@@ -23,7 +23,8 @@ int launch_selfjoin(const uint16_t* db, long long n_rows, int d, long long row_l
                     cudaStream_t stream);
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-std::atomic<long long> g_use_pdl{0};   // measured: no gain on configs[1] (0.487 vs 0.478 ms), 30 us WORSE on configs[0]
+std::atomic<long long> g_chain_trace{0};
+std::atomic<long long> g_use_pdl{0};   // see common.cuh launch_pdl
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -321,6 +322,7 @@ int rvo_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "pool_path")) g_force_cuda_core_pool = value == 1;
     else if (!strcmp(name, "pdl")) g_use_pdl = value;
     else if (!strcmp(name, "select_trace")) opt_select_trace = value;
+    else if (!strcmp(name, "chain_trace")) g_chain_trace = value;
     else if (!strcmp(name, "pool_trace")) g_pool_trace = (void*)(uintptr_t)value;
     else {
         set_error("unknown option '%s'", name);

@@ -43,11 +43,16 @@ extern std::atomic<long long> g_launches;
 int select_device_of(const void* dev_ptr, int* sm_count);
 
 // Launch with programmatic stream serialization (see ptx.cuh): the kernel must call grid_dependency_wait() before it
-// reads or writes global memory.
-extern std::atomic<long long> g_use_pdl;   // option "pdl": 1 = programmatic dependent launch along the chain; default 0 (measured slower)
+// reads or writes global memory a predecessor may touch.
+// option "pdl": 0 (default) off; 2 the tensor-path chain only — normalise -> seed scan -> seed threshold -> scan -> select overlap
+// their launch latencies and prologues; 1 also the Q <= 4 chain.  Measured with the in-stream timeline (scripts/dev/trace_chain.py)
+// and same-box bench runs: 96.3 -> 92.2 us per step on a 125k-row shard (the 8-GPU shard of configs[1]), but nothing at 1M rows,
+// where the board's power cap sets the period (serial 0.4669 -> 0.4648 ms, two batches in flight 0.4604 -> 0.4634), and 30 us
+// WORSE on the Q <= 4 chain — hence off by default.
+extern std::atomic<long long> g_use_pdl;
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                     Args... args) {
+static inline cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
@@ -58,9 +63,34 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_use_pdl.load() ? 1 : 0;
+    cfg.numAttrs = on ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+    return launch_pdl_if(g_use_pdl.load() != 0, kernel, grid, block, smem, stream, args...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_small(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                           Args... args) {
+    return launch_pdl_if(g_use_pdl.load() == 1, kernel, grid, block, smem, stream, args...);
+}
+
+// option "chain_trace": device buffer u64 [8][2] (earliest start, latest end of the CTAs of one kernel, %globaltimer ns) filled
+// by the kernels of the search chain: 0 normalise, 1 seed scan, 2 seed threshold, 3 FILTER scan(s), 4 select.  The caller initialises
+// it to (UINT64_MAX, 0) pairs (scripts/dev/trace_chain.py); nullptr (the default) costs one predicated branch per CTA.
+extern std::atomic<long long> g_chain_trace;
+#ifdef __CUDACC__
+__device__ __forceinline__ void chain_stamp(unsigned long long* tr, int id, bool end) {
+    if (tr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if (end) atomicMax(tr + 2 * id + 1, t);
+        else atomicMin(tr + 2 * id, t);
+    }
+}
+#endif
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -15,10 +15,15 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
                                                              long long dst_ld, long long tiled_row0,
                                                              float* __restrict__ dst_f32, long long f32_ld,
                                                              float* __restrict__ margin_out, long long n_pad_rows,
-                                                             uint4* __restrict__ zero_base, long long zero_u4) {
+                                                             uint4* __restrict__ zero_base, long long zero_u4,
+        unsigned long long* tr) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the seed scan may pre-launch (it waits for this grid)
+    chain_stamp(tr, 0, false);
+    // launched behind the previous search's select (option "pdl"): nothing below may be written before that grid has completed
+    // (it still reads the counters and margins this launch resets); the seed scan that follows may pre-launch in turn
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // scratch the search driver needs cleared (candidate counters): folded into this launch instead of a separate memset node
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < zero_u4; i += (long long)gridDim.x * blockDim.x)
         zero_base[i] = make_uint4(0, 0, 0, 0);
@@ -31,6 +36,7 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
                 for (long long i = lane; i < f32_ld; i += 32) dst_f32[(size_t)row * (size_t)f32_ld + i] = 0.f;
             if (margin_out && lane == 0) margin_out[row] = 0.f;
         }
+        chain_stamp(tr, 0, true);
         return;
     }
     const float* s = src + (size_t)row * (size_t)src_ld;
@@ -82,6 +88,7 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
         float* o = dst_f32 + (size_t)row * (size_t)f32_ld;
         for (long long i = lane; i < f32_ld; i += 32) o[i] = (usable && i < d) ? s[i] * inv : 0.f;
     }
+    chain_stamp(tr, 0, true);
 }
 
 // Register-resident variant for d_pad <= 32 * NV: the row is read ONCE — NV independent loads per lane, all in flight together —
@@ -95,17 +102,22 @@ __global__ void __launch_bounds__(256) normalize_rows_reg_kernel(const float* __
                                                                  long long dst_ld, long long tiled_row0,
                                                                  float* __restrict__ dst_f32, long long f32_ld,
                                                                  float* __restrict__ margin_out, long long n_pad_rows,
-                                                                 uint4* __restrict__ zero_base, long long zero_u4) {
+                                                                 uint4* __restrict__ zero_base, long long zero_u4,
+        unsigned long long* tr) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    chain_stamp(tr, 0, false);
     float v[NV];
     const bool live = row < n;
-    if (live) {
+    if (live) {   // the source rows are never written by a kernel of the chain: they may be read before the dependency wait
         const float* s = src + (size_t)row * (size_t)src_ld;
 #pragma unroll
         for (int j = 0; j < NV; ++j) v[j] = lane + 32 * j < d ? __ldg(s + lane + 32 * j) : 0.f;
     }
+    // launched behind the previous search's select (option "pdl"): no write before that grid has completed (it still reads the
+    // counters and margins this launch resets); the seed scan that follows may pre-launch in turn
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < zero_u4; i += (long long)gridDim.x * blockDim.x)
         zero_base[i] = make_uint4(0, 0, 0, 0);
     if (!live) {
@@ -116,6 +128,7 @@ __global__ void __launch_bounds__(256) normalize_rows_reg_kernel(const float* __
                 for (long long i = lane; i < f32_ld; i += 32) dst_f32[(size_t)row * (size_t)f32_ld + i] = 0.f;
             if (margin_out && lane == 0) margin_out[row] = 0.f;
         }
+        chain_stamp(tr, 0, true);
         return;
     }
     float amax = 0.f;
@@ -164,6 +177,7 @@ __global__ void __launch_bounds__(256) normalize_rows_reg_kernel(const float* __
         for (int j = 0; j < NV; ++j)
             if (lane + 32 * j < f32_ld) o[lane + 32 * j] = v[j];
     }
+    chain_stamp(tr, 0, true);
 }
 
 int launch_normalize_rows(const float* src, long long n, int d, long long src_ld, uint16_t* dst_bf16, long long dst_ld,
@@ -176,8 +190,9 @@ int launch_normalize_rows(const float* src, long long n, int d, long long src_ld
     // rows of up to 2048 (padded) elements stay in registers; both kernels give the same bits
     const long long widest = dst_ld > f32_ld ? (dst_ld > d ? dst_ld : d) : (f32_ld > d ? f32_ld : d);
     auto kern = widest > 2048 ? normalize_rows_kernel : widest <= 1024 ? normalize_rows_reg_kernel<32> : normalize_rows_reg_kernel<64>;
-    kern<<<(unsigned)blocks, 256, 0, stream>>>(src, n, d, src_ld, dst_bf16, dst_ld, tiled_row0, dst_f32, f32_ld, margin_out,
-                                               n_pad_rows, (uint4*)zero_base, (long long)(zero_bytes / 16));
+    RVO_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(256), 0, stream, src, n, d, src_ld, dst_bf16, dst_ld, tiled_row0, dst_f32,
+                        f32_ld, margin_out, n_pad_rows, (uint4*)zero_base, (long long)(zero_bytes / 16),
+                        (unsigned long long*)(uintptr_t)g_chain_trace.load()));
     RVO_LAUNCHED();
     return RVO_OK;
 }
@@ -352,7 +367,7 @@ static int launch_small_t(const SmallScanArgs& a, bool dense, bool norm, int sm_
         if (per_sm < 1) per_sm = 1;                                                                                  \
         long long grid = (long long)sm_count * per_sm;                                                               \
         if (grid > want) grid = want;                                                                                \
-        RVO_CUDA(launch_pdl(scan_small_kernel<NQ, CPL, D_, N_>, dim3((unsigned)grid), dim3(256), 0, stream, a));     \
+        RVO_CUDA(launch_pdl_small(scan_small_kernel<NQ, CPL, D_, N_>, dim3((unsigned)grid), dim3(256), 0, stream, a)); \
     } while (0)
     if (dense && norm) RVO_SMALL_LAUNCH(true, true);
     else if (dense) RVO_SMALL_LAUNCH(true, false);

@@ -56,6 +56,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
     const uint32_t q_chunk_bytes = (uint32_t)nq_blk * 128u;
     const long long total_work = p.num_super * (long long)p.num_qblk;
 
+    chain_stamp(p.trace, MODE == kModeDense ? 1 : 3, false);
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) {
             printf("rvo: dynamic shared memory base not 1024-byte aligned\n");
@@ -348,6 +349,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+    chain_stamp(p.trace, MODE == kModeDense ? 1 : 3, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -516,6 +518,7 @@ int launch_scan_tc(int mode, const uint16_t* db, long long n_rows, long long sup
     p.dense = dense;
     p.dense_ld = dense_ld;
     p.dense_max = mode == kModeDenseMax;
+    p.trace = (unsigned long long*)(uintptr_t)g_chain_trace.load();
 
     const long long total = p.num_super * pl.num_qblk;
     const int grid = (int)(total < sm_count ? total : sm_count);

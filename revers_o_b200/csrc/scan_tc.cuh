@@ -47,6 +47,7 @@ struct ScanParams {
     float* dense;                  // [nq_pad][dense_ld]
     long long dense_ld;
     int dense_max;                 // 1: kModeDenseMax
+    unsigned long long* trace;     // option "chain_trace" (common.cuh) or nullptr
 };
 
 #ifdef __CUDACC__

@@ -49,6 +49,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
     const long long total_work = p.num_super * (long long)p.num_qblk;
     constexpr int kPairRows = 2 * kBlockM;
 
+    chain_stamp(p.trace, MODE == kModeDense ? 1 : 3, false);
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
         for (int i = 0; i < kMaxStages; ++i) {
@@ -292,6 +293,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_db, const __grid_consta
     tc_fence_before();
     cluster_sync_all();   // the peer may still be reading this CTA's smem / arriving on its barriers
     if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+    chain_stamp(p.trace, MODE == kModeDense ? 1 : 3, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -361,6 +363,7 @@ int launch_scan_tc2(int mode, const uint16_t* db, long long n_rows, long long su
     p.dense = dense;
     p.dense_ld = dense_ld;
     p.dense_max = mode == kModeDenseMax;
+    p.trace = (unsigned long long*)(uintptr_t)g_chain_trace.load();
 
     const long long total = p.num_super * pl.num_qblk;
     long long pairs = sm_count / 2;

@@ -1088,11 +1088,11 @@ int launch_dense_topk(const DenseTopkArgs& a, const FinalArgs* f, int nq, cudaSt
     else memset(&ff, 0, sizeof(ff));
     const bool cached = a.n_cols <= (long long)kDenseCache * kDenseThreads;
     if (f) {
-        if (cached) RVO_CUDA(launch_pdl(dense_topk_kernel<true, true>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
-        else RVO_CUDA(launch_pdl(dense_topk_kernel<false, true>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
+        if (cached) RVO_CUDA(launch_pdl_small(dense_topk_kernel<true, true>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
+        else RVO_CUDA(launch_pdl_small(dense_topk_kernel<false, true>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
     } else {
-        if (cached) RVO_CUDA(launch_pdl(dense_topk_kernel<true, false>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
-        else RVO_CUDA(launch_pdl(dense_topk_kernel<false, false>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
+        if (cached) RVO_CUDA(launch_pdl_small(dense_topk_kernel<true, false>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
+        else RVO_CUDA(launch_pdl_small(dense_topk_kernel<false, false>, dim3(nq), dim3(kDenseThreads), 0, stream, a, ff));
     }
     RVO_LAUNCHED();
     return RVO_OK;
@@ -1101,11 +1101,13 @@ int launch_dense_topk(const DenseTopkArgs& a, const FinalArgs* f, int nq, cudaSt
 // ---- seed threshold from per-thread maxima (see select.cuh) ----------------------------------------------------------
 __global__ void __launch_bounds__(512) seed_tau_kernel(const float* __restrict__ dense, long long dense_ld, long long n_dense,
                                                        int nq, int k, const float* __restrict__ margin, float score_floor,
-                                                       float* __restrict__ tau_out, int hot_rank, float* __restrict__ tau_hot_out) {
+                                                       float* __restrict__ tau_out, int hot_rank, float* __restrict__ tau_hot_out,
+                                                       unsigned long long* tr) {
     __shared__ uint32_t s[512];
     const int q = blockIdx.x, t = threadIdx.x;
     grid_dependency_wait();
     grid_launch_dependents();
+    chain_stamp(tr, 2, false);
     if (q >= nq) {  // padded query rows of the tensor path never admit anything
         if (t == 0) {
             tau_out[q] = __int_as_float(0x7f800000);
@@ -1162,13 +1164,14 @@ __global__ void __launch_bounds__(512) seed_tau_kernel(const float* __restrict__
             tau_hot_out[q] = rth > tau ? rth : tau;
         }
     }
+    chain_stamp(tr, 2, true);
 }
 
 int launch_seed_tau(const float* dense, long long dense_ld, long long n_dense, int nq, int grid_q, int k, const float* margin,
                     float score_floor, float* tau_out, cudaStream_t stream, int hot_rank, float* tau_hot_out) {
     if (grid_q <= 0) return RVO_OK;
     RVO_CUDA(launch_pdl(seed_tau_kernel, dim3(grid_q), dim3(512), 0, stream, dense, dense_ld, n_dense, nq, k, margin, score_floor,
-                        tau_out, hot_rank, tau_hot_out));
+                        tau_out, hot_rank, tau_hot_out, (unsigned long long*)(uintptr_t)g_chain_trace.load()));
     RVO_LAUNCHED();
     return RVO_OK;
 }
