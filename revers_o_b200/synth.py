@@ -45,7 +45,7 @@ def make_db(n: int, d: int, queries: torch.Tensor | None = None, n_plant: int = 
         del x
         tiled[lo // 128: lo // 128 + nb_c].copy_(pad.view(nb_c, 128, nk, 64).permute(0, 2, 1, 3))
         del pad
-    if queries is not None and n_plant > 0 and n > 0:
+    if queries is not None and n_plant > 0 and n >= queries.shape[0]:   # fewer rows than queries: nothing to plant
         nq = queries.shape[0]
         qn = (queries.float() / queries.float().norm(dim=1, keepdim=True)).to(dev)
         gp = torch.Generator(device="cpu").manual_seed(seed + 1)

@@ -1,0 +1,21 @@
+"""Differential fuzz of K2 on the GPU (scripts/dev/fuzz_search.py): random shapes, thresholds, tie structures, adjacent near-copies
+and forced paths (fp32 scan, tensor, dense) against an fp32 restatement, scores to 1e-5 and id sets equal except among such ties."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("seed", [3, 11])
+def test_fuzz_search_against_fp32_restatement(seed):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dev", "fuzz_search.py"), "150", str(seed)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "150 cases, 0 mismatches" in r.stdout
