@@ -19,3 +19,15 @@ def test_fuzz_search_against_fp32_restatement(seed):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "150 cases, 0 mismatches" in r.stdout
+
+
+@pytest.mark.parametrize("seed", [5])
+def test_fuzz_mask_pool_against_fp32_restatement(seed):
+    """K1 with and without the fused ingest (scripts/dev/fuzz_maskpool.py): widths on and off the tensor path, bf16 / fp16, class
+    token, region caps, empty regions and images, any non-zero mask byte — counts, source indices and rows to 2e-5."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dev", "fuzz_maskpool.py"), "150", str(seed)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "150 cases, 0 mismatches" in r.stdout
