@@ -251,6 +251,14 @@ class PayloadStore:
             if r >= self.n:
                 self.n = r + 1
 
+    def mark_all_dirty(self, n: int) -> None:
+        """Bring the payloads of rows [0, n) into RAM and mark them unwritten: the next flush appends a fresh record for each
+        (used once when a collection's ids stop fitting a typed column and move into the log records)."""
+        for r in range(min(n, self.n)):
+            if r not in self._ram:
+                self._ram[r] = self[r]
+        self.dirty_rows.extend(range(min(n, self.n)))
+
     def truncate(self, n: int) -> None:
         if n >= self.n:
             return

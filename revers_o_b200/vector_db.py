@@ -812,6 +812,12 @@ class B200VectorDB:
                     fh.seek(st["ids_bytes"])
                     fh.write(arr[st["n"]:].tobytes())
             st["ids_dtype"], st["ids_bytes"] = dt, arr.nbytes
+        elif dt is None and st["ids_dtype"] is not None:
+            # the ids stopped fitting a typed column (an int id joined uuid strings, or the other way round): from now on they
+            # live in the log records, so every row persisted so far gets a fresh record carrying its id, and the stale column
+            # is no longer vouched for
+            c.payloads.mark_all_dirty(st["n"])
+            st["ids_dtype"], st["ids_bytes"] = None, 0
         st["log_bytes"], st["idx_bytes"] = c.payloads.flush(f["log"], f["idx"], st["log_bytes"], st["idx_bytes"], ids=c.ids)
         st["n"] = n
         self._write_meta(path, c, st)
@@ -900,6 +906,8 @@ class B200VectorDB:
                 else:
                     if m.get("ids_dtype"):
                         arr = np.fromfile(files["ids"], dtype=np.dtype(m["ids_dtype"]), count=n)
+                        if len(arr) != n:
+                            raise RvoError(f"{files['ids']}: {len(arr)} ids on disk, meta.json says {n}")
                         c.ids = IdTable.from_array(arr)
                     c.payloads = PayloadStore.open(files["log"], files["idx"], n, int(m.get("idx_bytes", 0)))
                     if not m.get("ids_dtype") and n:      # object ids live in the log

@@ -31,3 +31,17 @@ def test_fuzz_mask_pool_against_fp32_restatement(seed):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "150 cases, 0 mismatches" in r.stdout
+
+
+@pytest.mark.parametrize("seed,shards", [(1, 1), (2, 3)])
+def test_fuzz_vector_db_against_numpy_model(seed, shards):
+    """Model-based fuzz of the drop-in boundary (scripts/dev/fuzz_vector_db.py): random upserts (new ids, overwrites, duplicates
+    inside a batch, int / uuid ids and the switch between them), bulk ingest, searches, collection re-creation and close + reopen
+    from disk, checked against a numpy model after every step; `shards` = 3 runs the row-sharded collection code (on one GPU the
+    three shards share the device)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dev", "fuzz_vector_db.py"), "300", str(seed), str(shards)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "300 steps, 0 mismatches" in r.stdout

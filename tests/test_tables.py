@@ -69,3 +69,29 @@ def test_payload_store_log_is_append_only_and_lazy(tmp_path):
     # the state meta.json vouched for BEFORE the second flush is still readable (crash between flush and meta replace)
     old = PayloadStore.open(log, idx, 3, ib)
     assert [old[i] for i in range(3)] == [{"a": 1}, None, {"b": [1, 2]}]
+
+
+def test_payload_store_mark_all_dirty_rewrites_records_with_ids(tmp_path):
+    """A collection whose ids stop fitting a typed column (an int id joins uuid strings) moves its ids into the log records:
+    every row persisted so far must get a fresh record that carries its id, payloads read back from the old log."""
+    log, idx = str(tmp_path / "c.jsonl"), str(tmp_path / "c.idx")
+    ids = IdTable()
+    ids.append(["a", "b", "c"])
+    s = PayloadStore()
+    s.append_or_set(np.arange(3), [{"i": 0}, None, {"i": 2}])
+    lb, ib = s.flush(log, idx, 0, 0, ids=ids, drop_ram=True)          # typed ids: records carry no id
+    assert b'"id"' not in open(log, "rb").read()
+    s2 = PayloadStore.open(log, idx, 3, ib)
+    ids.append([7])                                                    # mixed types -> object kind
+    assert ids.kind == IdTable.KIND_OBJ
+    s2.append_or_set(np.array([3]), [{"i": 3}])
+    s2.mark_all_dirty(3)
+    lb2, ib2 = s2.flush(log, idx, lb, ib, ids=ids)
+    s3 = PayloadStore.open(log, idx, 4, ib2)
+    assert [s3[r] for r in range(4)] == [{"i": 0}, None, {"i": 2}, {"i": 3}]
+    import json
+    byrow = {}
+    for line in open(log, "rb").read()[:lb2].splitlines():
+        rec = json.loads(line)
+        byrow[rec["row"]] = rec.get("id")
+    assert [byrow[r] for r in range(4)] == ["a", "b", "c", 7]
