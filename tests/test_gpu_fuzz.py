@@ -45,3 +45,15 @@ def test_fuzz_vector_db_against_numpy_model(seed, shards):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "300 steps, 0 mismatches" in r.stdout
+
+
+def test_fuzz_selfjoin_against_bruteforce():
+    """configs[4] path (scripts/dev/fuzz_selfjoin.py): sizes around the 4096-row query block, thresholds, planted near-copies,
+    static-scene cliques, row ranges, id offsets, and small candidate / output capacities that force the exact fallbacks —
+    every pair with cos >= threshold (fp32, 1e-4 band at the threshold) exactly once, i < j, scores to 1e-4."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dev", "fuzz_selfjoin.py"), "60", "2"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "60 cases, 0 mismatches" in r.stdout
