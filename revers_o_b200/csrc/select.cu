@@ -1308,7 +1308,7 @@ int launch_merge(const int64_t* ids, const float* scores, const int32_t* counts,
         return RVO_E_INVALID;
     }
     const size_t smem = (size_t)G * k * 12;
-    if (smem > 48 * 1024)
+    if (smem > 47 * 1024)   // the 48 KB default covers dynamic + static shared memory (the kernel has ~300 B of the latter)
         RVO_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_kernel<<<nq, 256, smem, stream>>>(ids, scores, counts, ids_gs, scores_gs, counts_gs, G, k, out_ids, out_scores,
                                             out_counts, wait_flags, wait_epoch,

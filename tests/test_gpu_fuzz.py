@@ -57,3 +57,14 @@ def test_fuzz_selfjoin_against_bruteforce():
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "60 cases, 0 mismatches" in r.stdout
+
+
+def test_fuzz_merge_against_numpy():
+    """K3 (scripts/dev/fuzz_merge.py): up to 64 lists, short / empty lists, cross-shard score ties (lower id first), G * k at
+    the 4096 limit (48 KB of dynamic shared memory), a shard's overflow flag must survive the merge — bit-exact."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dev", "fuzz_merge.py"), "100", "4"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "100 cases, 0 mismatches" in r.stdout
