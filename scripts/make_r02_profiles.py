@@ -84,21 +84,25 @@ write("r02_cfg1_step.md", [
     "## Launch list of one timed step (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)", "",
     *ll, "",
     "Round 1 (profiles/r01_cfg1_step_final.md): memset + normalise 6.6 + seed scan 15.1 + seed threshold 30.2 (9 with the maxima kernel) + scan 367.1 + "
-    "select 48.3 = 467 us.  Now: the memset is folded into the normalise launch, the last-level select reads only the HOT sub-lists "
-    "(the ~600 best survivors per query instead of ~6100), re-scores one row per warp and ranks by counting.", "",
+    "select 48.3 = 467 us.  Now: the memset is folded into the (register-resident) normalise launch, the seed scan writes one maximum per 32 sample "
+    "rows instead of every score, the last-level select reads only the HOT sub-lists (the ~600 best survivors per query instead of ~6100), "
+    "re-scores one row per warp and ranks by counting.  The same chain as it runs IN THE STREAM, with the gaps between launches: "
+    "profiles/r02_chain_timeline.md.", "",
     "## `ncu --set full` of the chain kernels (select_kernel<1> twice, normalise, seed_tau)", "", *chain, "",
-    "## `ncu --set full` of the scan kernels (full-shard FILTER launch, then the DENSE seed launch)", "", *scan, "",
+    "## `ncu --set full` of the two scan launches of one step (DENSE seed sample and full-shard FILTER, in capture order)", "", *scan, "",
     f"DRAM traffic of the full-shard scan: {traffic['cfg1'] / 1e9:.4f} GB for 2.048 GB algorithmic (x{traffic['cfg1'] / 2.048e9:.3f}).", "",
     "## bench.py line of the plain (un-profiled) run of the same command", "", "```json", json.dumps({k: b[k] for k in ("value", "ms_per_step", "e2e", "gpu_launches", "roofline", "verify", "results_ok")}), "```", "",
     "## Reading",
-    "* The scan is unchanged in substance (same DRAM bytes, tensor pipe ~93 % active): a same-box A/B against the round-1 build under ncu gave "
-    "388.5 vs 388.8 us.  An intermediate version that chose the hot/safe sub-list INSIDE the compare loop cost 18 % of the scan in the real "
-    "stream (0.438 vs 0.372 ms, same box, alternating runs) although ncu's isolated replays showed no difference; the choice now happens when "
-    "a survivor's queue entry is read back.",
+    "* The scan is unchanged in substance since round 1 (same DRAM bytes, tensor pipe ~93 % active).  Isolated under ncu it takes ~388 us on "
+    "every box; in the stream it takes 355 us right after an idle period and 381-401 us from the second back-to-back step on, depending on the "
+    "box: the board's power cap (profiles/r02_chain_timeline.md), the same effect that separates cuBLAS's burst (1638 TF/s) and sustained "
+    "(1410 TF/s) bf16 figures in MEASURED_PEAKS.json.  537 GFLOP / 0.382 ms = 1405 TF/s.",
     "* select_kernel<1>: 48 -> 23 us.  55 MB of its DRAM reads are the fp32 re-score gathers (256 queries x ~101 rows x 2 KB): at ~8 us for that "
     "phase it runs at HBM speed, so the kernel is within ~2x of its floor.",
-    "* Same-box, alternating runs of the round-1 build and this one (20 steps each): 0.4747 -> 0.4585 ms/step resident, 0.523-0.544 -> 0.499-0.518 "
-    "e2e (blocking), 0.49 e2e pipelined (two batches in flight).",
+    "* seed level: DENSE seed scan 16.3 -> ~13 us and seed threshold 9.9 -> ~5 us under ncu (one maximum per 32 sample rows: 0.5 MB instead of "
+    "17 MB written and read back); normalise 8.5 -> ~4 us (row kept in registers).",
+    "* Same-box, alternating runs: round-1 build 0.4747 -> 0.4585 ms/step (hot lists), then 0.4621 -> 0.4577 serial on another box (seed maxima + "
+    "normalise).",
 ])
 
 # ---- configs[0] ---------------------------------------------------------------------------------------------------------
