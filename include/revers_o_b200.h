@@ -296,7 +296,12 @@ float rvo_last_scan_ms(void);
  *         "cand_cap" (candidates per query, default 32768), "final_ratio" (default 48),
  *         "time_scan" (0/1, see rvo_last_scan_ms), "pool_path" (0 auto: tensor-core mask pooling when the
  *         shape fits TMEM, 1: CUDA-core kernels), "hot" (1 default: hot candidate sub-lists + one-pass final select,
- *         0: general select only), "exchange_timeout_ms" (peer-exchange wait limit, default 60000)            */
+ *         0: general select only), "exchange_timeout_ms" (peer-exchange wait limit, default 60000),
+ *         "seed_max" (1 default: the seed scan writes one maximum per 32 sample rows; 0: every score),
+ *         "pdl" (programmatic dependent launch along the search chain: 0 default off, 2 tensor-path chain, 1 also the Q <= 4 chain),
+ *         debugging (value = a device pointer the caller owns, 0 = off): "chain_trace" (u64 [8][2]: earliest start / latest end
+ *         of normalise, seed scan, seed threshold, scan, select on %globaltimer; initialise to (UINT64_MAX, 0) pairs),
+ *         "select_trace" (u64 [nq][16] phase stamps of the last-level select), "merge_trace" (u64 [3]), "pool_trace".        */
 int rvo_set_option(const char* name, int64_t value);
 
 #ifdef __cplusplus
