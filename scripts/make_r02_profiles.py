@@ -96,7 +96,7 @@ write("r02_cfg1_step.md", [
     "* The scan is unchanged in substance since round 1 (same DRAM bytes, tensor pipe ~93 % active).  Isolated under ncu it takes ~388 us on "
     "every box; in the stream it takes 355 us right after an idle period and 381-401 us from the second back-to-back step on, depending on the "
     "box: the board's power cap (profiles/r02_chain_timeline.md), the same effect that separates cuBLAS's burst (1638 TF/s) and sustained "
-    "(1410 TF/s) bf16 figures in MEASURED_PEAKS.json.  537 GFLOP / 0.382 ms = 1405 TF/s.",
+    "(1410 TF/s) bf16 figures in MEASURED_PEAKS.json.  524 GFLOP / 0.382 ms = 1372 TF/s (0.97 of sustained).",
     "* select_kernel<1>: 48 -> 23 us.  55 MB of its DRAM reads are the fp32 re-score gathers (256 queries x ~101 rows x 2 KB): at ~8 us for that "
     "phase it runs at HBM speed, so the kernel is within ~2x of its floor.",
     "* seed level: DENSE seed scan 16.3 -> ~13 us and seed threshold 9.9 -> ~5 us under ncu (one maximum per 32 sample rows: 0.5 MB instead of "
