@@ -95,3 +95,93 @@ def test_payload_store_mark_all_dirty_rewrites_records_with_ids(tmp_path):
         rec = json.loads(line)
         byrow[rec["row"]] = rec.get("id")
     assert [byrow[r] for r in range(4)] == ["a", "b", "c", 7]
+
+
+def test_id_table_random_operations_against_a_dict_model():
+    """Random appends (new, known, duplicates inside a batch, assume_new bulk), lookups, roll-backs and array round trips for
+    string-only, int-only and mixed collections, against a plain dict + list model."""
+    for seed, flavour in enumerate(["str", "int", "mixed", "str", "int"]):
+        rs = np.random.RandomState(seed)
+        t, order, row = IdTable(), [], {}
+
+        def fresh():
+            if flavour == "str" or (flavour == "mixed" and rs.rand() < 0.5):
+                return str(uuid.UUID(int=int(rs.randint(1 << 62)))) if rs.rand() < 0.8 else "id-" + "x" * int(rs.randint(1, 60))
+            return int(rs.randint(-(1 << 40), 1 << 40))
+
+        for step in range(300):
+            op = rs.choice(["append", "bulk", "lookup", "truncate", "reload"], p=[0.45, 0.1, 0.3, 0.05, 0.1])
+            if op == "append":
+                ids = [order[rs.randint(len(order))] if order and rs.rand() < 0.3 else fresh() for _ in range(int(rs.randint(1, 30)))]
+                if len(ids) > 2 and rs.rand() < 0.3:
+                    ids.append(ids[0])
+                got = t.append(ids)
+                for i, r in zip(ids, got.tolist()):
+                    if i not in row:
+                        row[i] = len(order)
+                        order.append(i)
+                    assert row[i] == r, (flavour, step, i, r, row[i])
+            elif op == "bulk":
+                ids = []
+                while len(ids) < 200:
+                    i = fresh()
+                    if i not in row and i not in ids:
+                        ids.append(i)
+                got = t.append(ids, assume_new=True)
+                assert got.tolist() == list(range(len(order), len(order) + len(ids)))
+                for i in ids:
+                    row[i] = len(order)
+                    order.append(i)
+            elif op == "lookup":
+                ids = [order[rs.randint(len(order))] if order and rs.rand() < 0.6 else fresh() for _ in range(20)]
+                assert t.lookup(ids).tolist() == [row.get(i, -1) for i in ids], (flavour, step)
+            elif op == "truncate" and order:
+                n = int(rs.randint(0, len(order) + 1))
+                t.truncate(n)
+                for i in order[n:]:
+                    del row[i]
+                del order[n:]
+            elif op == "reload" and order and t.disk_dtype() is not None:   # typed columns round-trip through their array
+                t = IdTable.from_array(np.frombuffer(t.array().tobytes(), dtype=np.dtype(t.disk_dtype())).copy())
+            assert len(t) == len(order)
+            if order:
+                j = int(rs.randint(len(order)))
+                assert t[j] == order[j]
+        assert list(t) == order
+
+
+def test_payload_store_random_operations_against_a_dict_model(tmp_path):
+    """Random writes / overwrites, write-through flushes, reopen from the log and roll-backs against a dict."""
+    for seed in range(3):
+        rs = np.random.RandomState(seed)
+        log, idx = str(tmp_path / f"p{seed}.jsonl"), str(tmp_path / f"p{seed}.idx")
+        s, model, lb, ib, persisted_n = PayloadStore(), [], 0, 0, 0
+        for step in range(200):
+            op = rs.choice(["write", "flush", "reopen", "truncate", "read"], p=[0.4, 0.2, 0.1, 0.05, 0.25])
+            if op == "write":
+                rows, pays = [], []
+                for _ in range(int(rs.randint(1, 20))):
+                    r = int(rs.randint(len(model))) if model and rs.rand() < 0.3 else len(model)
+                    p = None if rs.rand() < 0.2 else {"step": step, "v": rs.randint(0, 9, 3).tolist(), "s": "é" * int(rs.randint(0, 4))}
+                    if r == len(model):
+                        model.append(p)
+                    else:
+                        model[r] = p
+                    rows.append(r)
+                    pays.append(p)
+                s.append_or_set(np.asarray(rows), pays)
+            elif op == "flush":
+                lb, ib = s.flush(log, idx, lb, ib, drop_ram=bool(rs.rand() < 0.5))
+                persisted_n = len(model)
+            elif op == "reopen" and persisted_n == len(model) and not s.dirty_rows:
+                s.close()
+                s = PayloadStore.open(log, idx, len(model), ib)
+            elif op == "truncate" and len(model) > persisted_n:
+                n = int(rs.randint(persisted_n, len(model) + 1))      # a failed upsert rolls back rows that were never persisted
+                s.truncate(n)
+                del model[n:]
+            assert len(s) == len(model)
+            if model:
+                j = int(rs.randint(len(model)))
+                assert s[j] == model[j], (seed, step, j)
+        s.close()
