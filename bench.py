@@ -278,14 +278,26 @@ def run_b200(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)) / steps, _lib.kernel_launch_count() - l0, out
 
-    def scan_rooflines(idx, q, kk, ms_step, reps):
+    def scan_rooflines(idx, q, kk, ms_step, reps, after_idle=False):
         """The dominant kernel (full-shard scan) timed alone with CUDA events recorded by the library around that one
-        launch on its stream; algorithmic bytes = n_local*d*2 (DB read once), flops = 2*Q*n_local*d."""
+        launch on its stream; algorithmic bytes = n_local*d*2 (DB read once), flops = 2*Q*n_local*d.
+        `kernel_ms` is taken in back-to-back steps (the regime `value` is measured in; for sub-millisecond tensor-heavy steps
+        that is the board's power-capped regime).  `after_idle` adds the same launch timed after a 10-step burst and 20 ms of idle GPU — the
+        kernel by itself at full clocks, comparable with the BURST peaks of MEASURED_PEAKS.json."""
         _lib.set_option("time_scan", 1)
         scan_ms = []
         for _ in range(reps):
             idx.search_local(q, kk)
             scan_ms.append(float(lib.rvo_last_scan_ms()))
+        idle_ms = []
+        if after_idle:
+            for _ in range(7):
+                for _ in range(10):          # a burst first: the GPU holds full clocks only after sustained load ...
+                    idx.search_local(q, kk)
+                torch.cuda.synchronize()
+                time.sleep(0.02)             # ... then 20 ms for the power limiter to relax (0.3-3 ms would catch the clock ramp instead:
+                idx.search_local(q, kk)      # scripts/dev/scan_after_idle.py, profiles/r02_chain_timeline.md)
+                idle_ms.append(float(lib.rvo_last_scan_ms()))
         _lib.set_option("time_scan", 0)
         torch.cuda.synchronize()
         scan_fastest = min_over_ranks(statistics.mean(scan_ms))     # the spread between the GPUs of one box under simultaneous load
@@ -301,6 +313,11 @@ def run_b200(args):
                "kernel": "scan_small_kernel (fp32, every row)" if small_ else "scan_tc2_kernel<FILTER> / scan_tc_kernel<FILTER> (full-shard level)",
                "kernel_ms": scan_avg, "kernel_ms_fastest_rank": scan_fastest, "algorithmic_bytes": alg_bytes,
                "share_of_step": scan_avg / ms_step}
+        if idle_ms:
+            alone = max_over_ranks(statistics.median(idle_ms))
+            hbm["after_idle"] = {"kernel_ms": alone, "achieved": alg_bytes / (alone * 1e-3) / 1e9, "frac": alg_bytes / (alone * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                 "tflops": alg_flops / (alone * 1e-3) / 1e12, "frac_of_burst_bf16": alg_flops / (alone * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                                 "what": "the same launch after a 10-step burst + 20 ms of idle GPU (median of 7): the kernel by itself at full clocks, before the board's power limiter engages"}
         tensor = None if small_ else {
             "bound": "tensor", "achieved": tf_ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": tf_ach / peaks["bf16_tflops"], "peak_kind": peaks_kind + " burst (kernel timed alone)",
@@ -420,7 +437,7 @@ def run_b200(args):
         local_ms, _, _ = timed(lambda: index.search_local(q_dev, k), args.steps, 3)
 
     # ---- roofline: the dominant kernel (full-shard scan) ------------------------------------------------
-    roofline, roofline_tensor = scan_rooflines(index, q_dev, k, ms_step, max(5, min(args.steps, 30)))
+    roofline, roofline_tensor = scan_rooflines(index, q_dev, k, ms_step, max(5, min(args.steps, 30)), after_idle=n_local * d * 2 < 8e9)
     small = nq <= _lib.RVO_SMALL_Q
     alg_bytes = n_local * d * 2
     roofline["traffic"] = traffic.get(args.workload)
